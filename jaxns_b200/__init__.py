@@ -1,0 +1,13 @@
+"""
+jaxns_b200: B200-native drop-in for the static nested-sampling hot path of Joshuaalbert/jaxns 2.6.9.
+Same user-facing names as `jaxns` (/root/reference/src/jaxns/__init__.py:3-7) for the path in scope.
+"""
+from jaxns_b200 import distributions, likelihoods, random  # noqa: F401
+from jaxns_b200.framework import Model, Prior  # noqa: F401
+from jaxns_b200.nested_sampler import ShardedStaticNestedSampler  # noqa: F401
+from jaxns_b200.public import DefaultNestedSampler, NestedSampler  # noqa: F401
+from jaxns_b200.samplers import UniDimSliceSampler, UniformSampler  # noqa: F401
+from jaxns_b200.types import (NestedSamplerResults, NestedSamplerState, TerminationCondition)  # noqa: F401
+from jaxns_b200.utils import summary  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,331 @@
+// Engine-side kernels of the static nested-sampling loop: per-iteration key chain and bookkeeping,
+// dead-store appends, rank-merge of the replaced shell, register update and termination decision.
+//
+// Reference: _main_ns_thread / _collect_shell / _add_samples_to_state
+// (/root/reference/src/jaxns/nested_samplers/sharded/sharded_static.py:40-85, :210-324, :427-574),
+// determine_termination (nested_samplers/common/termination.py:13-147),
+// linear_to_log_stats / effective_sample_size_kish (internals/stats.py:55-86),
+// replace_index = clamped dynamic_update_slice (internals/maps.py:15-25).
+#pragma once
+#include "ns_stats.cuh"
+
+namespace nsb {
+
+// Device-resident loop control (one instance per engine).
+struct DevCtl {
+    Key key;               // NestedSamplerState.key
+    long long next_idx;    // next_sample_idx
+    long long num_samples; // num_samples
+    long long iteration;
+    // derived per iteration by k_iter_prologue
+    Key sample_key;
+    double contour;
+    long long disc_start;  // clamped write offset of the discarded shell
+    long long ph_start;    // clamped write offset of the phantom rows
+    long long sender;      // sender_node_idx of the replacements
+    int active;            // 0 once the register says done: every step kernel becomes a no-op
+    int cur;               // which of the two live buffers is current
+};
+
+struct LiveSet {
+    long long *sender;
+    double *U;
+    double *logL_constraint;
+    double *logL;
+    long long *nevals;
+};
+
+struct DeadStore {
+    long long *sender;
+    double *logL;
+    double *U;
+    long long *nevals;
+    unsigned char *phantom;
+    long long capacity;
+};
+
+__device__ __forceinline__ long long clampll(long long v, long long lo, long long hi) {
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+// body prologue: the three key splits of one loop body (sharded_static.py:491,248,510), the contour
+// (:250-251) and the dead-store bookkeeping of _add_samples_to_state (:54,76-78).
+__global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSet live0, const LiveSet live1,
+                                long long m, long long kph, long long capacity, int intended_sender) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->active = reg->done ? 0 : 1;
+    if (!ctl->active) return;
+    const LiveSet &live = ctl->cur ? live1 : live0;
+    Key k = split_child(ctl->key, 0);      // :491  key, ephemeral_key = split(state.key)
+    ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
+    k = split_child(k, 0);
+    ctl->key = split_child(k, 0);          // :510  key, ephemeral_key = split(state.key)
+    ctl->contour = live.logL[m - 1];
+    ctl->disc_start = clampll(ctl->next_idx, 0, capacity - m);
+    ctl->next_idx = (ctl->next_idx + m) % capacity;
+    ctl->num_samples += m;
+    ctl->sender = intended_sender ? ctl->next_idx : ctl->next_idx - 1;  // :261
+    if (kph > 0) {
+        ctl->ph_start = clampll(ctl->next_idx, 0, capacity - m * kph);
+        ctl->next_idx = (ctl->next_idx + m * kph) % capacity;
+        ctl->num_samples += m * kph;
+    }
+    ctl->iteration += 1;
+}
+
+// Append live rows [0, count) to the dead store at ctl->disc_start (discarded shell) or at an
+// explicit offset (final live-set append, sharded_static.py:834-838).
+__global__ void k_append_live(const DevCtl *ctl, const LiveSet live0, const LiveSet live1, DeadStore dead,
+                              long long count, int D, int final_append) {
+    if (!final_append && !ctl->active) return;
+    const LiveSet &live = ctl->cur ? live1 : live0;
+    const long long start = final_append ? clampll(ctl->next_idx, 0, dead.capacity - count) : ctl->disc_start;
+    const long long total = count * D;
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < total;
+         e += (long long) gridDim.x * blockDim.x) {
+        dead.U[start * D + e] = live.U[e];
+        if (e < count) {
+            dead.sender[start + e] = live.sender[e];
+            dead.logL[start + e] = live.logL[e];
+            dead.nevals[start + e] = live.nevals[e];
+            dead.phantom[start + e] = 0;
+        }
+    }
+}
+
+__global__ void k_finalize_ctl(DevCtl *ctl, long long count, long long capacity) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->next_idx = (ctl->next_idx + count) % capacity;
+    ctl->num_samples += count;
+}
+
+// Rank of every element of the next live set under a stable ascending sort of
+// [new_0 .. new_{m-1}, survivor_m .. survivor_{N-1}]  (sharded_static.py:269-275): new rows come
+// first on ties.  packed rows: [U[D], logL, nevals, ...].
+__global__ void __launch_bounds__(256) k_merge_rank(const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
+                                                    const double *packed, long long row_doubles, int D,
+                                                    long long m, long long N, unsigned *rank_out) {
+    if (!ctl->active) return;
+    __shared__ uint64_t tile[1024];
+    const LiveSet &live = ctl->cur ? live1 : live0;
+    const long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < N;
+    const bool is_new = e < m;
+    uint64_t key = 0;
+    if (valid) key = sort_key_f64(is_new ? packed[e * row_doubles + D] : live.logL[e]);
+    unsigned cnt = 0;
+    for (long long t0 = 0; t0 < m; t0 += 1024) {
+        const int tn = (int) min((long long) 1024, m - t0);
+        __syncthreads();
+        for (int q = threadIdx.x; q < tn; q += blockDim.x) tile[q] = sort_key_f64(packed[(t0 + q) * row_doubles + D]);
+        __syncthreads();
+        if (valid) {
+            if (is_new) {
+                for (int q = 0; q < tn; ++q) {
+                    const uint64_t kq = tile[q];
+                    cnt += (kq < key) || (kq == key && (t0 + q) < e);
+                }
+            } else {
+                for (int q = 0; q < tn; ++q) cnt += (tile[q] <= key);
+            }
+        }
+    }
+    if (!valid) return;
+    if (is_new) {
+        // survivors strictly below (lower_bound over the sorted survivors)
+        long long lo = m, hi = N;
+        while (lo < hi) {
+            long long mid = lo + ((hi - lo) >> 1);
+            if (sort_key_f64(live.logL[mid]) < key) lo = mid + 1; else hi = mid;
+        }
+        cnt += (unsigned) (lo - m);
+    } else {
+        cnt += (unsigned) (e - m);
+    }
+    rank_out[e] = cnt;
+}
+
+// Scatter rows into the other live buffer at their rank; phantom rows go to the dead store
+// (add_phantom_samples_to_state, sharded_static.py:181-207).
+__global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const LiveSet live1, const double *packed,
+                                long long row_doubles, int D, long long m, long long N, int kph,
+                                const unsigned *rank, DeadStore dead) {
+    if (!ctl->active) return;
+    const LiveSet &src = ctl->cur ? live1 : live0;
+    const LiveSet &dst = ctl->cur ? live0 : live1;
+    const long long total = N * D;
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (long long) gridDim.x * blockDim.x) {
+        const long long e = t / D;
+        const int j = (int) (t - e * D);
+        const long long r = rank[e];
+        const bool is_new = e < m;
+        dst.U[r * D + j] = is_new ? packed[e * row_doubles + j] : src.U[e * D + j];
+        if (j == 0) {
+            if (is_new) {
+                dst.sender[r] = ctl->sender;
+                dst.logL[r] = packed[e * row_doubles + D];
+                dst.logL_constraint[r] = ctl->contour;
+                dst.nevals[r] = __double_as_longlong(packed[e * row_doubles + D + 1]);
+            } else {
+                dst.sender[r] = src.sender[e];
+                dst.logL[r] = src.logL[e];
+                dst.logL_constraint[r] = src.logL_constraint[e];
+                dst.nevals[r] = src.nevals[e];
+            }
+        }
+    }
+    if (kph > 0) {
+        const long long ptotal = m * kph * (long long) D;
+        for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < ptotal;
+             t += (long long) gridDim.x * blockDim.x) {
+            const long long row = t / D;  // phantom row index: chain * k + slot
+            const int j = (int) (t - row * D);
+            const long long chain = row / kph, slot = row - chain * kph;
+            const double *p = packed + chain * row_doubles + (D + 2) + slot * (D + 1);
+            const long long o = ctl->ph_start + row;
+            dead.U[o * D + j] = p[j];
+            if (j == 0) {
+                dead.sender[o] = ctl->sender;
+                dead.logL[o] = p[D];
+                dead.nevals[o] = 0;
+                dead.phantom[o] = 1;
+            }
+        }
+    }
+}
+
+// linear_to_log_stats (stats.py:55-74)
+__device__ __forceinline__ void linear_to_log_stats(double log_f_mean, double log_f2_mean, double &mu, double &var) {
+    mu = 2.0 * log_f_mean - 0.5 * log_f2_mean;
+    var = fmax(log_f2_mean - 2.0 * log_f_mean, 2.220446049250313e-16);
+}
+
+// determine_termination (termination.py:13-147)
+__device__ inline void determine_termination(const NsTermCond &tc, NsRegister &reg) {
+    long long reason = 0;
+    bool done = false;
+    const NsEvidenceCalc &ec = reg.evidence_calc, &ecr = reg.evidence_calc_with_remaining;
+#define NSB_BIT(cond, bit) \
+    if (cond) {            \
+        done = true;       \
+        reason += (1ll << (bit)); \
+    }
+    if (tc.mask & (1u << 4)) NSB_BIT((double) reg.num_samples_used >= tc.max_samples, 0)
+    if (tc.mask & (1u << 1)) {
+        double mu, var;
+        linear_to_log_stats(ecr.log_Z_mean, ecr.log_Z2_mean, mu, var);
+        NSB_BIT(var <= tc.evidence_uncert * tc.evidence_uncert, 1)
+    }
+    if (tc.mask & (1u << 3)) {
+        double m1, v1, m0, v0;
+        linear_to_log_stats(ecr.log_Z_mean, ecr.log_Z2_mean, m1, v1);
+        linear_to_log_stats(ec.log_Z_mean, ec.log_Z2_mean, m0, v0);
+        NSB_BIT((m1 - m0) < tc.dlogZ, 2)
+    }
+    if (tc.mask & (1u << 0)) {
+        const double ess = exp(2.0 * ecr.log_Z_mean - ecr.log_dZ2_mean);
+        NSB_BIT(ess >= tc.ess, 3)
+    }
+    if (tc.mask & (1u << 5)) NSB_BIT((double) reg.num_likelihood_evaluations >= tc.max_num_likelihood_evaluations, 4)
+    if (tc.mask & (1u << 6)) NSB_BIT(reg.log_L_contour >= tc.log_L_contour, 5)
+    if (tc.mask & (1u << 7)) NSB_BIT(reg.efficiency < tc.efficiency_threshold, 6)
+    NSB_BIT(reg.plateau != 0, 7)
+    if (tc.mask & (1u << 8)) NSB_BIT(reg.relative_spread < tc.rtol, 8)
+    if (tc.mask & (1u << 9)) NSB_BIT(reg.absolute_spread < tc.atol, 9)
+    NSB_BIT(reg.no_seed_points != 0, 10)
+    if (tc.mask & (1u << 10)) {
+        const double log_XL = ec.log_X_mean + ec.log_L;
+        NSB_BIT(log_XL < reg.peak_log_XL + log(tc.peak_XL_frac), 11)
+    }
+#undef NSB_BIT
+    reg.done = done ? 1 : 0;
+    reg.termination_reason = reason;
+}
+
+// Register update of _collect_shell (sharded_static.py:281-323) followed by the loop condition.
+// One CTA of 1024 threads.  `old` = live set before the merge (its first m rows are the discarded
+// shell), `cur` = merged live set.
+__global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0,
+                                                        const LiveSet live1, const double *packed,
+                                                        long long row_doubles, int D, long long m, long long N,
+                                                        NsTermCond tc, int init_only) {
+    __shared__ double sh[33];
+    __shared__ NsEvidenceCalc s_mid, s_fin;
+    __shared__ long long s_ll[2];
+    __shared__ int s_flag;
+    if (!init_only && !ctl->active) return;
+    if (init_only) {
+        // _main_ns_thread entry (:471-473): no_seed_points of the initial live set, then cond.
+        if (threadIdx.x == 0) {
+            const LiveSet &live = ctl->cur ? live1 : live0;
+            reg->no_seed_points = live.logL[m - 1] >= live.logL[N - 1];
+            determine_termination(tc, *reg);
+        }
+        return;
+    }
+    const LiveSet &old = ctl->cur ? live1 : live0;
+    const LiveSet &cur = ctl->cur ? live0 : live1;
+    EvSeq q;
+    q.la = old.logL;
+    q.na = nullptr;
+    q.len_a = m;
+    q.n_const_a = (double) N;  // :288, n = N for the whole shell
+    q.lb = cur.logL;
+    q.len_b = N;
+    q.n_start_b = (double) N;  // :296, n = N..1
+    EvOut out;
+    out.mid = &s_mid;
+    out.mark = m;
+    out.fin = &s_fin;
+    out.per_sample = nullptr;
+    evidence_scan_block(q, reg->evidence_calc, out, sh);
+    // sums of likelihood evaluations, plateau flag
+    long long sum_new = 0, sum_live = 0;
+    int not_plateau = 0;
+    const double l0 = cur.logL[0];
+    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+        sum_live += cur.nevals[i];
+        not_plateau |= !(cur.logL[i] == l0);
+        if (i < m) sum_new += __double_as_longlong(packed[i * row_doubles + D + 1]);
+    }
+    if (threadIdx.x == 0) {
+        s_ll[0] = 0;
+        s_ll[1] = 0;
+        s_flag = 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sum_new += __shfl_xor_sync(0xFFFFFFFFu, sum_new, o);
+        sum_live += __shfl_xor_sync(0xFFFFFFFFu, sum_live, o);
+        not_plateau |= __shfl_xor_sync(0xFFFFFFFFu, not_plateau, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd((unsigned long long *) &s_ll[0], (unsigned long long) sum_new);
+        atomicAdd((unsigned long long *) &s_ll[1], (unsigned long long) sum_live);
+        if (not_plateau) atomicOr(&s_flag, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        NsRegister r = *reg;
+        r.num_samples_used = ctl->num_samples;
+        r.evidence_calc = s_mid;
+        r.evidence_calc_with_remaining = s_fin;
+        r.num_likelihood_evaluations += s_ll[0];
+        r.log_L_contour = ctl->contour;
+        r.efficiency = (double) N / (double) s_ll[1];
+        r.plateau = s_flag ? 0 : 1;
+        const double lo = cur.logL[0], hi = cur.logL[N - 1];
+        r.absolute_spread = fabs(hi - lo);
+        r.relative_spread = 2.0 * r.absolute_spread / fabs(lo + hi);
+        r.no_seed_points = cur.logL[m - 1] >= hi;
+        r.peak_log_XL = fmax(r.peak_log_XL, s_mid.log_X_mean + s_mid.log_L);
+        r.iteration = ctl->iteration;
+        determine_termination(tc, r);
+        *reg = r;
+        ctl->cur ^= 1;
+    }
+}
+
+}  // namespace nsb

@@ -1,0 +1,514 @@
+// Statistics kernels over the live / dead point sets: stable LSD radix argsort, rank-merge of a
+// replaced shell into the sorted survivors, tree-structure live-point counting, the log-space
+// evidence recurrences as parallel scans, logsumexp.
+//
+// Reference: count_crossed_edges (/root/reference/src/jaxns/internals/tree_structure.py:33-108),
+// _update_evidence_calc_op / compute_evidence_stats (internals/shrinkage_statistics.py:43-157),
+// cumulative_op_static/dynamic (internals/cumulative_ops.py:50-130), LogSpace.sum
+// (internals/log_semiring.py:187-190), jnp.argsort call sites sharded_static.py:174,274.
+#pragma once
+#include "ns_math.cuh"
+#include "../../include/nsb200.h"
+
+namespace nsb {
+
+// =================================================================================================
+// Block-level scan helpers (warp shuffles + one shared array of 32 partials).
+// =================================================================================================
+struct OpAdd {
+    __device__ __forceinline__ static double id() { return 0.0; }
+    __device__ __forceinline__ static double ap(double a, double b) { return a + b; }
+};
+struct OpLae {
+    __device__ __forceinline__ static double id() { return -__longlong_as_double(0x7FF0000000000000ll); }
+    __device__ __forceinline__ static double ap(double a, double b) { return logaddexp(a, b); }
+};
+
+// Exclusive scan of one value per thread across the CTA; returns the exclusive prefix and (in
+// `total`) the CTA aggregate.  `sh` = 33 doubles of shared memory.  Contains __syncthreads().
+template <class Op>
+__device__ __forceinline__ double block_scan_excl(double v, double *sh, double &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc = Op::ap(y, inc);
+    }
+    double exc = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    if (lane == 0) exc = Op::id();
+    __syncthreads();
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        double w = (lane < nw) ? sh[lane] : Op::id();
+        double winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double y = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= o) winc = Op::ap(y, winc);
+        }
+        double wexc = __shfl_up_sync(0xFFFFFFFFu, winc, 1);
+        if (lane == 0) wexc = Op::id();
+        sh[lane] = wexc;
+        if (lane == 31) sh[32] = winc;
+    }
+    __syncthreads();
+    total = sh[32];
+    return Op::ap(sh[warp], exc);
+}
+
+// =================================================================================================
+// Stable LSD radix argsort on order-preserving u64 keys (8-bit digits, 8 passes).
+// =================================================================================================
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;
+
+// keys_out[i + offset] = sort_key(x[i]); vals = iota.  `lead_neg_inf` prepends the -inf root node.
+__global__ void k_sort_prep(const double *x, long long n, int lead_neg_inf, uint64_t *keys, uint32_t *vals) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = n + (lead_neg_inf ? 1 : 0);
+    if (i >= total) return;
+    double v;
+    if (lead_neg_inf) v = (i == 0) ? -__longlong_as_double(0x7FF0000000000000ll) : x[i - 1];
+    else v = x[i];
+    keys[i] = sort_key_f64(v);
+    vals[i] = (uint32_t) i;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint64_t *keys, long long n, int shift,
+                                                             uint32_t *hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const long long base = (long long) blockIdx.x * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const long long i = base + (long long) r * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t) threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+// In-place exclusive scan of `cnt` uint32 entries by one CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_scan_u32_excl(uint32_t *data, long long cnt) {
+    __shared__ uint32_t sh[33];
+    const long long per = (cnt + blockDim.x - 1) / blockDim.x;
+    const long long b = (long long) threadIdx.x * per, e = min(cnt, b + per);
+    uint32_t s = 0;
+    for (long long i = b; i < e; ++i) s += data[i];
+    // block exclusive scan of s
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = sh[lane], winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xFFFFFFFFu, winc, o);
+            if (lane >= o) winc += y;
+        }
+        sh[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t run = sh[warp] + (inc - s);
+    for (long long i = b; i < e; ++i) {
+        uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint64_t *keys_in, const uint32_t *vals_in,
+                                                                uint64_t *keys_out, uint32_t *vals_out,
+                                                                long long n, int shift, const uint32_t *offsets,
+                                                                int nblocks) {
+    __shared__ uint32_t base[256];
+    __shared__ uint32_t wcnt[kSortThreads / 32][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    base[tid] = offsets[(size_t) tid * nblocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < kSortThreads / 32; ++w) wcnt[w][tid] = 0;
+    __syncthreads();
+    const long long tile = (long long) blockIdx.x * kSortTile;
+    for (int r = 0; r < kSortItems; ++r) {
+        const long long i = tile + (long long) r * kSortThreads + tid;
+        const bool valid = i < n;
+        uint64_t key = 0;
+        uint32_t val = 0;
+        unsigned digit = 256u;  // sentinel for out-of-range lanes
+        if (valid) {
+            key = keys_in[i];
+            val = vals_in[i];
+            digit = (unsigned) ((key >> shift) & 255u);
+        }
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
+        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
+        if (valid && rank == 0) wcnt[warp][digit] = __popc(peers);
+        __syncthreads();
+        if (valid) {
+            uint32_t off = base[digit];
+            for (int w = 0; w < warp; ++w) off += wcnt[w][digit];
+            keys_out[off + rank] = key;
+            vals_out[off + rank] = val;
+        }
+        __syncthreads();
+        uint32_t add = 0;
+#pragma unroll
+        for (int w = 0; w < kSortThreads / 32; ++w) {
+            add += wcnt[w][tid];
+            wcnt[w][tid] = 0;
+        }
+        base[tid] += add;
+        __syncthreads();
+    }
+}
+
+struct SortWorkspace {
+    uint64_t *keys[2];
+    uint32_t *vals[2];
+    uint32_t *hist;
+    int nblocks;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+inline size_t sort_workspace_bytes(long long n) {
+    const long long nb = (n + kSortTile - 1) / kSortTile;
+    return 2 * align256((size_t) n * 8) + 2 * align256((size_t) n * 4) + align256((size_t) 256 * nb * 4) + 256;
+}
+
+inline SortWorkspace carve_sort_workspace(void *ws, long long n) {
+    SortWorkspace w;
+    char *p = (char *) ws;
+    p = (char *) align256((size_t) p);
+    w.nblocks = (int) ((n + kSortTile - 1) / kSortTile);
+    w.keys[0] = (uint64_t *) p; p += align256((size_t) n * 8);
+    w.keys[1] = (uint64_t *) p; p += align256((size_t) n * 8);
+    w.vals[0] = (uint32_t *) p; p += align256((size_t) n * 4);
+    w.vals[1] = (uint32_t *) p; p += align256((size_t) n * 4);
+    w.hist = (uint32_t *) p;
+    return w;
+}
+
+// Sorts keys[0]/vals[0] (n entries); result ends in keys[0]/vals[0] (8 passes = even).
+inline void radix_sort_pairs(const SortWorkspace &w, long long n, cudaStream_t st) {
+    if (n <= 0) return;
+    int cur = 0;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        k_radix_hist<<<w.nblocks, kSortThreads, 0, st>>>(w.keys[cur], n, shift, w.hist, w.nblocks);
+        k_scan_u32_excl<<<1, 1024, 0, st>>>(w.hist, (long long) 256 * w.nblocks);
+        k_radix_scatter<<<w.nblocks, kSortThreads, 0, st>>>(w.keys[cur], w.vals[cur], w.keys[cur ^ 1], w.vals[cur ^ 1],
+                                                             n, shift, w.hist, w.nblocks);
+        cur ^= 1;
+    }
+}
+
+__global__ void k_vals_to_i64(const uint32_t *vals, long long n, long long *out) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (long long) vals[i];
+}
+
+// =================================================================================================
+// Tree-structure live-point counting.
+// =================================================================================================
+__global__ void k_out_degree(const long long *sender, long long M, int *outdeg) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < M) {
+        long long s = sender[i];
+        if (s < 0) s = 0;  // lax.max(sender, 0), tree_structure.py:54-56
+        atomicAdd(&outdeg[s], 1);
+    }
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// pass 1: per-tile sums of delta_i = outdeg[sort_idx[i]] - 1
+__global__ void __launch_bounds__(kScanThreads) k_tree_tile_sums(const uint32_t *sort_idx, const int *outdeg,
+                                                                 long long n, int *tile_sums) {
+    __shared__ int sh[kScanThreads / 32];
+    const long long base = (long long) blockIdx.x * kScanTile + (long long) threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        const long long i = base + r;
+        if (i < n) s += outdeg[sort_idx[i]] - 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// pass 2: exclusive scan of tile sums by a single CTA (reuses the u32 scan; int32 wraps identically)
+// pass 3: per-tile inclusive scan + outputs
+__global__ void __launch_bounds__(kScanThreads) k_tree_apply(const uint32_t *sort_idx, const int *outdeg, long long n,
+                                                             const int *tile_offsets, long long M,
+                                                             long long num_samples, long long *out_idx,
+                                                             int *out_nlive) {
+    __shared__ int sh[kScanThreads / 32 + 1];
+    const long long base = (long long) blockIdx.x * kScanTile + (long long) threadIdx.x * kScanItems;
+    int loc[kScanItems];
+    int s = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        const long long i = base + r;
+        int dlt = 0;
+        if (i < n) dlt = outdeg[sort_idx[i]] - 1;
+        s += dlt;
+        loc[r] = s;
+    }
+    // exclusive scan of s across the CTA
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) {
+            int v = sh[w];
+            sh[w] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+    const int prefix = tile_offsets[blockIdx.x] + sh[warp] + (inc - s) + 1;  // init = 1
+    const bool dynamic = num_samples >= 0;
+    const int fake = dynamic ? (int) (M - num_samples) : 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        const long long i = base + r;
+        if (i < M) {  // drop the last node (crossed[:-1]); samples_indices = sort_idx[1:] - 1
+            int crossed = prefix + loc[r];
+            if (dynamic) crossed = ((i < num_samples) ? crossed : fake) - fake;
+            out_nlive[i] = crossed;
+            out_idx[i] = (long long) sort_idx[i + 1] - 1;
+        }
+    }
+}
+
+// =================================================================================================
+// Evidence recurrences as scans.  One CTA; every thread owns a contiguous chunk.
+// =================================================================================================
+// The scanned sequence is segment A followed by segment B:
+//   A: log_L = la[i], n = na ? na[i] : n_const_a          (dead points / discarded shell)
+//   B: log_L = lb[i], n = n_start_b - i                   (remaining live points, n = N..1)
+struct EvSeq {
+    const double *la;
+    const double *na;
+    long long len_a;
+    double n_const_a;
+    const double *lb;
+    long long len_b;
+    double n_start_b;
+};
+
+struct EvTerms {
+    double T, T2, t, t2, tT, mid;
+};
+
+__device__ __forceinline__ void ev_get(const EvSeq &q, long long i, double &logL, double &n) {
+    if (i < q.len_a) {
+        logL = q.la[i];
+        n = q.na ? q.na[i] : q.n_const_a;
+    } else {
+        const long long j = i - q.len_a;
+        logL = q.lb[j];
+        n = q.n_start_b - (double) j;
+    }
+}
+
+__device__ __forceinline__ EvTerms ev_terms(double logL, double prevL, double n) {
+    const double kLog2 = 0.6931471805599453, kLogHalf = -0.6931471805599453;
+    EvTerms e;
+    const double ln = log(n), lnp1 = log(n + 1.0), lnp2 = log(n + 2.0);
+    e.mid = kLogHalf + logaddexp(logL, prevL);
+    e.T = -logaddexp(0.0, -ln);
+    e.t = -lnp1;
+    e.T2 = -logaddexp(0.0, kLog2 - ln);
+    e.t2 = kLog2 - lnp1 - lnp2;
+    e.tT = e.T - lnp2;
+    return e;
+}
+
+struct EvOut {
+    NsEvidenceCalc *mid;     // state after element index mark-1 (nullable)
+    long long mark;
+    NsEvidenceCalc *fin;     // state after the last element (nullable)
+    double *per_sample;      // [8][M] field-major (nullable)
+};
+
+// Must be called by all threads of a CTA.  sh = 33 doubles.
+__device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double *sh) {
+    const double kLog2 = 0.6931471805599453;
+    const long long M = q.len_a + q.len_b;
+    const long long per = (M + blockDim.x - 1) / blockDim.x;
+    const long long b = min(M, (long long) threadIdx.x * per), e = min(M, b + per);
+    double tot;
+    double prev0 = init.log_L;
+    if (b > 0 && b < M) {
+        double nn;
+        ev_get(q, b - 1, prev0, nn);
+    }
+    // pass 1: cumsum of T, T2
+    double sT = 0.0, sT2 = 0.0;
+    {
+        double prevL = prev0;
+        for (long long i = b; i < e; ++i) {
+            double logL, n;
+            ev_get(q, i, logL, n);
+            EvTerms t = ev_terms(logL, prevL, n);
+            sT += t.T;
+            sT2 += t.T2;
+            prevL = logL;
+        }
+    }
+    const double X0 = init.log_X_mean + block_scan_excl<OpAdd>(sT, sh, tot);
+    const double X20 = init.log_X2_mean + block_scan_excl<OpAdd>(sT2, sh, tot);
+    // pass 2: Z, dZ2, W = ZX / X
+    const double kNegInf = OpLae::id();
+    double sa = kNegInf, sb = kNegInf, sw = kNegInf;
+    {
+        double prevL = prev0, lX = X0, lX2 = X20;
+        for (long long i = b; i < e; ++i) {
+            double logL, n;
+            ev_get(q, i, logL, n);
+            EvTerms t = ev_terms(logL, prevL, n);
+            sa = logaddexp(sa, lX + t.t + t.mid);
+            sb = logaddexp(sb, lX2 + t.t2 + 2.0 * t.mid);
+            sw = logaddexp(sw, (lX2 + t.tT + t.mid) - (lX + t.T));
+            lX += t.T;
+            lX2 += t.T2;
+            prevL = logL;
+        }
+    }
+    const double Z0 = logaddexp(init.log_Z_mean, block_scan_excl<OpLae>(sa, sh, tot));
+    const double dZ20 = logaddexp(init.log_dZ2_mean, block_scan_excl<OpLae>(sb, sh, tot));
+    const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, block_scan_excl<OpLae>(sw, sh, tot));
+    // pass 3: Z2
+    double sc = kNegInf;
+    {
+        double prevL = prev0, lX = X0, lX2 = X20, lW = W0;
+        for (long long i = b; i < e; ++i) {
+            double logL, n;
+            ev_get(q, i, logL, n);
+            EvTerms t = ev_terms(logL, prevL, n);
+            const double zx_prev = lX + lW;
+            sc = logaddexp(sc, logaddexp(kLog2 + zx_prev + t.t + t.mid, lX2 + t.t2 + 2.0 * t.mid));
+            lW = logaddexp(lW, (lX2 + t.tT + t.mid) - (lX + t.T));
+            lX += t.T;
+            lX2 += t.T2;
+            prevL = logL;
+        }
+    }
+    const double Z20 = logaddexp(init.log_Z2_mean, block_scan_excl<OpLae>(sc, sh, tot));
+    // pass 4: outputs
+    {
+        double prevL = prev0, lX = X0, lX2 = X20, lW = W0, lZ = Z0, ldZ2 = dZ20, lZ2 = Z20;
+        for (long long i = b; i < e; ++i) {
+            double logL, n;
+            ev_get(q, i, logL, n);
+            EvTerms t = ev_terms(logL, prevL, n);
+            const double dZ = lX + t.t + t.mid;
+            const double x2t2m2 = lX2 + t.t2 + 2.0 * t.mid;
+            const double zx_prev = lX + lW;
+            lZ2 = logaddexp(logaddexp(lZ2, kLog2 + zx_prev + t.t + t.mid), x2t2m2);
+            lZ = logaddexp(lZ, dZ);
+            ldZ2 = logaddexp(ldZ2, x2t2m2);
+            lW = logaddexp(lW, (lX2 + t.tT + t.mid) - (lX + t.T));
+            lX += t.T;
+            lX2 += t.T2;
+            prevL = logL;
+            NsEvidenceCalc c;
+            c.log_L = logL;
+            c.log_X_mean = lX;
+            c.log_X2_mean = lX2;
+            c.log_Z_mean = lZ;
+            c.log_ZX_mean = lX + lW;
+            c.log_Z2_mean = lZ2;
+            c.log_dZ_mean = dZ;
+            c.log_dZ2_mean = ldZ2;
+            if (out.per_sample) {
+                double *p = out.per_sample + i;
+                p[0 * M] = c.log_L;
+                p[1 * M] = c.log_X_mean;
+                p[2 * M] = c.log_X2_mean;
+                p[3 * M] = c.log_Z_mean;
+                p[4 * M] = c.log_ZX_mean;
+                p[5 * M] = c.log_Z2_mean;
+                p[6 * M] = c.log_dZ_mean;
+                p[7 * M] = c.log_dZ2_mean;
+            }
+            if (out.mid && i == out.mark - 1) *out.mid = c;
+            if (out.fin && i == M - 1) *out.fin = c;
+        }
+    }
+    if (M == 0 && threadIdx.x == 0) {
+        if (out.fin) *out.fin = init;
+        if (out.mid) *out.mid = init;
+    } else if (out.mid && out.mark == 0 && threadIdx.x == 0) {
+        *out.mid = init;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out) {
+    __shared__ double sh[33];
+    evidence_scan_block(q, init, out, sh);
+}
+
+// =================================================================================================
+// logsumexp (single CTA, two passes over the data).
+// =================================================================================================
+__global__ void __launch_bounds__(1024) k_logsumexp(const double *x, long long n, double *out) {
+    __shared__ double sh[33];
+    const double kNegInf = -__longlong_as_double(0x7FF0000000000000ll);
+    double mx = kNegInf;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) mx = fmax(mx, x[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m2 = kNegInf;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) m2 = fmax(m2, sh[w]);
+        sh[32] = m2;
+    }
+    __syncthreads();
+    mx = sh[32];
+    __syncthreads();
+    const double shift = (mx == kNegInf || mx != mx || mx == -kNegInf) ? 0.0 : mx;
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += exp(x[i] - shift);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < (blockDim.x >> 5); ++w) t += sh[w];
+        out[0] = log(t) + shift;
+    }
+}
+
+}  // namespace nsb

@@ -1,0 +1,823 @@
+// C ABI of the B200-native nested-sampling hot path (see include/nsb200.h for the contract and the
+// reference interfaces each entry point replaces).  Single translation unit: kernels are templates
+// in the .cuh headers next to this file.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "ns_engine.cuh"
+#include "ns_slice.cuh"
+
+using namespace nsb;
+
+// -------------------------------------------------------------------------------------------------
+// error plumbing
+// -------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return 1;
+}
+
+#define NSB_CUDA(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define NSB_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+extern "C" int nsb200_abi_version(void) { return NSB200_ABI_VERSION; }
+extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
+
+// -------------------------------------------------------------------------------------------------
+// launch geometry: group size G (lanes per chain) and DPL (dims per lane)
+// -------------------------------------------------------------------------------------------------
+struct Geometry {
+    int G, DPL, DP;
+};
+
+static int pick_geometry(int D, Geometry &g) {
+    if (D < 1) return fail("model.D must be >= 1, got %d", D);
+    if (D > 256) return fail("model.D = %d exceeds the supported maximum of 256", D);
+    int G = 1;
+    while (G < D && G < 32) G <<= 1;
+    int dpl = (D + G - 1) / G;
+    int DPL = 1;
+    while (DPL < dpl) DPL <<= 1;
+    g.G = G;
+    g.DPL = DPL;
+    g.DP = G * DPL;
+    return 0;
+}
+
+static int check_model(const NsModelDesc *m) {
+    if (!m) return fail("model is NULL");
+    if (m->family < 0 || m->family > NSB200_FAM_SHELLS) return fail("unknown likelihood family %d", m->family);
+    if (m->prior_kind != NSB200_PRIOR_UNIFORM && m->prior_kind != NSB200_PRIOR_NORMAL)
+        return fail("unknown prior kind %d", m->prior_kind);
+    if (!m->prior_a || !m->prior_b) return fail("model prior arrays are NULL");
+    const long long D = m->D, K = m->K;
+    long long need = 0;
+    switch (m->family) {
+        case NSB200_FAM_GAUSS_DENSE: need = 1 + D + D * D; break;
+        case NSB200_FAM_GAUSS_MIX_DIAG: need = K * (1 + 2 * D); break;
+        case NSB200_FAM_SHELLS: need = K * (2 + D); break;
+        default: need = 0;
+    }
+    if ((m->family == NSB200_FAM_GAUSS_MIX_DIAG || m->family == NSB200_FAM_SHELLS) && K < 1)
+        return fail("family %d needs K >= 1", m->family);
+    if (need > 0 && (!m->params || m->n_params < need))
+        return fail("family %d with D=%lld K=%lld needs %lld params, got %lld", m->family, D, K, need,
+                    (long long) m->n_params);
+    return 0;
+}
+
+template <typename KernelT>
+static int set_smem(KernelT kernel, size_t bytes) {
+    if (bytes > 227 * 1024) return fail("model needs %zu bytes of shared memory per CTA (> 227 KB)", bytes);
+    if (bytes > 48 * 1024) NSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes));
+    return 0;
+}
+
+#define NSB_DISPATCH_DPL(DPLV, ...)                          \
+    switch (DPLV) {                                          \
+        case 1: { constexpr int kDPL = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int kDPL = 2; __VA_ARGS__; } break; \
+        case 4: { constexpr int kDPL = 4; __VA_ARGS__; } break; \
+        case 8: { constexpr int kDPL = 8; __VA_ARGS__; } break; \
+        default: return fail("unsupported DPL %d", DPLV);    \
+    }
+
+// -------------------------------------------------------------------------------------------------
+// jax.random primitives
+// -------------------------------------------------------------------------------------------------
+__global__ void k_threefry(Key key, const uint32_t *x0, const uint32_t *x1, long long n, uint32_t *o0, uint32_t *o1) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t a = x0[i], b = x1[i];
+    threefry2x32(key.a, key.b, a, b);
+    o0[i] = a;
+    o1[i] = b;
+}
+
+// mode 0: split -> out u32[n,2]; 1: bits64; 2: uniform(lo,hi); 3: normal
+__global__ void k_random(Key key, long long n, int mode, double lo, double hi, void *out) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mode == 0) {
+        Key c = split_child(key, (uint64_t) i);
+        ((uint32_t *) out)[2 * i] = c.a;
+        ((uint32_t *) out)[2 * i + 1] = c.b;
+    } else if (mode == 1) {
+        ((uint64_t *) out)[i] = bits64(key, (uint64_t) i);
+    } else if (mode == 2) {
+        ((double *) out)[i] = uniform_lohi(bits64(key, (uint64_t) i), lo, hi);
+    } else {
+        ((double *) out)[i] = normal_from_bits(bits64(key, (uint64_t) i));
+    }
+}
+
+static inline int grid_for(long long n, int threads) { return (int) ((n + threads - 1) / threads); }
+
+extern "C" int nsb200_threefry2x32(const uint32_t key[2], const uint32_t *x0, const uint32_t *x1, int64_t n,
+                                   uint32_t *out0, uint32_t *out1, nsb200_stream_t stream) {
+    if (n <= 0) return 0;
+    k_threefry<<<grid_for(n, 256), 256, 0, (cudaStream_t) stream>>>(Key{key[0], key[1]}, x0, x1, n, out0, out1);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_random(const uint32_t key[2], int64_t n, int mode, double lo, double hi, void *out, nsb200_stream_t stream) {
+    if (n <= 0) return 0;
+    if (!out) return fail("output pointer is NULL");
+    k_random<<<grid_for(n, 256), 256, 0, (cudaStream_t) stream>>>(Key{key[0], key[1]}, n, mode, lo, hi, out);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_random_split(const uint32_t key[2], int64_t n, uint32_t *out, nsb200_stream_t stream) {
+    return launch_random(key, n, 0, 0, 0, out, stream);
+}
+extern "C" int nsb200_random_bits64(const uint32_t key[2], int64_t n, uint64_t *out, nsb200_stream_t stream) {
+    return launch_random(key, n, 1, 0, 0, out, stream);
+}
+extern "C" int nsb200_random_uniform(const uint32_t key[2], int64_t n, double lo, double hi, double *out,
+                                     nsb200_stream_t stream) {
+    return launch_random(key, n, 2, lo, hi, out, stream);
+}
+extern "C" int nsb200_random_normal(const uint32_t key[2], int64_t n, double *out, nsb200_stream_t stream) {
+    return launch_random(key, n, 3, 0, 0, out, stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// model / samplers
+// -------------------------------------------------------------------------------------------------
+static size_t sampler_smem_bytes(const NsModelDesc &m, const Geometry &g, bool slice) {
+    const size_t per_chain = slice ? chain_smem_doubles(g.DP, g.G) : (size_t) g.DP;
+    return 8 * (model_smem_doubles(m.family, m.D, g.DP, m.K) + (kThreadsPerBlock / g.G) * per_chain);
+}
+
+extern "C" int nsb200_forward_batch(const NsModelDesc *model, const double *U, int64_t n, double *out_logL,
+                                    double *out_X, nsb200_stream_t stream) {
+    if (check_model(model)) return 1;
+    if (n <= 0) return 0;
+    if (!U) return fail("U is NULL");
+    Geometry g;
+    if (pick_geometry(model->D, g)) return 1;
+    ForwardArgs a{*model, U, out_logL, out_X, n, g.G};
+    const size_t smem = sampler_smem_bytes(*model, g, false);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_DPL(g.DPL, {
+        if (set_smem(k_forward<kDPL>, smem)) return 1;
+        k_forward<kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, (cudaStream_t) stream>>>(a);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+__global__ void k_seed_table(long long N, double *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double acc = -__longlong_as_double(0x7FF0000000000000ll);
+    for (long long q = 0; q < N; ++q) {
+        acc = logaddexp(acc, 0.0);
+        out[q] = acc;
+    }
+}
+
+extern "C" int nsb200_seed_table(int64_t N, double *out, nsb200_stream_t stream) {
+    if (N <= 0) return 0;
+    if (!out) return fail("out is NULL");
+    k_seed_table<<<1, 1, 0, (cudaStream_t) stream>>>(N, out);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int launch_draw(const NsModelDesc *model, Key key, const double *contour, long long begin, long long end,
+                       double *out_U, double *out_logL, long long *out_nevals, int uniform_sampler,
+                       cudaStream_t st) {
+    if (check_model(model)) return 1;
+    if (end <= begin) return 0;
+    Geometry g;
+    if (pick_geometry(model->D, g)) return 1;
+    DrawArgs a{*model, key, contour, out_U, out_logL, out_nevals, begin, end, g.G, uniform_sampler};
+    const size_t smem = sampler_smem_bytes(*model, g, false);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_DPL(g.DPL, {
+        if (set_smem(k_draw<kDPL>, smem)) return 1;
+        k_draw<kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, st>>>(a);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_init_batch(const NsModelDesc *model, const uint32_t sample_key[2], int64_t N, int64_t begin,
+                                 int64_t end, double *out_U, double *out_logL, int64_t *out_nevals,
+                                 nsb200_stream_t stream) {
+    if (begin < 0 || end > N || begin > end) return fail("bad range [%lld, %lld) of %lld", (long long) begin, (long long) end, (long long) N);
+    if (!out_U || !out_logL || !out_nevals) return fail("output pointer is NULL");
+    return launch_draw(model, Key{sample_key[0], sample_key[1]}, nullptr, begin, end, out_U, out_logL,
+                       (long long *) out_nevals, 0, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_uniform_batch(const NsModelDesc *model, const uint32_t key[2], const double *contour,
+                                    int64_t num_samples, int64_t chain_begin, int64_t chain_end, double *out_U,
+                                    double *out_logL, int64_t *out_nevals, nsb200_stream_t stream) {
+    if (chain_begin < 0 || chain_end > num_samples || chain_begin > chain_end) return fail("bad chain range");
+    if (!contour) return fail("contour is NULL");
+    if (!out_U || !out_logL || !out_nevals) return fail("output pointer is NULL");
+    return launch_draw(model, Key{key[0], key[1]}, contour, chain_begin, chain_end, out_U, out_logL,
+                       (long long *) out_nevals, 1, (cudaStream_t) stream);
+}
+
+static int launch_slice(const SliceArgs &a0, cudaStream_t st) {
+    SliceArgs a = a0;
+    Geometry g;
+    if (pick_geometry(a.model.D, g)) return 1;
+    a.G = g.G;
+    const long long n = a.chain_end - a.chain_begin;
+    if (n <= 0) return 0;
+    const size_t smem = sampler_smem_bytes(a.model, g, true);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_DPL(g.DPL, {
+        if (set_smem(k_slice_chains<kDPL>, smem)) return 1;
+        k_slice_chains<kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, st>>>(a);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                                  const double *contour, const double *live_U, const double *live_logL,
+                                  const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
+                                  double *ph_U, double *ph_logL, nsb200_stream_t stream) {
+    if (check_model(model)) return 1;
+    if (!p) return fail("params is NULL");
+    if (p->num_slices < 1) return fail("num_slices should be >= 1, got %d", p->num_slices);
+    if (p->num_phantom < 0) return fail("num_phantom_save should be >= 0, got %d", p->num_phantom);
+    if (p->num_phantom >= p->num_slices)
+        return fail("num_phantom_save should be < num_slices, got %d >= %d", p->num_phantom, p->num_slices);
+    if (p->num_live < 1) return fail("num_live must be >= 1");
+    if (p->chain_begin < 0 || p->chain_end > p->num_samples || p->chain_begin > p->chain_end)
+        return fail("bad chain range [%lld, %lld) of %lld", (long long) p->chain_begin, (long long) p->chain_end,
+                    (long long) p->num_samples);
+    if (!contour || !live_U || !live_logL || !seed_table) return fail("input pointer is NULL");
+    if (!out_U || !out_logL || !out_nevals) return fail("output pointer is NULL");
+    if (p->num_phantom > 0 && (!ph_U || !ph_logL)) return fail("phantom outputs are NULL but num_phantom > 0");
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.model = *model;
+    a.key = Key{key[0], key[1]};
+    a.contour = contour;
+    a.live_U = live_U;
+    a.live_logL = live_logL;
+    a.seed_table = seed_table;
+    a.out_U = out_U;
+    a.out_logL = out_logL;
+    a.out_nevals = (long long *) out_nevals;
+    a.ph_U = ph_U;
+    a.ph_logL = ph_logL;
+    a.N = p->num_live;
+    a.chain_begin = p->chain_begin;
+    a.chain_end = p->chain_end;
+    a.S = p->num_slices;
+    a.k = p->num_phantom;
+    a.midpoint = p->midpoint_shrink;
+    a.packed = nullptr;
+    a.packed_row_doubles = 0;
+    return launch_slice(a, (cudaStream_t) stream);
+}
+
+// -------------------------------------------------------------------------------------------------
+// statistics
+// -------------------------------------------------------------------------------------------------
+static size_t tree_workspace_bytes(long long M) {
+    const long long n = M + 1;
+    const long long tiles = (n + kScanTile - 1) / kScanTile;
+    return sort_workspace_bytes(n) + align256((size_t) n * 4) + align256((size_t) tiles * 4) + 512;
+}
+
+extern "C" int64_t nsb200_workspace_bytes(int32_t op, int64_t n) {
+    if (n < 0) n = 0;
+    switch (op) {
+        case NSB200_WS_ARGSORT: return (int64_t) sort_workspace_bytes(n > 0 ? n : 1);
+        case NSB200_WS_COUNT_CROSSED_EDGES: return (int64_t) tree_workspace_bytes(n);
+        case NSB200_WS_EVIDENCE_STATS: return 256;
+        case NSB200_WS_LOGSUMEXP: return 256;
+        default: return -1;
+    }
+}
+
+extern "C" int nsb200_argsort_f64(const double *keys, int64_t n, int64_t *out_idx, void *workspace,
+                                  int64_t workspace_bytes, nsb200_stream_t stream) {
+    if (n <= 0) return 0;
+    if (n >= (1ll << 32)) return fail("argsort supports n < 2^32");
+    if (!keys || !out_idx || !workspace) return fail("NULL pointer");
+    if (workspace_bytes < (int64_t) sort_workspace_bytes(n)) return fail("workspace too small: %lld < %zu", (long long) workspace_bytes, sort_workspace_bytes(n));
+    cudaStream_t st = (cudaStream_t) stream;
+    SortWorkspace w = carve_sort_workspace(workspace, n);
+    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(keys, n, 0, w.keys[0], w.vals[0]);
+    radix_sort_pairs(w, n, st);
+    k_vals_to_i64<<<grid_for(n, 256), 256, 0, st>>>(w.vals[0], n, (long long *) out_idx);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_count_crossed_edges(const int64_t *sender_node_idx, const double *log_L, int64_t M,
+                                          int64_t num_samples, int64_t *out_samples_indices,
+                                          int32_t *out_num_live_points, void *workspace, int64_t workspace_bytes,
+                                          nsb200_stream_t stream) {
+    if (M <= 0) return 0;
+    if (M + 1 >= (1ll << 31)) return fail("count_crossed_edges supports M < 2^31 - 1");
+    if (num_samples > M) return fail("num_samples (%lld) > M (%lld)", (long long) num_samples, (long long) M);
+    if (!sender_node_idx || !log_L || !out_samples_indices || !out_num_live_points || !workspace) return fail("NULL pointer");
+    if (workspace_bytes < (int64_t) tree_workspace_bytes(M)) return fail("workspace too small");
+    cudaStream_t st = (cudaStream_t) stream;
+    const long long n = M + 1;
+    SortWorkspace w = carve_sort_workspace(workspace, n);
+    char *p = (char *) w.hist + align256((size_t) 256 * w.nblocks * 4);
+    int *outdeg = (int *) p;
+    p += align256((size_t) n * 4);
+    int *tile_sums = (int *) p;
+    const int tiles = (int) ((n + kScanTile - 1) / kScanTile);
+    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(log_L, M, 1, w.keys[0], w.vals[0]);
+    radix_sort_pairs(w, n, st);
+    NSB_CUDA(cudaMemsetAsync(outdeg, 0, (size_t) n * 4, st));
+    k_out_degree<<<grid_for(M, 256), 256, 0, st>>>((const long long *) sender_node_idx, M, outdeg);
+    k_tree_tile_sums<<<tiles, kScanThreads, 0, st>>>(w.vals[0], outdeg, n, tile_sums);
+    k_scan_u32_excl<<<1, 1024, 0, st>>>((uint32_t *) tile_sums, tiles);
+    k_tree_apply<<<tiles, kScanThreads, 0, st>>>(w.vals[0], outdeg, n, tile_sums, M, num_samples,
+                                                 (long long *) out_samples_indices, out_num_live_points);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static NsEvidenceCalc init_evidence_calc() {
+    NsEvidenceCalc c;
+    c.log_L = -INFINITY;
+    c.log_X_mean = 0.0;
+    c.log_X2_mean = 0.0;
+    c.log_Z_mean = -INFINITY;
+    c.log_ZX_mean = -INFINITY;
+    c.log_Z2_mean = -INFINITY;
+    c.log_dZ_mean = -INFINITY;
+    c.log_dZ2_mean = -INFINITY;
+    return c;
+}
+
+extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *log_L, const double *num_live_points,
+                                     int64_t M, NsEvidenceCalc *out_final, double *out_per_sample, void *workspace,
+                                     int64_t workspace_bytes, nsb200_stream_t stream) {
+    (void) workspace;
+    (void) workspace_bytes;
+    if (M < 0) return fail("M < 0");
+    if (M > 0 && (!log_L || !num_live_points)) return fail("NULL input");
+    if (!out_final) return fail("out_final is NULL");
+    EvSeq q;
+    q.la = log_L;
+    q.na = num_live_points;
+    q.len_a = M;
+    q.n_const_a = 0.0;
+    q.lb = nullptr;
+    q.len_b = 0;
+    q.n_start_b = 0.0;
+    EvOut o;
+    o.mid = nullptr;
+    o.mark = -1;
+    o.fin = out_final;
+    o.per_sample = out_per_sample;
+    k_evidence_stats<<<1, 1024, 0, (cudaStream_t) stream>>>(q, init ? *init : init_evidence_calc(), o);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_logsumexp(const double *x, int64_t n, double *out, void *workspace, int64_t workspace_bytes,
+                                nsb200_stream_t stream) {
+    (void) workspace;
+    (void) workspace_bytes;
+    if (!out) return fail("out is NULL");
+    if (n > 0 && !x) return fail("x is NULL");
+    k_logsumexp<<<1, 1024, 0, (cudaStream_t) stream>>>(x, n, out);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// engine
+// -------------------------------------------------------------------------------------------------
+// Slice kernel launched from the loop: key, contour and the current live buffer come from the
+// device-resident control block, so the host never has to know them.
+template <int DPL>
+__global__ void __launch_bounds__(kThreadsPerBlock)
+k_slice_chains_engine(NsModelDesc model, const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
+                      const double *seed_table, double *packed, long long row_doubles, long long N,
+                      long long begin, long long end, int S, int k, int midpoint, int G) {
+    extern __shared__ double smem[];
+    if (!ctl->active) return;
+    const LiveSet &live = ctl->cur ? live1 : live0;
+    SliceArgs a;
+    a.model = model;
+    a.key = ctl->sample_key;
+    a.contour = &ctl->contour;
+    a.live_U = live.U;
+    a.live_logL = live.logL;
+    a.seed_table = seed_table;
+    a.out_U = nullptr;
+    a.out_logL = nullptr;
+    a.out_nevals = nullptr;
+    a.ph_U = nullptr;
+    a.ph_logL = nullptr;
+    a.N = N;
+    a.chain_begin = begin;
+    a.chain_end = end;
+    a.S = S;
+    a.k = k;
+    a.midpoint = midpoint;
+    a.G = G;
+    a.packed = packed;
+    a.packed_row_doubles = row_doubles;
+    slice_chains_body<DPL>(a, smem);
+}
+
+__global__ void k_fill_f64(double *p, long long n, double v) {
+    for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void k_init_ctl(DevCtl *ctl, Key key) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->key = key;
+    ctl->next_idx = 0;
+    ctl->num_samples = 0;
+    ctl->iteration = 0;
+    ctl->sample_key = Key{0, 0};
+    ctl->contour = -__longlong_as_double(0x7FF0000000000000ll);
+    ctl->disc_start = 0;
+    ctl->ph_start = 0;
+    ctl->sender = 0;
+    ctl->active = 1;
+    ctl->cur = 1;  // the init scatter writes live0 ("other" buffer of cur = 1)
+}
+
+__global__ void k_set_cur(DevCtl *ctl, int cur) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctl->cur = cur;
+}
+
+// packs k_draw outputs into packed rows [U[D], logL, nevals]
+__global__ void k_pack_rows(const double *U, const double *logL, const long long *nev, long long n, int D,
+                            double *packed, long long row_doubles) {
+    const long long total = n * (D + 2);
+    for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long) gridDim.x * blockDim.x) {
+        const long long i = t / (D + 2);
+        const int j = (int) (t - i * (D + 2));
+        double v;
+        if (j < D) v = U[i * D + j];
+        else if (j == D) v = logL[i];
+        else v = __longlong_as_double(nev[i]);
+        packed[i * row_doubles + j] = v;
+    }
+}
+
+struct NsEngine {
+    NsEngineConfig cfg;
+    int D = 0;
+    long long N = 0, m = 0, k = 0, cap = 0;
+    long long rows_per_rank = 0, row_doubles = 0, packed_rows = 0;
+    LiveSet live[2];
+    DeadStore dead;
+    DevCtl *ctl = nullptr;
+    NsRegister *reg = nullptr;       // device
+    NsRegister *reg_host = nullptr;  // pinned
+    DevCtl *ctl_host = nullptr;      // pinned
+    double *seed_table = nullptr;
+    double *packed = nullptr;
+    unsigned *rank = nullptr;
+    NsTermCond tc;
+    std::vector<void *> allocs;
+    // profiling
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    double slice_ms = 0.0;
+    long long slice_launches = 0, all_launches = 0;
+    bool initialised = false;
+};
+
+template <typename T>
+static int dev_alloc(NsEngine *e, T **p, size_t count) {
+    void *q = nullptr;
+    cudaError_t err = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
+    if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
+    e->allocs.push_back(q);
+    *p = (T *) q;
+    return 0;
+}
+
+extern "C" void nsb200_engine_destroy(NsEngine *e) {
+    if (!e) return;
+    for (void *p : e->allocs) cudaFree(p);
+    if (e->reg_host) cudaFreeHost(e->reg_host);
+    if (e->ctl_host) cudaFreeHost(e->ctl_host);
+    for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    delete e;
+}
+
+extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
+    if (!cfg || !out) return fail("NULL argument");
+    if (check_model(&cfg->model)) return 1;
+    Geometry g;
+    if (pick_geometry(cfg->model.D, g)) return 1;
+    if (cfg->num_live_points < 2) return fail("num_live_points must be >= 2");
+    if (cfg->shell_size < 1 || cfg->shell_size > cfg->num_live_points) return fail("bad shell_size %lld", (long long) cfg->shell_size);
+    if (cfg->num_slices < 1) return fail("num_slices should be >= 1, got %d", cfg->num_slices);
+    if (cfg->num_phantom < 0 || cfg->num_phantom >= cfg->num_slices)
+        return fail("expected 0 <= num_phantom < num_slices, got %d, %d", cfg->num_phantom, cfg->num_slices);
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size) return fail("bad rank/world_size");
+    if (cfg->shell_size % cfg->world_size != 0)
+        return fail("shell_size %lld is not a multiple of world_size %d (round_up_num_live_points)", (long long) cfg->shell_size, cfg->world_size);
+    const long long block = cfg->shell_size * (1 + (long long) cfg->num_phantom);
+    if (cfg->max_samples < cfg->num_live_points || cfg->max_samples < block)
+        return fail("max_samples %lld too small", (long long) cfg->max_samples);
+    if (cfg->num_live_points >= (1ll << 31)) return fail("num_live_points too large");
+    NsEngine *e = new NsEngine();
+    e->cfg = *cfg;
+    e->D = cfg->model.D;
+    e->N = cfg->num_live_points;
+    e->m = cfg->shell_size;
+    e->k = cfg->num_phantom;
+    e->cap = cfg->max_samples;
+    e->rows_per_rank = e->m / cfg->world_size;
+    e->row_doubles = (e->D + 2) + e->k * (e->D + 1);
+    e->packed_rows = e->N > e->m ? e->N : e->m;  // the init pass packs all N prior draws
+    const size_t D = e->D;
+    int rc = 0;
+    for (int b = 0; b < 2 && !rc; ++b) {
+        rc |= dev_alloc(e, &e->live[b].sender, e->N);
+        rc |= dev_alloc(e, &e->live[b].U, e->N * D);
+        rc |= dev_alloc(e, &e->live[b].logL_constraint, e->N);
+        rc |= dev_alloc(e, &e->live[b].logL, e->N);
+        rc |= dev_alloc(e, &e->live[b].nevals, e->N);
+    }
+    e->dead.capacity = e->cap;
+    if (!rc) rc |= dev_alloc(e, &e->dead.sender, e->cap);
+    if (!rc) rc |= dev_alloc(e, &e->dead.logL, e->cap);
+    if (!rc) rc |= dev_alloc(e, &e->dead.U, e->cap * D);
+    if (!rc) rc |= dev_alloc(e, &e->dead.nevals, e->cap);
+    if (!rc) rc |= dev_alloc(e, &e->dead.phantom, e->cap);
+    if (!rc) rc |= dev_alloc(e, &e->ctl, 1);
+    if (!rc) rc |= dev_alloc(e, &e->reg, 1);
+    if (!rc) rc |= dev_alloc(e, &e->seed_table, e->N);
+    if (!rc) rc |= dev_alloc(e, &e->packed, (size_t) e->packed_rows * e->row_doubles);
+    if (!rc) rc |= dev_alloc(e, &e->rank, e->N);
+    if (!rc && cudaMallocHost((void **) &e->reg_host, sizeof(NsRegister)) != cudaSuccess) rc = fail("cudaMallocHost failed");
+    if (!rc && cudaMallocHost((void **) &e->ctl_host, sizeof(DevCtl)) != cudaSuccess) rc = fail("cudaMallocHost failed");
+    if (rc) {
+        nsb200_engine_destroy(e);
+        return 1;
+    }
+    *out = e;
+    return 0;
+}
+
+static NsRegister init_register_host() {
+    NsRegister r;
+    memset(&r, 0, sizeof(r));
+    r.evidence_calc = init_evidence_calc();
+    r.evidence_calc_with_remaining = init_evidence_calc();
+    r.log_L_contour = -INFINITY;
+    r.efficiency = 0.0;
+    r.relative_spread = INFINITY;
+    r.absolute_spread = INFINITY;
+    r.peak_log_XL = -INFINITY;
+    return r;
+}
+
+// _main_ns_thread lowers max_samples by one iteration's space (sharded_static.py:464-470).
+static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
+    NsTermCond t;
+    if (tc) t = *tc;
+    else {
+        memset(&t, 0, sizeof(t));
+        t.mask = (1u << 3) | (1u << 4);
+        t.dlogZ = log(1.0 + 1e-3);
+        t.max_samples = (double) e->cap;
+    }
+    if (t.mask & (1u << 4)) {
+        const double lim = (double) (e->cap - e->m * (1 + e->k));
+        if (t.max_samples > lim) t.max_samples = lim;
+    }
+    return t;
+}
+
+extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
+                                  nsb200_stream_t stream) {
+    if (!e || !key) return fail("NULL argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    const int D = e->D;
+    e->tc = effective_term_cond(e, term_cond);
+    e->slice_ms = 0.0;
+    e->slice_launches = 0;
+    e->all_launches = 0;
+    e->ev_used = 0;
+    // create_init_state (initialisation.py:38-47): empty dead store, key split
+    NSB_CUDA(cudaMemsetAsync(e->dead.sender, 0, (size_t) e->cap * 8, st));
+    NSB_CUDA(cudaMemsetAsync(e->dead.U, 0, (size_t) e->cap * D * 8, st));
+    NSB_CUDA(cudaMemsetAsync(e->dead.nevals, 0, (size_t) e->cap * 8, st));
+    NSB_CUDA(cudaMemsetAsync(e->dead.phantom, 0, (size_t) e->cap, st));
+    k_fill_f64<<<592, 256, 0, st>>>(e->dead.logL, e->cap, INFINITY);
+    const Key k0{key[0], key[1]};
+    const Key key1 = split_child(k0, 0), sample_key = split_child(k0, 1);
+    k_init_ctl<<<1, 1, 0, st>>>(e->ctl, key1);
+    if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
+    // N prior draws (replicated on every rank), packed, ranked (stable argsort) and scattered
+    double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
+    long long *tmpN = e->live[1].nevals;
+    if (launch_draw(&e->cfg.model, sample_key, nullptr, 0, e->N, tmpU, tmpL, tmpN, 0, st)) return 1;
+    k_pack_rows<<<592, 256, 0, st>>>(tmpU, tmpL, tmpN, e->N, D, e->packed, e->row_doubles);
+    k_merge_rank<<<grid_for(e->N, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
+                                                       e->N, e->N, e->rank);
+    DeadStore nodead = e->dead;
+    k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->N, e->N, 0,
+                                          e->rank, nodead);
+    k_set_cur<<<1, 1, 0, st>>>(e->ctl, 0);
+    // create_init_termination_register + the loop-entry no_seed_points and first cond
+    *e->reg_host = init_register_host();
+    NSB_CUDA(cudaMemcpyAsync(e->reg, e->reg_host, sizeof(NsRegister), cudaMemcpyHostToDevice, st));
+    k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
+                                         e->N, e->tc, 1);
+    NSB_LAUNCH_CHECK();
+    e->all_launches += 9;
+    e->initialised = true;
+    return 0;
+}
+
+static cudaEvent_t next_event(NsEngine *e) {
+    if (e->ev_used == e->ev_pool.size()) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        e->ev_pool.push_back(ev);
+    }
+    return e->ev_pool[e->ev_used++];
+}
+
+// resolves pending event pairs into slice_ms (requires the stream to be idle)
+static void drain_events(NsEngine *e) {
+    for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]) == cudaSuccess) e->slice_ms += ms;
+    }
+    e->ev_used = 0;
+}
+
+extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
+    if (!e || !e->initialised) return fail("engine not initialised");
+    cudaStream_t st = (cudaStream_t) stream;
+    const int D = e->D;
+    k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender);
+    k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
+    NSB_LAUNCH_CHECK();
+    // this rank's chains -> its block of the gather buffer
+    Geometry g;
+    if (pick_geometry(D, g)) return 1;
+    const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
+    cudaEvent_t e0 = next_event(e), e1 = next_event(e);
+    cudaEventRecord(e0, st);
+    {
+        const size_t smem = sampler_smem_bytes(e->cfg.model, g, true);
+        const int per_block = kThreadsPerBlock / g.G;
+        NSB_DISPATCH_DPL(g.DPL, {
+            if (set_smem(k_slice_chains_engine<kDPL>, smem)) return 1;
+            k_slice_chains_engine<kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, st>>>(
+                e->cfg.model, e->ctl, e->live[0], e->live[1], e->seed_table, e->packed + begin * e->row_doubles,
+                e->row_doubles, e->N, begin, end, e->cfg.num_slices, e->cfg.num_phantom, e->cfg.midpoint_shrink, g.G);
+        });
+    }
+    cudaEventRecord(e1, st);
+    NSB_LAUNCH_CHECK();
+    e->slice_launches += 1;
+    e->all_launches += 3;
+    return 0;
+}
+
+extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
+    if (!e || !e->initialised) return fail("engine not initialised");
+    cudaStream_t st = (cudaStream_t) stream;
+    const int D = e->D;
+    k_merge_rank<<<grid_for(e->N, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
+                                                       e->m, e->N, e->rank);
+    k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
+                                          (int) e->k, e->rank, e->dead);
+    k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
+                                         e->N, e->tc, 0);
+    NSB_LAUNCH_CHECK();
+    e->all_launches += 3;
+    return 0;
+}
+
+extern "C" int nsb200_engine_step(NsEngine *e, nsb200_stream_t stream) {
+    if (!e) return fail("NULL engine");
+    if (e->cfg.world_size != 1) return fail("engine_step requires world_size == 1; use step_begin / all-gather / step_end");
+    if (nsb200_engine_step_begin(e, stream)) return 1;
+    return nsb200_engine_step_end(e, stream);
+}
+
+extern "C" int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *rows_per_rank, int64_t *row_doubles) {
+    if (!e) return fail("NULL engine");
+    if (buf) *buf = e->packed;
+    if (rows_per_rank) *rows_per_rank = e->rows_per_rank;
+    if (row_doubles) *row_doubles = e->row_doubles;
+    return 0;
+}
+
+extern "C" int nsb200_engine_register(NsEngine *e, NsRegister *out, nsb200_stream_t stream) {
+    if (!e || !out) return fail("NULL argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    NSB_CUDA(cudaMemcpyAsync(e->reg_host, e->reg, sizeof(NsRegister), cudaMemcpyDeviceToHost, st));
+    NSB_CUDA(cudaStreamSynchronize(st));
+    drain_events(e);
+    *out = *e->reg_host;
+    return 0;
+}
+
+extern "C" int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream) {
+    if (!e || !e->initialised) return fail("engine not initialised");
+    cudaStream_t st = (cudaStream_t) stream;
+    k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->N, e->D, 1);
+    k_finalize_ctl<<<1, 1, 0, st>>>(e->ctl, e->N, e->cap);
+    NSB_LAUNCH_CHECK();
+    e->all_launches += 2;
+    return 0;
+}
+
+extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
+                                 int64_t max_iterations, NsRegister *out_register, nsb200_stream_t stream) {
+    if (!e) return fail("NULL engine");
+    if (e->cfg.world_size != 1) return fail("engine_run requires world_size == 1");
+    if (nsb200_engine_init(e, key, term_cond, stream)) return 1;
+    NsRegister r;
+    if (nsb200_engine_register(e, &r, stream)) return 1;
+    // Steps are no-ops on the device once the register says done, so the host may run ahead: it
+    // enqueues a few bodies between polls instead of synchronising after each one.
+    const int lookahead = 4;
+    long long launched = 0;
+    while (!r.done && (max_iterations < 0 || launched < max_iterations)) {
+        long long burst = lookahead;
+        if (max_iterations >= 0 && launched + burst > max_iterations) burst = max_iterations - launched;
+        for (long long b = 0; b < burst; ++b) {
+            if (nsb200_engine_step(e, stream)) return 1;
+        }
+        launched += burst;
+        if (nsb200_engine_register(e, &r, stream)) return 1;
+    }
+    if (nsb200_engine_finalize(e, stream)) return 1;
+    NSB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    if (out_register) *out_register = r;
+    return 0;
+}
+
+extern "C" int nsb200_engine_state(NsEngine *e, NsStateView *out, nsb200_stream_t stream) {
+    if (!e || !out) return fail("NULL argument");
+    cudaStream_t st = (cudaStream_t) stream;
+    NSB_CUDA(cudaMemcpyAsync(e->ctl_host, e->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
+    NSB_CUDA(cudaStreamSynchronize(st));
+    drain_events(e);
+    const LiveSet &live = e->live[e->ctl_host->cur];
+    out->sender_node_idx = (int64_t *) e->dead.sender;
+    out->log_L = e->dead.logL;
+    out->U_samples = e->dead.U;
+    out->num_likelihood_evaluations = (int64_t *) e->dead.nevals;
+    out->phantom = e->dead.phantom;
+    out->live_sender_node_idx = (int64_t *) live.sender;
+    out->live_U = live.U;
+    out->live_log_L_constraint = live.logL_constraint;
+    out->live_log_L = live.logL;
+    out->live_num_likelihood_evaluations = (int64_t *) live.nevals;
+    out->key[0] = e->ctl_host->key.a;
+    out->key[1] = e->ctl_host->key.b;
+    out->next_sample_idx = e->ctl_host->next_idx;
+    out->num_samples = e->ctl_host->num_samples;
+    out->capacity = e->cap;
+    out->num_live_points = e->N;
+    out->D = e->D;
+    out->reserved = 0;
+    return 0;
+}
+
+extern "C" int nsb200_engine_slice_profile(NsEngine *e, double *slice_ms, int64_t *slice_launches, int64_t *all_launches) {
+    if (!e) return fail("NULL engine");
+    if (slice_ms) *slice_ms = e->slice_ms;
+    if (slice_launches) *slice_launches = e->slice_launches;
+    if (all_launches) *all_launches = e->all_launches;
+    return 0;
+}

@@ -1,0 +1,180 @@
+"""
+Model / Prior with the reference's signatures (/root/reference/src/jaxns/framework/model.py:24-208,
+framework/prior.py:65-161, framework/ops.py:21-36,240-326) for registered likelihood families.
+
+`prior_model` stays a generator function that yields Prior objects and returns the likelihood
+inputs; `log_likelihood` must be a RegisteredLikelihood (jaxns_b200.likelihoods).  Arbitrary traced
+JAX likelihoods are SURVEY §8(f) row 1 and raise NotImplementedError.
+"""
+import ctypes
+from typing import Callable, List, Optional
+
+import numpy as np
+import torch
+
+from jaxns_b200 import _lib, distributions
+from jaxns_b200.likelihoods import RegisteredLikelihood
+
+__all__ = ["Prior", "Model"]
+
+
+class _Var:
+    """Placeholder sent into the prior_model generator for a yielded Prior."""
+
+    def __init__(self, index: int, size: int, name: Optional[str]):
+        self.index, self.size, self.name = index, size, name
+
+
+class Prior:
+    """Prior(dist_or_value, name=None) (framework/prior.py:65-161)."""
+
+    def __init__(self, dist_or_value, name: Optional[str] = None):
+        self.name = name
+        self.dist = distributions.from_any(dist_or_value)
+
+    def parametrised(self, random_init: bool = False):
+        raise NotImplementedError("Parametrised priors are out of the hot-path scope (SURVEY §2.1).")
+
+
+class Model:
+    """Model(prior_model, log_likelihood, params=None) (framework/model.py:29-41)."""
+
+    def __init__(self, prior_model: Callable, log_likelihood, params=None):
+        if params is not None:
+            raise NotImplementedError("Parametrised models are out of the hot-path scope (SURVEY §2.1).")
+        if not isinstance(log_likelihood, RegisteredLikelihood):
+            raise NotImplementedError(
+                "log_likelihood must be a registered family (jaxns_b200.likelihoods.*); arbitrary traced "
+                "likelihoods need the split propose/accept path (SURVEY §8f row 1).")
+        self.prior_model = prior_model
+        self.log_likelihood = log_likelihood
+        self._priors: List[Prior] = []
+        gen = prior_model()
+        try:
+            p = next(gen)
+            while True:
+                if not isinstance(p, Prior):
+                    raise TypeError(f"prior_model must yield Prior objects, got {type(p)}")
+                v = _Var(len(self._priors), p.dist.event_size(), p.name)
+                self._priors.append(p)
+                p = gen.send(v)
+        except StopIteration as stop:
+            ret = stop.value
+        ret = ret if isinstance(ret, tuple) else (ret,)
+        if [getattr(r, "index", None) for r in ret] != list(range(len(self._priors))):
+            raise NotImplementedError("prior_model must return its yielded variables in order: the registered "
+                                      "likelihood consumes their concatenation.")
+        kinds = {p.dist.prior_kind for p in self._priors}
+        if len(kinds) != 1:
+            raise NotImplementedError("Mixing Uniform and Normal priors in one model is not supported yet.")
+        self._prior_kind = kinds.pop()
+        self._a = np.concatenate([p.dist.quantile_params()[1] for p in self._priors])
+        self._b = np.concatenate([p.dist.quantile_params()[2] for p in self._priors])
+        self._D = int(self._a.size)
+        self._params_host = np.ascontiguousarray(log_likelihood.pack(self._D), np.float64)
+        self._dev = None
+
+    # -- reference properties -----------------------------------------------------------------
+    @property
+    def U_ndims(self) -> int:
+        return self._D
+
+    @property
+    def U_placeholder(self):
+        return np.zeros(self._D)
+
+    @property
+    def params(self):
+        return {}
+
+    @property
+    def num_params(self) -> int:
+        return 0
+
+    def __hash__(self):
+        return id(self)
+
+    # -- C-ABI descriptor -----------------------------------------------------------------------
+    def host_arrays(self):
+        """(family, D, prior_kind, K, prior_a, prior_b, params) as host numpy: what NsModelDesc packs."""
+        return (self.log_likelihood.family, self._D, self._prior_kind, self.log_likelihood.K, self._a, self._b,
+                self._params_host)
+
+    def desc(self) -> _lib.NsModelDesc:
+        _lib.require_cuda()
+        if self._dev is None:
+            a = torch.from_numpy(self._a).cuda()
+            b = torch.from_numpy(self._b).cuda()
+            p = torch.from_numpy(self._params_host if self._params_host.size else np.zeros(1)).cuda()
+            self._dev = (a, b, p)
+        a, b, p = self._dev
+        return _lib.NsModelDesc(self.log_likelihood.family, self._D, self._prior_kind, self.log_likelihood.K,
+                                a.data_ptr(), b.data_ptr(), p.data_ptr(), int(self._params_host.size))
+
+    # -- reference methods ----------------------------------------------------------------------
+    def _forward_batch(self, U: torch.Tensor, want_X: bool):
+        _lib.require_cuda()
+        U = torch.as_tensor(U, dtype=torch.float64, device="cuda")
+        batched = U.dim() == 2
+        U2 = U.reshape(-1, self._D).contiguous()
+        n = U2.shape[0]
+        logL = torch.empty(n, dtype=torch.float64, device="cuda")
+        X = torch.empty_like(U2) if want_X else None
+        d = self.desc()
+        _lib.check(_lib.lib().nsb200_forward_batch(ctypes.byref(d), _lib.ptr(U2), ctypes.c_int64(n), _lib.ptr(logL),
+                                                    _lib.ptr(X), _lib.stream_arg()))
+        if not batched:
+            return logL[0], (X[0] if want_X else None)
+        return logL, X
+
+    def forward(self, U, allow_nan: bool = False):
+        """log L at U (framework/model.py:167-176); accepts [D] or a batch [n, D] (= vmap(forward))."""
+        if allow_nan:
+            raise NotImplementedError("allow_nan=True is not supported by the fused kernel (NaN -> -inf).")
+        return self._forward_batch(U, False)[0]
+
+    def log_prob_likelihood(self, U, allow_nan: bool = False):
+        return self.forward(U, allow_nan)
+
+    def transform(self, U):
+        """U -> X dict keyed by prior names (framework/model.py:155-159)."""
+        X = self._forward_batch(U, True)[1]
+        out, o = {}, 0
+        for i, p in enumerate(self._priors):
+            n = p.dist.event_size()
+            if p.name is not None:
+                out[p.name] = X[..., o:o + n]
+            o += n
+        return out
+
+    def transform_parametrised(self, U):
+        return {}
+
+    def prepare_input(self, U):
+        return (self._forward_batch(U, True)[1],)
+
+    def sample_U(self, key):
+        """uniform(split(key, 2)[1], (D,)) (framework/model.py:122-138, context.py:107-109)."""
+        from jaxns_b200 import random
+        return random.uniform(random.split(key, 2)[1], self._D)
+
+    def log_prob_prior(self, U):
+        """Prior log density of the transformed point (framework/model.py:178-187); host-side helper
+        used only for NestedSamplerResults.log_posterior_density."""
+        X = self._forward_batch(U, True)[1]
+        Xh = X.detach().cpu().numpy()
+        out = np.zeros(Xh.shape[:-1])
+        o = 0
+        for p in self._priors:
+            n = p.dist.event_size()
+            out = out + p.dist.log_prob(Xh[..., o:o + n])
+            o += n
+        return torch.from_numpy(np.asarray(out)).cuda()
+
+    def sanity_check(self, key, S: int):
+        from jaxns_b200 import random
+        U = random.uniform(key, S * self._D).reshape(S, self._D)
+        logL = self.forward(U)
+        if torch.isnan(logL).any():
+            raise AssertionError("NaN log-likelihood in sanity check")
+        return True

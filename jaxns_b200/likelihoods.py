@@ -1,0 +1,97 @@
+"""
+Registered likelihood families: objects a user passes as `log_likelihood` to Model so that the fused
+slice kernel can evaluate them as device functions (include/nsb200.h NSB200_FAM_*).  Each mirrors a
+likelihood used by the reference's benchmarks / examples:
+
+* DenseGaussianLikelihood   tfpd.MultivariateNormalTriL(loc, chol(cov)).log_prob
+                            (/root/reference/docs/papers/phantom-powered-nested-sampling/run_experiment.py:23-50,
+                             src/jaxns/tests/conftest.py:217-251)
+* GaussianMixtureLikelihood logaddexp of diagonal Gaussians (benchmarks/difficult_problems/main.py:95-125)
+* EggBoxLikelihood          (2 + prod cos(theta/2))^5 (docs/examples/egg_box.ipynb cell 2)
+* RosenbrockLikelihood      benchmarks/difficult_problems/main.py:69-92
+* GaussianShellsLikelihood  docs/examples/gaussian_shells.ipynb cell 2
+"""
+import numpy as np
+
+from jaxns_b200 import _consts
+
+
+class RegisteredLikelihood:
+    """Base class; `family` and `pack(D)` define the C-ABI model descriptor."""
+    family: int
+    K: int = 0
+    __nsb200_family__ = True
+
+    def pack(self, D: int) -> np.ndarray:
+        return np.zeros(0)
+
+    def __call__(self, *args):
+        raise RuntimeError("Registered likelihoods are evaluated on the device; use Model.forward(U).")
+
+
+class DenseGaussianLikelihood(RegisteredLikelihood):
+    family = _consts.FAM_GAUSS_DENSE
+
+    def __init__(self, loc, covariance_matrix=None, scale_tril=None):
+        self.loc = np.atleast_1d(np.asarray(loc, np.float64))
+        if (covariance_matrix is None) == (scale_tril is None):
+            raise ValueError("Give exactly one of covariance_matrix / scale_tril.")
+        if scale_tril is None:
+            scale_tril = np.linalg.cholesky(np.asarray(covariance_matrix, np.float64))
+        self.scale_tril = np.tril(np.asarray(scale_tril, np.float64))
+
+    def pack(self, D: int) -> np.ndarray:
+        if self.loc.size != D or self.scale_tril.shape != (D, D):
+            raise ValueError(f"Gaussian likelihood is {self.loc.size}-D but the prior has {D} dims.")
+        L = self.scale_tril
+        Linv = np.tril(np.linalg.solve(L, np.eye(D)))
+        c = -np.sum(np.log(np.diag(L))) - 0.5 * D * np.log(2.0 * np.pi)
+        return np.concatenate([[c], self.loc, Linv.reshape(-1)])
+
+
+class GaussianMixtureLikelihood(RegisteredLikelihood):
+    """log sum_k w_k N(x | mean_k, diag(var_k)); weights default to 1 (the reference's spike-and-slab
+    adds two normalised densities)."""
+    family = _consts.FAM_GAUSS_MIX_DIAG
+
+    def __init__(self, means, variances, log_weights=None):
+        self.means = np.atleast_2d(np.asarray(means, np.float64))
+        self.K, D = self.means.shape
+        v = np.asarray(variances, np.float64)
+        if v.ndim == 1 and v.size == self.K:
+            v = np.repeat(v[:, None], D, axis=1)
+        self.variances = np.broadcast_to(v, (self.K, D)).copy()
+        self.log_weights = np.zeros(self.K) if log_weights is None else np.asarray(log_weights, np.float64)
+
+    def pack(self, D: int) -> np.ndarray:
+        if self.means.shape[1] != D:
+            raise ValueError(f"Mixture is {self.means.shape[1]}-D but the prior has {D} dims.")
+        rows = []
+        for k in range(self.K):
+            logc = self.log_weights[k] - 0.5 * np.sum(np.log(2.0 * np.pi * self.variances[k]))
+            rows.append(np.concatenate([[logc], self.means[k], 1.0 / np.sqrt(self.variances[k])]))
+        return np.concatenate(rows)
+
+
+class EggBoxLikelihood(RegisteredLikelihood):
+    family = _consts.FAM_EGGBOX
+
+
+class RosenbrockLikelihood(RegisteredLikelihood):
+    family = _consts.FAM_ROSENBROCK
+
+
+class GaussianShellsLikelihood(RegisteredLikelihood):
+    family = _consts.FAM_SHELLS
+
+    def __init__(self, centres, radii, widths):
+        self.centres = np.atleast_2d(np.asarray(centres, np.float64))
+        self.K = self.centres.shape[0]
+        self.radii = np.broadcast_to(np.asarray(radii, np.float64), (self.K,)).copy()
+        self.widths = np.broadcast_to(np.asarray(widths, np.float64), (self.K,)).copy()
+
+    def pack(self, D: int) -> np.ndarray:
+        if self.centres.shape[1] != D:
+            raise ValueError(f"Shells are {self.centres.shape[1]}-D but the prior has {D} dims.")
+        return np.concatenate([np.concatenate([[self.widths[k], self.radii[k]], self.centres[k]])
+                               for k in range(self.K)])

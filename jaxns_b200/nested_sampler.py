@@ -1,0 +1,306 @@
+"""
+ShardedStaticNestedSampler: the static nested-sampling engine behind the reference's interface
+(/root/reference/src/jaxns/nested_samplers/sharded/sharded_static.py:577-851), driving the
+C-ABI engine (include/nsb200.h, nsb200_engine_*).  One process per GPU; with torch.distributed
+initialised (world_size > 1) the m chains of an iteration are split into contiguous blocks per rank
+exactly like PartitionSpec('shard') on split(sample_key, m) (:104-110,128) and the packed new rows
+are all-gathered over NCCL between the two halves of a step.
+"""
+import ctypes
+import dataclasses
+import math
+import warnings
+from typing import Any, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from jaxns_b200 import _lib, termination
+from jaxns_b200.internals.shrinkage_statistics import compute_evidence_stats, logsumexp
+from jaxns_b200.internals.stats import effective_sample_size_kish, linear_to_log_stats
+from jaxns_b200.internals.tree_structure import SampleTreeGraph, count_crossed_edges
+from jaxns_b200.samplers import AbstractSampler, UniDimSliceSampler
+from jaxns_b200.types import (NestedSamplerResults, NestedSamplerState, Sample, SampleCollection,
+                              TerminationCondition, TerminationRegister)
+
+__all__ = ["ShardedStaticNestedSampler"]
+
+
+def round_up_num_live_points(init_num_live_points, shell_frac, num_devices):
+    """sharded_static.py:577-584"""
+    num_live_points = int(init_num_live_points)
+    while True:
+        shell_size = int(num_live_points * shell_frac)
+        if shell_size % num_devices == 0:
+            break
+        num_live_points += 1
+    return num_live_points
+
+
+def round_up_max_samples(init_max_samples, num_discard, num_phantom_points):
+    """sharded_static.py:587-594"""
+    max_samples = int(init_max_samples)
+    block_size = num_discard * (1 + num_phantom_points)
+    while True:
+        if max_samples % block_size == 0:
+            break
+        max_samples += 1
+    return max_samples
+
+
+def _dist_info():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def get_samples(key, mesh, sampler: AbstractSampler, sampler_state: Any, log_L_contour, num_samples: int
+                ) -> Tuple[Sample, Sample]:
+    """get_samples (sharded_static.py:88-129).  `mesh` = (rank, world_size) or None; each rank
+    evaluates its contiguous block of chains and the blocks are all-gathered."""
+    rank, world = mesh if mesh is not None else _dist_info()
+    per = num_samples // world
+    sample, phantom = sampler.get_samples_batch(key, log_L_contour, sampler_state, num_samples,
+                                                chain_begin=rank * per, chain_end=(rank + 1) * per)
+    if world == 1:
+        return sample, phantom
+    import torch.distributed as dist
+
+    def gather(x):
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous())
+        return out
+
+    return Sample(*[gather(x) for x in sample]), Sample(*[gather(x) for x in phantom])
+
+
+class _DevView:
+    """Zero-copy torch view of engine-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner):
+        self.__cuda_array_interface__ = dict(shape=tuple(int(s) for s in shape), typestr=typestr,
+                                             data=(int(ptr), False), version=2)
+        self._owner = owner
+
+
+def _view(ptr, shape, typestr, owner) -> torch.Tensor:
+    if int(np.prod(shape)) == 0:
+        dt = {"<f8": torch.float64, "<i8": torch.int64, "|u1": torch.uint8}[typestr]
+        return torch.empty(tuple(shape), dtype=dt, device="cuda")
+    return torch.as_tensor(_DevView(ptr, shape, typestr, owner), device="cuda")
+
+
+class _Engine:
+    """RAII wrapper of NsEngine*."""
+
+    def __init__(self, cfg: _lib.NsEngineConfig, keepalive):
+        self._h = ctypes.c_void_p()
+        self._keepalive = keepalive
+        _lib.check(_lib.lib().nsb200_engine_create(ctypes.byref(cfg), ctypes.byref(self._h)))
+
+    @property
+    def h(self):
+        return self._h
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.lib().nsb200_engine_destroy(self._h)
+                self._h = ctypes.c_void_p()
+        except Exception:  # interpreter shutdown
+            pass
+
+
+@dataclasses.dataclass(eq=False)
+class ShardedStaticNestedSampler:
+    model: Any
+    max_samples: int
+    init_efficiency_threshold: float
+    sampler: AbstractSampler
+    num_live_points: int
+    shell_fraction: Optional[float] = None
+    num_dynamic_refinement_iterations: int = 0
+    refine_threshold: float = 0.01
+    devices: Optional[List[Any]] = None
+    verbose: bool = False
+
+    def __post_init__(self):
+        if self.shell_fraction is None:
+            self.shell_fraction = 0.5
+        self.shell_fraction = max(self.shell_fraction, 1. / self.num_live_points)
+        if (self.shell_fraction <= 0.) or (self.shell_fraction > 1.):
+            raise ValueError(
+                f"Expected 0 < shell_fraction <= 1, got {self.shell_fraction}. Best to keep it around 0.5.")
+        self._rank, self._world = _dist_info()
+        if self.devices is None:
+            self.devices = list(range(self._world))
+        if len(self.devices) > 1 and self._rank == 0:
+            print(f"Running over {len(self.devices)} devices.")
+        self.num_live_points = round_up_num_live_points(
+            init_num_live_points=self.num_live_points,
+            shell_frac=self.shell_fraction,
+            num_devices=len(self.devices)
+        )
+        self.max_samples = round_up_max_samples(
+            init_max_samples=self.max_samples,
+            num_discard=int(self.shell_fraction * self.num_live_points),
+            num_phantom_points=self.sampler.num_phantom()
+        )
+        if self.num_dynamic_refinement_iterations > 0:
+            raise NotImplementedError("Dynamic refinement is experimental in the reference and out of scope here.")
+        if not isinstance(self.sampler, UniDimSliceSampler):
+            raise NotImplementedError("The device loop runs UniDimSliceSampler chains.")
+        self._engine = None
+        self.last_register = None
+        self.last_profile = None
+
+    # ------------------------------------------------------------------------------------------
+    def _make_engine(self) -> _Engine:
+        if self._engine is None:
+            s = self.sampler
+            desc = self.model.desc()
+            cfg = _lib.NsEngineConfig(desc, int(self.num_live_points), int(self.max_samples),
+                                      int(self.num_live_points * self.shell_fraction), s.num_slices,
+                                      s.num_phantom_save, int(s.midpoint_shrink), 0, self._rank,
+                                      len(self.devices) if self._world > 1 else 1)
+            self._engine = _Engine(cfg, keepalive=(self.model, desc))
+        return self._engine
+
+    def _run(self, key, term_cond) -> Tuple[int, TerminationRegister, NestedSamplerState]:
+        """_run (sharded_static.py:775-851): init, (no-op) uniform phase, slice phase, final append."""
+        _lib.require_cuda()
+        L = _lib.lib()
+        eng = self._make_engine()
+        stream = _lib.stream_arg()
+        plain = isinstance(term_cond, TerminationCondition)
+        if plain:
+            if term_cond.live_evidence_frac is not None:
+                warnings.warn("live_evidence_frac is deprecated, use dlogZ instead.")
+            tc = termination.to_c(term_cond)
+        else:
+            tc = _lib.NsTermCond()  # device stops only on plateau / no seed points; host decides the rest
+        reg = _lib.NsRegister()
+        world = len(self.devices) if self._world > 1 else 1
+        if plain and world == 1:
+            _lib.check(L.nsb200_engine_run(eng.h, _lib.key_arg(key), ctypes.byref(tc), ctypes.c_int64(-1),
+                                           ctypes.byref(reg), stream))
+        else:
+            _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
+            _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+            gather = self._gather_tensor(eng) if world > 1 else None
+            host_tc = self._effective_host_cond(term_cond) if not plain else None
+            lookahead = 4 if plain else 1
+            while True:
+                if plain:
+                    done = bool(reg.done)
+                else:
+                    done = termination.determine_termination(host_tc, termination.register_from_c(reg))[0] or bool(reg.done)
+                if done:
+                    break
+                for _ in range(lookahead):
+                    _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
+                    if world > 1:
+                        import torch.distributed as dist
+                        rows = gather.shape[0] // world
+                        dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+                    _lib.check(L.nsb200_engine_step_end(eng.h, stream))
+                _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+            _lib.check(L.nsb200_engine_finalize(eng.h, stream))
+        register = termination.register_from_c(reg)
+        if plain:
+            termination_reason = int(reg.termination_reason)
+        else:
+            termination_reason = termination.determine_termination(host_tc, register)[1]
+        state = self._state(eng)
+        self.last_register = reg
+        ms = ctypes.c_double()
+        nsl = ctypes.c_int64()
+        nall = ctypes.c_int64()
+        _lib.check(L.nsb200_engine_slice_profile(eng.h, ctypes.byref(ms), ctypes.byref(nsl), ctypes.byref(nall)))
+        self.last_profile = dict(slice_ms=ms.value, slice_launches=nsl.value, all_launches=nall.value,
+                                 iterations=int(reg.iteration))
+        return termination_reason, register, state
+
+    def _effective_host_cond(self, term_cond):
+        """max_samples lowered by one iteration's space (sharded_static.py:464-470), applied to every leaf."""
+        m = int(self.num_live_points * self.shell_fraction)
+        lim = self.max_samples - m * (1 + self.sampler.num_phantom())
+
+        def fix(c):
+            if isinstance(c, TerminationCondition):
+                if c.max_samples is not None:
+                    return c._replace(max_samples=min(float(termination._f(c.max_samples)), lim))
+                return c
+            return type(c)(conds=[fix(x) for x in c.conds])
+
+        return fix(term_cond)
+
+    def _gather_tensor(self, eng) -> torch.Tensor:
+        buf = ctypes.c_void_p()
+        rows = ctypes.c_int64()
+        rd = ctypes.c_int64()
+        _lib.check(_lib.lib().nsb200_engine_gather_buffer(eng.h, ctypes.byref(buf), ctypes.byref(rows), ctypes.byref(rd)))
+        world = len(self.devices)
+        return _view(buf.value, (rows.value * world, rd.value), "<f8", eng)
+
+    def _state(self, eng) -> NestedSamplerState:
+        v = _lib.NsStateView()
+        _lib.check(_lib.lib().nsb200_engine_state(eng.h, ctypes.byref(v), _lib.stream_arg()))
+        cap, D = v.capacity, v.D
+        sc = SampleCollection(
+            sender_node_idx=_view(v.sender_node_idx, (cap,), "<i8", eng),
+            log_L=_view(v.log_L, (cap,), "<f8", eng),
+            U_samples=_view(v.U_samples, (cap, D), "<f8", eng),
+            num_likelihood_evaluations=_view(v.num_likelihood_evaluations, (cap,), "<i8", eng),
+            phantom=_view(v.phantom, (cap,), "|u1", eng).bool(),
+        )
+        return NestedSamplerState(key=np.array([v.key[0], v.key[1]], dtype=np.uint32),
+                                  next_sample_idx=int(v.next_sample_idx), num_samples=int(v.num_samples),
+                                  sample_collection=sc)
+
+    # ------------------------------------------------------------------------------------------
+    def _to_results(self, termination_reason, state: NestedSamplerState, trim: bool) -> NestedSamplerResults:
+        """_to_results (sharded_static.py:652-773)."""
+        sc = state.sample_collection
+        capacity = sc.log_L.numel()
+        num_samples = min(int(state.num_samples), capacity)
+        if trim:
+            sc = SampleCollection(*[x[:num_samples] for x in sc])
+            counts = count_crossed_edges(SampleTreeGraph(sc.sender_node_idx, sc.log_L))
+        else:
+            counts = count_crossed_edges(SampleTreeGraph(sc.sender_node_idx, sc.log_L), num_samples=num_samples)
+        idx = counts.samples_indices
+        num_live_points = counts.num_live_points
+        log_L = sc.log_L[idx]
+        U_samples = sc.U_samples[idx]
+        num_likelihood_evaluations = sc.num_likelihood_evaluations[idx]
+        final, per = compute_evidence_stats(log_L, num_live_points, num_samples=None if trim else num_samples)
+        log_Z_mean, log_Z_var = linear_to_log_stats(final.log_Z_mean, log_f2_mean=final.log_Z2_mean)
+        log_Z_uncert = math.sqrt(log_Z_var)
+        total_phantom = int(sc.phantom.sum().item())
+        phantom_fraction = total_phantom / num_samples
+        k = phantom_fraction / (1. - phantom_fraction)
+        log_Z_uncert = log_Z_uncert * math.sqrt(1. + k)
+        ESS = effective_sample_size_kish(final.log_Z_mean, final.log_dZ2_mean) / (1. + k)
+        samples = self.model.transform(U_samples)
+        # dp = normalise_log_space(LogSpace(log_dZ_mean)) (internals/log_semiring.py:359-378)
+        norm = logsumexp(per.log_dZ_mean)
+        log_dp = per.log_dZ_mean - norm
+        if norm == -math.inf:
+            log_dp = torch.full_like(log_dp, -math.inf)
+        # H estimators (:728-737); sums are small reductions over M handled by torch on the device
+        ll = torch.where(torch.isneginf(log_dp), torch.zeros_like(log_L), log_L)
+        H_instable = -(float((torch.exp(log_dp) * ll).sum().item()) - log_Z_mean)
+        H_stable = -float((torch.exp(log_dp) * (-per.log_X_mean)).sum().item())
+        H_mean = H_instable if math.isfinite(H_instable) else H_stable
+        total_evals = int(num_likelihood_evaluations.sum().item())
+        log_eff = math.log(num_samples) - (math.log(total_evals) if total_evals > 0 else -math.inf)
+        log_post = log_L + self.model.log_prob_prior(U_samples)
+        return NestedSamplerResults(
+            log_Z_mean=log_Z_mean, log_Z_uncert=log_Z_uncert, ESS=ESS, H_mean=H_mean, samples=samples,
+            parametrised_samples={}, U_samples=U_samples, log_L_samples=log_L, log_dp_mean=log_dp,
+            log_X_mean=per.log_X_mean, log_posterior_density=log_post, num_live_points_per_sample=num_live_points,
+            num_likelihood_evaluations_per_sample=num_likelihood_evaluations, total_num_samples=num_samples,
+            total_phantom_samples=total_phantom, total_num_likelihood_evaluations=total_evals,
+            log_efficiency=log_eff, termination_reason=termination_reason)

@@ -1,0 +1,346 @@
+"""GPU parity tests: the CUDA path through the C ABI against the CPU oracle on identical seeded inputs.
+Integers (Threefry words, seed indices via n_evals, tree counts, sample counts) are compared exactly;
+float64 results to the tolerance stated at each assert."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from tests.models import product_models, to_oracle  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+# ---------------------------------------------------------------------------------------------
+# RNG: bit-exact
+# ---------------------------------------------------------------------------------------------
+def test_threefry_kat(torch_cuda):
+    torch = torch_cuda
+    from jaxns_b200 import random
+    kats = [((0, 0), (0, 0), (0x6b200159, 0x99ba4efe)),
+            ((0xffffffff, 0xffffffff), (0xffffffff, 0xffffffff), (0x1cb996fc, 0xbb002be7)),
+            ((0x13198a2e, 0x03707344), (0x243f6a88, 0x85a308d3), (0xc4923a9c, 0x483df7a0))]
+    for key, ctr, exp in kats:
+        x0 = torch.tensor([ctr[0]], dtype=torch.int64).to(torch.int32).cuda() if ctr[0] < 2 ** 31 else \
+            torch.tensor([ctr[0] - 2 ** 32], dtype=torch.int32).cuda()
+        x1 = torch.tensor([ctr[1] - 2 ** 32 if ctr[1] >= 2 ** 31 else ctr[1]], dtype=torch.int32).cuda()
+        o0, o1 = random.threefry2x32(np.array(key, dtype=np.uint32), x0, x1)
+        got = (int(o0.cpu().numpy().view(np.uint32)[0]), int(o1.cpu().numpy().view(np.uint32)[0]))
+        assert got == exp
+
+
+def test_random_streams_bit_exact(torch_cuda, oracle):
+    from jaxns_b200 import random
+    for seed in (0, 42, 2 ** 40 + 17):
+        key = random.PRNGKey(seed)
+        assert np.array_equal(key, oracle.PRNGKey(seed))
+        np.testing.assert_array_equal(random.split(key, 37), oracle.split(key, 37))
+        bits = random.bits(key, 100).cpu().numpy().view(np.uint64)
+        np.testing.assert_array_equal(bits, oracle.random_bits64(key, 100))
+        # uniform: pure bit manipulation + exact arithmetic -> bit-exact
+        np.testing.assert_array_equal(random.uniform(key, 100).cpu().numpy(), oracle.uniform(key, 100))
+        # normal goes through log1p/sqrt of libdevice vs glibc -> few ulp
+        np.testing.assert_allclose(random.normal(key, 100).cpu().numpy(), oracle.normal(key, 100), rtol=1e-12)
+    np.testing.assert_array_equal(random.split(random.PRNGKey(0), 2),
+                                  np.array([[1797259609, 2579123966], [928981903, 3453687069]], dtype=np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------
+# Model.forward for every registered family
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,D", [("gauss", 1), ("gauss", 2), ("gauss", 8), ("gauss", 32), ("gauss", 33),
+                                    ("gauss", 100), ("gauss", 200), ("eggbox", 2), ("eggbox", 5),
+                                    ("rosenbrock", 10), ("rosenbrock", 70), ("shells", 2), ("shells", 10),
+                                    ("mixture", 2), ("mixture", 100)])
+def test_forward_parity(torch_cuda, oracle, name, D):
+    torch = torch_cuda
+    model = product_models()[name](D)
+    om = to_oracle(model, oracle)
+    rng = np.random.default_rng(D)
+    U = rng.uniform(size=(257, D))
+    U[0, 0] = 0.0  # ndtri(0) = -inf edge
+    U[1, -1] = 1e-300
+    U[2, 0] = 1.0 - 1e-16
+    got = model.forward(torch.from_numpy(U).cuda()).cpu().numpy()
+    exp = om.forward(U)
+    # tolerance: float64 with different summation order / libm; cond(Sigma) ~ 3e3 amplifies rounding
+    np.testing.assert_allclose(got, exp, rtol=1e-9, atol=1e-9)
+    X = model._forward_batch(torch.from_numpy(U).cuda(), True)[1].cpu().numpy()
+    np.testing.assert_allclose(X, om.transform(U), rtol=1e-12, atol=1e-300)
+
+
+# ---------------------------------------------------------------------------------------------
+# B1: batched samplers
+# ---------------------------------------------------------------------------------------------
+def test_init_batch_parity(torch_cuda, oracle):
+    torch = torch_cuda
+    import ctypes
+    from jaxns_b200 import _lib, random
+    for name, D in [("gauss", 2), ("gauss", 32), ("eggbox", 2), ("mixture", 100)]:
+        model = product_models()[name](D)
+        om = to_oracle(model, oracle)
+        key = random.PRNGKey(7)
+        N = 300
+        U = torch.empty((N, D), dtype=torch.float64, device="cuda")
+        logL = torch.empty(N, dtype=torch.float64, device="cuda")
+        nev = torch.empty(N, dtype=torch.int64, device="cuda")
+        d = model.desc()
+        _lib.check(_lib.lib().nsb200_init_batch(ctypes.byref(d), _lib.key_arg(key), ctypes.c_int64(N),
+                                                 ctypes.c_int64(0), ctypes.c_int64(N), _lib.ptr(U), _lib.ptr(logL),
+                                                 _lib.ptr(nev), _lib.stream_arg()))
+        oU, ologL, onev = oracle.init_batch(om, key, N)
+        np.testing.assert_array_equal(nev.cpu().numpy(), onev)
+        np.testing.assert_array_equal(U.cpu().numpy(), oU)  # uniforms are bit-exact
+        np.testing.assert_allclose(logL.cpu().numpy(), ologL, rtol=1e-9, atol=1e-9)
+
+
+SLICE_CASES = [
+    # name, D, N, S, k, midpoint
+    ("gauss", 2, 500, 10, 0, True),
+    ("gauss", 8, 240, 40, 3, True),
+    ("gauss", 32, 320, 32, 0, True),
+    ("gauss", 100, 200, 20, 2, True),
+    ("eggbox", 2, 400, 20, 0, False),
+    ("rosenbrock", 10, 200, 30, 10, False),
+    ("shells", 10, 200, 20, 0, True),
+    ("mixture", 100, 128, 10, 0, True),
+    ("gauss", 1, 100, 5, 0, True),
+]
+
+
+@pytest.mark.parametrize("name,D,N,S,k,midpoint", SLICE_CASES)
+def test_slice_batch_parity(torch_cuda, oracle, name, D, N, S, k, midpoint):
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.types import LivePointCollection
+    model = product_models()[name](D)
+    om = to_oracle(model, oracle)
+    # a sorted live set from prior draws, contour = median (the loop's situation)
+    oU, ologL, _ = oracle.init_batch(om, random.PRNGKey(3), N)
+    order = np.argsort(ologL, kind="stable")
+    live_U, live_logL = oU[order], ologL[order]
+    m = N // 2
+    contour = live_logL[m - 1]
+    key = random.PRNGKey(11)
+    exp = oracle.slice_batch(om, key, contour, live_U, live_logL, S, k, midpoint, num_samples=m)
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint,
+                                   perfect=True)
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    sample, phantom = sampler.get_samples_batch(key, contour, state, m)
+    # integer path: number of likelihood evaluations per chain must agree exactly
+    np.testing.assert_array_equal(sample.num_likelihood_evaluations.cpu().numpy(), exp["n_evals"])
+    # floats: same trajectory up to libm / summation-order rounding
+    np.testing.assert_allclose(sample.U_sample.cpu().numpy(), exp["U"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(sample.log_L.cpu().numpy(), exp["log_L"], rtol=1e-7, atol=1e-7)
+    assert bool((sample.log_L > contour).all())
+    if k:
+        np.testing.assert_allclose(phantom.U_sample.cpu().numpy(), exp["ph_U"], rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(phantom.log_L.cpu().numpy(), exp["ph_log_L"], rtol=1e-7, atol=1e-7)
+    # sharding invariance: two half-ranges reproduce the full batch bit-for-bit
+    a, _ = sampler.get_samples_batch(key, contour, state, m, 0, m // 2)
+    b, _ = sampler.get_samples_batch(key, contour, state, m, m // 2, m)
+    assert torch.equal(torch.cat([a.U_sample, b.U_sample]), sample.U_sample)
+    assert torch.equal(torch.cat([a.num_likelihood_evaluations, b.num_likelihood_evaluations]),
+                       sample.num_likelihood_evaluations)
+
+
+def test_slice_plateau_and_no_seed(torch_cuda, oracle):
+    """Edge cases of the reference: contour at the maximum (no satisfying seed -> index 0)."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.types import LivePointCollection
+    model = product_models()["gauss"](2)
+    om = to_oracle(model, oracle)
+    oU, ologL, _ = oracle.init_batch(om, random.PRNGKey(5), 64)
+    order = np.argsort(ologL, kind="stable")
+    live_U, live_logL = oU[order], ologL[order]
+    # contour just below the top point: exactly one seed candidate
+    contour = live_logL[-2]
+    exp = oracle.slice_batch(om, random.PRNGKey(1), contour, live_U, live_logL, 6, 0, True, num_samples=16)
+    assert np.all(exp["seed_idx"] == 63)
+    sampler = j.UniDimSliceSampler(model=model, num_slices=6, num_phantom_save=0, midpoint_shrink=True, perfect=True)
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    sample, _ = sampler.get_samples_batch(random.PRNGKey(1), contour, state, 16)
+    np.testing.assert_array_equal(sample.num_likelihood_evaluations.cpu().numpy(), exp["n_evals"])
+    np.testing.assert_allclose(sample.U_sample.cpu().numpy(), exp["U"], rtol=1e-7, atol=1e-9)
+
+
+def test_uniform_sampler_parity(torch_cuda, oracle):
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    model = product_models()["eggbox"](2)
+    om = to_oracle(model, oracle)
+    contour = 100.0
+    exp = oracle.uniform_batch(om, random.PRNGKey(9), contour, 200)
+    s, _ = j.UniformSampler(model=model).get_samples_batch(random.PRNGKey(9), contour, None, 200)
+    np.testing.assert_array_equal(s.num_likelihood_evaluations.cpu().numpy(), exp["n_evals"])
+    np.testing.assert_array_equal(s.U_sample.cpu().numpy(), exp["U"])
+    np.testing.assert_allclose(s.log_L.cpu().numpy(), exp["log_L"], rtol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# statistics: sort, tree counts (bit-exact), evidence (1e-10)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 255, 2048, 2049, 50000, 300001])
+def test_argsort_matches_stable_numpy(torch_cuda, n):
+    torch = torch_cuda
+    from jaxns_b200.internals.tree_structure import argsort
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=n)
+    x[rng.integers(0, n, size=n // 3)] = np.round(x[rng.integers(0, n, size=n // 3)], 1)  # many ties
+    if n > 10:
+        x[3] = np.inf
+        x[5] = -np.inf
+        x[7] = 0.0
+        x[8] = -0.0
+        x[9] = np.nan
+    got = argsort(torch.from_numpy(x).cuda()).cpu().numpy()
+    np.testing.assert_array_equal(got, np.argsort(x, kind="stable"))
+
+
+def test_tree_golden_vectors(torch_cuda):
+    """Golden vectors of /root/reference/src/jaxns/internals/tests/test_tree_structure.py:19-70."""
+    torch = torch_cuda
+    from jaxns_b200.internals.tree_structure import SampleTreeGraph, count_crossed_edges
+    c = count_crossed_edges(SampleTreeGraph(torch.tensor([0, 0, 0, 1, 2, 3]), torch.tensor([1., 2, 3, 4, 5, 6])))
+    assert c.samples_indices.cpu().tolist() == [0, 1, 2, 3, 4, 5]
+    assert c.num_live_points.cpu().tolist() == [3, 3, 3, 3, 2, 1]
+    assert c.num_live_points.dtype == torch.int32
+    c = count_crossed_edges(SampleTreeGraph(torch.tensor([0, 0, 0, 1, 3, 2]), torch.tensor([1., 2, 3, 4, 6, 5])))
+    assert c.samples_indices.cpu().tolist() == [0, 1, 2, 3, 5, 4]
+    assert c.num_live_points.cpu().tolist() == [3, 3, 3, 3, 2, 1]
+    inf = float("inf")
+    c1 = count_crossed_edges(SampleTreeGraph(torch.tensor([0, 0, 0, 1, 2, 3, 4, 5, 0, 0]),
+                                             torch.tensor([1., 2, 3, 4, 5, 6, 7, 8, inf, inf])), num_samples=8)
+    c2 = count_crossed_edges(SampleTreeGraph(torch.tensor([0, 0, 0, 1, 2, 3, 4, 5]),
+                                             torch.tensor([1., 2, 3, 4, 5, 6, 7, 8])))
+    assert c1.num_live_points[:8].cpu().tolist() == c2.num_live_points.cpu().tolist()
+    assert c1.samples_indices[:8].cpu().tolist() == c2.samples_indices.cpu().tolist()
+    assert c1.num_live_points[8:].cpu().tolist() == [0, 0]
+
+
+@pytest.mark.parametrize("M", [60, 5000, 200000])
+def test_tree_random_bit_exact(torch_cuda, oracle, M):
+    torch = torch_cuda
+    from jaxns_b200.internals.tree_structure import SampleTreeGraph, count_crossed_edges
+    rng = np.random.default_rng(M)
+    # a valid NS-like tree: node i+1 has a parent among earlier nodes with lower log L, plus ties
+    logL = np.sort(rng.normal(size=M))
+    logL[M // 3:M // 3 + 5] = logL[M // 3]
+    sender = np.array([rng.integers(0, i + 1) for i in range(M)], dtype=np.int64)
+    perm = rng.permutation(M)
+    # store in arbitrary order: remap node ids
+    inv = np.empty(M, np.int64)
+    inv[perm] = np.arange(M)
+    s2 = np.where(sender == 0, 0, inv[np.maximum(sender - 1, 0)] + 1)[perm]
+    l2 = logL[perm]
+    got = count_crossed_edges(SampleTreeGraph(torch.from_numpy(s2).cuda(), torch.from_numpy(l2).cuda()))
+    idx, n = oracle.count_crossed_edges(s2, l2)
+    np.testing.assert_array_equal(got.samples_indices.cpu().numpy(), idx)
+    np.testing.assert_array_equal(got.num_live_points.cpu().numpy(), n)
+    ns = M - M // 4
+    s3 = s2.copy()
+    l3 = l2.copy()
+    s3[ns:] = 0
+    l3[ns:] = np.inf
+    got = count_crossed_edges(SampleTreeGraph(torch.from_numpy(s3).cuda(), torch.from_numpy(l3).cuda()), num_samples=ns)
+    idx, n = oracle.count_crossed_edges(s3, l3, ns)
+    np.testing.assert_array_equal(got.num_live_points.cpu().numpy(), n)
+    np.testing.assert_array_equal(got.samples_indices.cpu().numpy()[:ns], idx[:ns])
+
+
+@pytest.mark.parametrize("M", [1, 7, 1000, 4096, 150000])
+def test_evidence_stats_1e10(torch_cuda, oracle, M):
+    torch = torch_cuda
+    from jaxns_b200.internals.shrinkage_statistics import compute_evidence_stats
+    rng = np.random.default_rng(M)
+    logL = np.sort(rng.normal(size=M) * 30 - 100)
+    n = rng.integers(1, 500, size=M).astype(np.float64)
+    final, per = compute_evidence_stats(torch.from_numpy(logL).cuda(), torch.from_numpy(n).cuda())
+    ofinal, oper = oracle.evidence_scan(oracle.init_evidence_calc(), logL, n, per_sample=True)
+    # north-star tolerance: 1e-10 relative in float64 on the same dead-point set
+    np.testing.assert_allclose(np.array(final), ofinal, rtol=1e-10, atol=1e-10)
+    got = torch.stack(list(per)).cpu().numpy().T
+    np.testing.assert_allclose(got, oper, rtol=1e-10, atol=1e-10)
+
+
+# ---------------------------------------------------------------------------------------------
+# B2/B3: whole run vs the oracle's run on identical inputs
+# ---------------------------------------------------------------------------------------------
+RUN_CASES = [("gauss", 2, 100, 10, 0, True), ("gauss", 8, 64, 16, 2, True), ("eggbox", 2, 200, 20, 0, False),
+             ("gauss", 32, 128, 32, 0, True)]
+
+
+@pytest.mark.parametrize("name,D,N,S,k,midpoint", RUN_CASES)
+def test_engine_run_matches_oracle(torch_cuda, oracle, name, D, N, S, k, midpoint):
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    model = product_models()[name](D)
+    om = to_oracle(model, oracle)
+    max_samples = N * 40
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint, perfect=True)
+    ns = j.ShardedStaticNestedSampler(model=model, max_samples=max_samples, init_efficiency_threshold=0.1,
+                                      sampler=sampler, num_live_points=N)
+    tc = j.TerminationCondition(dlogZ=float(np.log(1 + 1e-3)), max_samples=float(ns.max_samples))
+    reason, register, state = ns._run(random.PRNGKey(42), tc)
+    res = ns._to_results(reason, state, trim=True)
+    ons = oracle.OracleNestedSampler(om, N, S, k, midpoint, max_samples=max_samples)
+    assert ons.max_samples == ns.max_samples and ons.N == ns.num_live_points
+    oreason, ost = ons.run(random.PRNGKey(42), oracle.TermCond(dlogZ=float(np.log(1 + 1e-3)), max_samples=float(ons.max_samples)))
+    ores = ons.to_results(oreason, ost)
+    # integers: exact
+    assert reason == oreason
+    assert state.num_samples == ost["num_samples"]
+    assert state.next_sample_idx == ost["next_sample_idx"]
+    np.testing.assert_array_equal(state.key, ost["key"])
+    assert res.total_num_samples == ores["total_num_samples"]
+    assert res.total_num_likelihood_evaluations == ores["total_num_likelihood_evaluations"]
+    ncap = min(state.num_samples, ns.max_samples)
+    np.testing.assert_array_equal(state.sample_collection.sender_node_idx[:ncap].cpu().numpy(), ost["sender"][:ncap])
+    np.testing.assert_array_equal(res.num_live_points_per_sample.cpu().numpy(), ores["num_live_points_per_sample"])
+    np.testing.assert_array_equal(res.num_likelihood_evaluations_per_sample.cpu().numpy(),
+                                  ores["num_likelihood_evaluations_per_sample"])
+    # floats
+    np.testing.assert_allclose(res.log_L_samples.cpu().numpy(), ores["log_L_samples"], rtol=1e-7, atol=1e-7)
+    assert abs(res.log_Z_mean - ores["log_Z_mean"]) < 1e-6
+    assert abs(res.log_Z_uncert - ores["log_Z_uncert"]) < 1e-6
+    assert abs(res.ESS - ores["ESS"]) < 1e-4 * ores["ESS"]
+    assert abs(res.H_mean - ores["H_mean"]) < 1e-5 * max(1.0, abs(ores["H_mean"]))
+    # in-loop register (termination decision inputs)
+    oreg = ons.register
+    np.testing.assert_allclose(np.array(register.evidence_calc), oreg["evidence_calc"], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(np.array(register.evidence_calc_with_remaining),
+                               oreg["evidence_calc_with_remaining"], rtol=1e-8, atol=1e-8)
+    assert register.num_likelihood_evaluations == oreg["num_likelihood_evaluations"]
+
+
+def test_public_api_gaussian_logZ(torch_cuda, oracle):
+    """End to end through NestedSampler with default settings: 2-D Gaussian (BASELINE config 1),
+    |logZ - analytic| < 3 sigma for every one of 10 seeds is too strict for a 3-sigma test, so the
+    reference's own criterion is used per seed (tests/test_nested_sampler.py:9-37) and the mean error
+    must be inside 3 sigma / sqrt(10)."""
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    model = product_models()["gauss"](2)
+    true = oracle.gauss_analytic_logZ(2)
+    errs, sig = [], []
+    ns = j.NestedSampler(model=model, num_live_points=500, max_samples=5e4)
+    assert ns.num_slices == 10 and ns.k == 0 and ns.c == 500
+    for seed in range(10):
+        reason, state = ns(random.PRNGKey(seed))
+        res = ns.to_results(reason, state)
+        errs.append(res.log_Z_mean - true)
+        sig.append(res.log_Z_uncert)
+        assert reason & 4  # terminated on dlogZ
+    errs, sig = np.array(errs), np.array(sig)
+    assert np.sum(np.abs(errs) < 3 * sig) >= 9
+    assert abs(errs.mean()) < 3 * sig.mean() / np.sqrt(10)
