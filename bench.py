@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""
+bench.py -- likelihood evals/sec and time-to-logZ of the static nested-sampling hot path.
+
+A "step" is one whole nested-sampling run to termination (default dlogZ = log(1+1e-3)) on the
+configuration BASELINE.json's metric is quoted on: the 32-D correlated Gaussian (dense covariance,
+analytic log Z = -141.429218), num_live_points = 3200, defaults s=5, k=0 (configs[1]); step i uses
+PRNGKey(i).  With --gpus N > 1 (one process per GPU under torchrun) the chains of every iteration
+are sharded over the ranks and all-gathered over NCCL; per-GPU work is held fixed (num_live_points =
+3200 * N), so scaling is "weak".
+
+  value         whole-job likelihood evals/s, model parameters resident in HBM, device-timed
+                (CUDA events on the launching stream around each run, max over ranks)
+  e2e           the same metric through the public API (Model -> NestedSampler -> to_results) with
+                host buffers: model parameters copied host->device and the posterior samples /
+                weights read back device->host inside the timed region
+  roofline      fused slice kernel: algorithmic FP64 flops (evals x (D^2 + 4D)) / its
+                CUDA-event time inside the runs, against an FP64-FMA peak measured in the same process
+  cpu_baseline  the oracle (CPU restatement of jaxns 2.6.9) on a bounded sample of the same workload
+
+--impl reference times the reference's CPU algorithm (the oracle port; the reference itself needs
+JAX/TFP, which cannot be installed offline -- see DESIGN.md) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+D = 32
+BASE_LIVE = 3200
+ANALYTIC_LOGZ = -141.4292184
+FLOPS_PER_EVAL = D * D + 4 * D  # triangular matvec D(D+1) + subtraction/dot 3D
+
+
+def workload_arrays():
+    cov = np.full((D, D), 0.99) + 0.01 * np.eye(D)
+    return np.zeros(D), np.ones(D), np.full(D, 15.0), cov
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------------
+def oracle_sample(num_live, iterations, seed=0, threads=None):
+    """init + the first `iterations` shells of the same workload; returns (evals, seconds, threads)."""
+    from oracle import oracle as o
+    if threads:
+        o.set_num_threads(threads)
+    om = o.gauss_model(D)
+    ns = o.OracleNestedSampler(om, num_live, D * 5, 0, True, max_samples=num_live * 100)
+    t0 = time.perf_counter()
+    reason, st = ns.run(o.PRNGKey(seed), max_iterations=iterations)
+    dt = time.perf_counter() - t0
+    n = min(st["num_samples"], ns.max_samples)
+    evals = int(st["n_evals"][:n].sum())
+    return evals, dt, o.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    num_live = BASE_LIVE * args.gpus
+    iters = 4
+    for _ in range(args.warmup):
+        oracle_sample(num_live, 1)
+    tot_e, tot_t = 0, 0.0
+    for s in range(args.steps):
+        e, t, cores = oracle_sample(num_live, iters, seed=s)
+        tot_e += e
+        tot_t += t
+    value = tot_e / tot_t
+    line = {
+        "impl": "reference", "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"32-D correlated Gaussian, num_live_points={num_live}, s=5, k=0 (BASELINE configs[1])",
+                   "sample": f"prior draws + first {iters} shells of the run per step"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": f"init + first {iters} shells per step, {args.steps} steps"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "oracle port of jaxns 2.6.9 (reference needs jax/tfp: not installable offline)",
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------
+# native arm
+# --------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    import jaxns_b200 as j
+    from jaxns_b200 import _lib, distributions as tfpd, likelihoods as lk, random
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    num_live = BASE_LIVE * world
+    p_loc, p_scale, mu, cov = workload_arrays()
+
+    def make_model():
+        def prior_model():
+            x = yield j.Prior(tfpd.MultivariateNormalTriL(loc=p_loc, scale_tril=np.diag(p_scale)), name="x")
+            return x
+
+        return j.Model(prior_model, lk.DenseGaussianLikelihood(mu, covariance_matrix=cov))
+
+    model = make_model()
+    ns = j.NestedSampler(model=model, num_live_points=num_live)
+    assert ns.num_slices == 160 and ns.k == 0
+    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_run(seed):
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        flush.fill_(float(seed))  # L2 flush between timed iterations (outside the timed region)
+        barrier()
+        ev0.record()
+        reason, state = ns(random.PRNGKey(seed))
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        n = min(state.num_samples, ns.nested_sampler.max_samples)
+        evals = int(state.sample_collection.num_likelihood_evaluations[:n].sum().item())
+        prof = dict(ns.nested_sampler.last_profile)
+        reg = ns.nested_sampler.last_register
+        return ms, evals, prof, reason, state, int(reg.num_likelihood_evaluations)
+
+    for w in range(args.warmup):
+        one_run(1000 + w)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    tot_ms, tot_evals, slice_ms, slice_evals, launches, iters = 0.0, 0, 0.0, 0, 0, 0
+    logZ = []
+    barrier()
+    for s in range(args.steps):
+        ms, evals, prof, reason, state, loop_evals = one_run(s)
+        tot_ms += ms
+        tot_evals += evals
+        slice_ms += prof["slice_ms"]
+        slice_evals += loop_evals // world  # this rank's share of the chains
+        launches += prof["all_launches"]
+        iters += prof["iterations"]
+        if rank == 0 and s < 3:
+            res = ns.to_results(reason, state)
+            logZ.append((res.log_Z_mean, res.log_Z_uncert))
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    t = torch.tensor([tot_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms_max = float(t.item())
+    value = tot_evals / (tot_ms_max * 1e-3)
+
+    # ---- e2e through the public API with host buffers --------------------------------------------
+    e2e_t, e2e_evals, h2d, d2h = 0.0, 0, 0, 0
+    n_e2e = max(1, min(args.steps, 3))
+    for s in range(n_e2e):
+        flush.fill_(0.5)
+        barrier()
+        t0 = time.perf_counter()
+        m2 = make_model()  # host numpy -> device copies happen inside (Model.desc)
+        ns2 = j.NestedSampler(model=m2, num_live_points=num_live)
+        reason, state = ns2(random.PRNGKey(s))
+        res = ns2.to_results(reason, state)
+        host = {"log_L": res.log_L_samples.cpu(), "log_dp": res.log_dp_mean.cpu(),
+                "x": res.samples["x"].cpu(), "logZ": res.log_Z_mean}
+        torch.cuda.synchronize()
+        e2e_t += time.perf_counter() - t0
+        e2e_evals += res.total_num_likelihood_evaluations
+        fam, D_, pk, K, a, b, params = m2.host_arrays()
+        h2d = int(a.nbytes + b.nbytes + params.nbytes + 8)
+        d2h = int(sum(v.numel() * v.element_size() for v in host.values() if hasattr(v, "numel")) + 8 * 8)
+        del ns2, m2
+    te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_evals / float(te.item())
+
+    if rank == 0:
+        # ---- roofline of the dominant kernel ----------------------------------------------------
+        tf = _lib.ctypes.c_double()
+        _lib.check(_lib.lib().nsb200_bench_fp64_fma(_lib.ctypes.c_int64(1 << 15), _lib.ctypes.byref(tf)))
+        achieved = slice_evals * FLOPS_PER_EVAL / (slice_ms * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
+                    "frac": achieved / tf.value if tf.value else None, "traffic": None,
+                    "kernel": "k_slice_chains_engine<1>",
+                    "kernel_share_of_step": slice_ms / tot_ms,
+                    "peak_source": "FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
+                                   f"figure; its hbm_gbs={peaks.get('hbm_gbs')} governs only the statistics kernels)",
+                    "algorithmic_flops_per_eval": FLOPS_PER_EVAL}
+        # ---- CPU baseline on a bounded sample -----------------------------------------------------
+        cpu_iters = 40
+        ce, ct, cores = oracle_sample(num_live, cpu_iters, seed=0)
+        line = {
+            "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"32-D correlated Gaussian (dense cov, rho=0.99, mu=15), num_live_points={num_live}, "
+                                   "num_slices=160, k=0, run to dlogZ=log(1+1e-3) (BASELINE configs[1])",
+                       "l2": "256 MB buffer written between timed runs (L2 flush)",
+                       "iterations_per_step": iters / args.steps, "evals_per_step": tot_evals / args.steps,
+                       "time_to_logZ_ms": tot_ms_max / args.steps,
+                       "logZ": [{"mean": m, "uncert": u, "analytic": ANALYTIC_LOGZ} for m, u in logZ]},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "runs": n_e2e},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": {"value": ce / ct, "unit": "evals/s", "cores": cores, "kind": "port",
+                             "sample": f"oracle (CPU restatement of jaxns 2.6.9): prior draws + first {cpu_iters} "
+                                       f"shells of the same run, {ce} evals in {ct:.1f}s"},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

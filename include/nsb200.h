@@ -265,6 +265,12 @@ int nsb200_engine_state(NsEngine *e, NsStateView *out, nsb200_stream_t stream);
  * accumulated since engine_init; used by bench.py for the roofline numerator/denominator. */
 int nsb200_engine_slice_profile(NsEngine *e, double *slice_ms, int64_t *slice_launches, int64_t *all_launches);
 
+/* ---- diagnostics ----------------------------------------------------------------------------- */
+/* Measures the FP64 FMA peak of the current device (independent DFMA chains, CUDA-event timed):
+ * the roofline denominator of the fused slice kernel (MEASURED_PEAKS.json has no FP64 figure).
+ * Synchronous; returns TFLOP/s in *out_tflops. */
+int nsb200_bench_fp64_fma(int64_t iters, double *out_tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,13 +64,20 @@ struct ModelSmem {
     double *prior_a;  // [DP]
     double *prior_b;  // [DP]
     double *params;   // family specific, see stage_model()
+    const double *dense_global;  // row-major Linv in global memory when the factor does not fit in smem
 };
+
+// Largest dense factor (in doubles) staged in shared memory; beyond it the kernel reads the
+// row-major factor from global memory (L1/L2 resident) instead.
+constexpr size_t kDenseSmemMaxDoubles = 20 * 1024;  // 160 KB
+
+__host__ __device__ inline bool dense_in_smem(int D, int DP) { return (size_t) D * DP <= kDenseSmemMaxDoubles; }
 
 // Doubles of shared memory the staged model needs.
 __host__ __device__ inline size_t model_smem_doubles(int family, int D, int DP, int K) {
     size_t n = 2 * (size_t) DP;
     switch (family) {
-        case NSB200_FAM_GAUSS_DENSE: n += 1 + DP + (size_t) D * DP; break;           // c, mu[DP], LT[D][DP]
+        case NSB200_FAM_GAUSS_DENSE: n += 1 + DP + (dense_in_smem(D, DP) ? (size_t) D * DP : 0); break;  // c, mu[DP], LT[D][DP]
         case NSB200_FAM_GAUSS_MIX_DIAG: n += (size_t) K * (1 + 2 * (size_t) DP); break;  // logc, mean[DP], inv[DP]
         case NSB200_FAM_SHELLS: n += (size_t) K * (2 + (size_t) DP); break;           // w, r, c[DP]
         default: break;
@@ -90,6 +97,7 @@ __device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, M
     out.prior_a = smem;
     out.prior_b = smem + DP;
     out.params = smem + 2 * DP;
+    out.dense_global = nullptr;
     for (int j = threadIdx.x; j < DP; j += blockDim.x) {
         out.prior_a[j] = (j < D) ? m.prior_a[j] : 0.0;
         out.prior_b[j] = (j < D) ? m.prior_b[j] : 0.0;
@@ -101,10 +109,14 @@ __device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, M
             // src = [c, mu[D], Linv[D*D] row-major]; dst = [c, mu[DP], LT[j][i] = Linv[i][j]]
             if (threadIdx.x == 0) P[0] = src[0];
             for (int j = threadIdx.x; j < DP; j += blockDim.x) P[1 + j] = (j < D) ? src[1 + j] : 0.0;
-            double *LT = P + 1 + DP;
-            for (int e = threadIdx.x; e < D * DP; e += blockDim.x) {
-                int j = e / DP, i = e - j * DP;
-                LT[e] = (i < D && j <= i) ? src[1 + D + (size_t) i * D + j] : 0.0;
+            if (dense_in_smem(D, DP)) {
+                double *LT = P + 1 + DP;
+                for (int e = threadIdx.x; e < D * DP; e += blockDim.x) {
+                    int j = e / DP, i = e - j * DP;
+                    LT[e] = (i < D && j <= i) ? src[1 + D + (size_t) i * D + j] : 0.0;
+                }
+            } else {
+                out.dense_global = src + 1 + D;
             }
             break;
         }
@@ -170,6 +182,18 @@ __device__ __forceinline__ double loglik_group(const ModelSmem &sm, const Grp &g
 #pragma unroll
             for (int s = 0; s < DPL; ++s) z[s] = 0.0;
             // z_i = sum_{j<=i} Linv[i][j] r_j ; rows of slot s end at (s+1)G-1
+            if (sm.dense_global) {
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int i = s * G + g.lane;
+                    if (i < D) {
+                        const double *row = sm.dense_global + (size_t) i * D;
+                        double acc = 0.0;
+                        for (int jj = 0; jj <= i; ++jj) acc = fma(__ldg(row + jj), scratch[jj], acc);
+                        z[s] = acc;
+                    }
+                }
+            } else
 #pragma unroll
             for (int s = 0; s < DPL; ++s) {
                 const int jend = min(D, (s + 1) * G);

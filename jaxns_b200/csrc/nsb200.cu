@@ -821,3 +821,52 @@ extern "C" int nsb200_engine_slice_profile(NsEngine *e, double *slice_ms, int64_
     if (all_launches) *all_launches = e->all_launches;
     return 0;
 }
+
+// -------------------------------------------------------------------------------------------------
+// diagnostics: FP64 FMA peak (roofline denominator of the slice kernel)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_fma_peak(double *sink, long long iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0,
+           x6 = x0 + 6.0, x7 = x0 + 7.0;
+    for (long long i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) sink[0] = s;
+}
+
+extern "C" int nsb200_bench_fp64_fma(int64_t iters, double *out_tflops) {
+    if (!out_tflops) return fail("out_tflops is NULL");
+    if (iters <= 0) iters = 1 << 14;
+    int dev = 0, sms = 0;
+    NSB_CUDA(cudaGetDevice(&dev));
+    NSB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    double *sink = nullptr;
+    NSB_CUDA(cudaMalloc(&sink, 8));
+    const int blocks = sms * 8, threads = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0, 0);
+        k_fp64_fma_peak<<<blocks, threads>>>(sink, iters, 0.999999, 1e-7);
+        cudaEventRecord(e1, 0);
+        cudaError_t err = cudaEventSynchronize(e1);
+        if (err != cudaSuccess) {
+            cudaFree(sink);
+            return fail("fp64 peak kernel failed: %s", cudaGetErrorString(err));
+        }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double) iters * blocks * threads;
+        const double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *out_tflops = best;
+    return 0;
+}
