@@ -8,41 +8,9 @@
 // replace_index = clamped dynamic_update_slice (internals/maps.py:15-25).
 #pragma once
 #include "ns_stats.cuh"
+#include "ns_types.cuh"
 
 namespace nsb {
-
-// Device-resident loop control (one instance per engine).
-struct DevCtl {
-    Key key;               // NestedSamplerState.key
-    long long next_idx;    // next_sample_idx
-    long long num_samples; // num_samples
-    long long iteration;
-    // derived per iteration by k_iter_prologue
-    Key sample_key;
-    double contour;
-    long long disc_start;  // clamped write offset of the discarded shell
-    long long ph_start;    // clamped write offset of the phantom rows
-    long long sender;      // sender_node_idx of the replacements
-    int active;            // 0 once the register says done: every step kernel becomes a no-op
-    int cur;               // which of the two live buffers is current
-};
-
-struct LiveSet {
-    long long *sender;
-    double *U;
-    double *logL_constraint;
-    double *logL;
-    long long *nevals;
-};
-
-struct DeadStore {
-    long long *sender;
-    double *logL;
-    double *U;
-    long long *nevals;
-    unsigned char *phantom;
-    long long capacity;
-};
 
 __device__ __forceinline__ long long clampll(long long v, long long lo, long long hi) {
     return v < lo ? lo : (v > hi ? hi : v);

@@ -4,9 +4,20 @@
 // warp); dimension j lives in lane (j % G), register slot (j / G), so a chain's D-vectors are
 // spread over the group's registers (DPL = ceil(D / G) doubles per lane per vector) and every
 // D-wide step (quantile transform, direction draw, cube bounds, matrix-vector product) runs
-// lane-parallel with shuffle reductions.  Likelihood parameters are staged once per CTA in shared
-// memory; the dense Gaussian factor is stored transposed (column j contiguous over rows) so that a
-// warp reads consecutive rows conflict-free while r_j is a broadcast load.
+// lane-parallel with shuffle reductions.  G and DPL are compile-time so masks, strides and unrolls
+// are constants.
+//
+// P proposals are evaluated per call ("batch"): the slice sampler's shrink sequence is known ahead
+// of the likelihood values (see ns_slice.cuh), so P candidate points are pushed through the prior
+// transform and the likelihood together.  A chain is one long dependency chain and config-2 sized
+// problems only put ~2.7 warps on each SM sub-partition, so this instruction-level parallelism is
+// what keeps the FP64 pipe busy.
+//
+// Likelihood parameters are staged once per CTA in shared memory.  The dense Gaussian factor is
+// stored transposed (column j contiguous over rows) so that a warp reads consecutive rows
+// conflict-free; for D <= 32 every lane keeps its row of L^-1 in registers instead.  The residuals
+// r_j of the P proposals are exchanged through a per-chain shared-memory scratch [DP][P] read with
+// broadcast loads.
 //
 // Reference: Model.forward (/root/reference/src/jaxns/framework/model.py:167-176) ->
 // compute_log_likelihood (framework/ops.py:302-326, NaN -> -inf at :323-325) ->
@@ -19,48 +30,51 @@ namespace nsb {
 
 constexpr int kThreadsPerBlock = 128;
 
+template <int G>
 struct Grp {
-    unsigned mask;  // lanes of this group inside the warp
+    unsigned mask;  // lanes of this group inside the warp (compile-time constant for G == 32)
     int lane;       // lane index inside the group
-    int G;          // group size
+    __device__ __forceinline__ Grp() {
+        const int wl = threadIdx.x & 31;
+        lane = wl & (G - 1);
+        if (G == 32) mask = 0xFFFFFFFFu;
+        else mask = ((1u << (G & 31)) - 1u) << (wl & ~(G - 1));
+    }
+    __device__ __forceinline__ unsigned m() const { return G == 32 ? 0xFFFFFFFFu : mask; }
 };
 
-__device__ __forceinline__ Grp make_group(int G) {
-    Grp g;
-    g.G = G;
-    const int wl = threadIdx.x & 31;
-    g.lane = wl & (G - 1);
-    const unsigned base = (G == 32) ? 0xFFFFFFFFu : ((1u << G) - 1u);
-    g.mask = base << (wl & ~(G - 1));
-    return g;
+template <int G>
+__device__ __forceinline__ void group_sync(const Grp<G> &g) {
+    if (G > 1) __syncwarp(g.m());
 }
-
-__device__ __forceinline__ void group_sync(const Grp &g) { __syncwarp(g.mask); }
-
-__device__ __forceinline__ double group_sum(const Grp &g, double v) {
-    for (int o = g.G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+template <int G>
+__device__ __forceinline__ double group_sum(const Grp<G> &g, double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.m(), v, o);
     return v;
 }
-__device__ __forceinline__ double group_prod(const Grp &g, double v) {
-    for (int o = g.G >> 1; o > 0; o >>= 1) v *= __shfl_xor_sync(g.mask, v, o);
+template <int G>
+__device__ __forceinline__ double group_prod(const Grp<G> &g, double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v *= __shfl_xor_sync(g.m(), v, o);
     return v;
 }
-__device__ __forceinline__ double group_min(const Grp &g, double v) {
-    for (int o = g.G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(g.mask, v, o));
+template <int G>
+__device__ __forceinline__ double group_min(const Grp<G> &g, double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(g.m(), v, o));
     return v;
 }
-__device__ __forceinline__ double group_max(const Grp &g, double v) {
-    for (int o = g.G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.mask, v, o));
-    return v;
-}
-__device__ __forceinline__ long long group_sum_ll(const Grp &g, long long v) {
-    for (int o = g.G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.mask, v, o);
+template <int G>
+__device__ __forceinline__ double group_max(const Grp<G> &g, double v) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(g.m(), v, o));
     return v;
 }
 
 // Shared-memory image of the model, built once per CTA.
 struct ModelSmem {
-    int D, DP, K, family, prior_kind;
+    int D, K, family, prior_kind;
     double *prior_a;  // [DP]
     double *prior_b;  // [DP]
     double *params;   // family specific, see stage_model()
@@ -72,14 +86,19 @@ struct ModelSmem {
 constexpr size_t kDenseSmemMaxDoubles = 20 * 1024;  // 160 KB
 
 __host__ __device__ inline bool dense_in_smem(int D, int DP) { return (size_t) D * DP <= kDenseSmemMaxDoubles; }
+// D <= 32 with one lane per dimension: the factor row lives in registers, nothing is staged.
+__host__ __device__ constexpr bool dense_in_regs(int G, int DPL) { return G == 32 && DPL == 1; }
 
 // Doubles of shared memory the staged model needs.
-__host__ __device__ inline size_t model_smem_doubles(int family, int D, int DP, int K) {
+__host__ __device__ inline size_t model_smem_doubles(int family, int D, int G, int DPL, int K) {
+    const int DP = G * DPL;
     size_t n = 2 * (size_t) DP;
     switch (family) {
-        case NSB200_FAM_GAUSS_DENSE: n += 1 + DP + (dense_in_smem(D, DP) ? (size_t) D * DP : 0); break;  // c, mu[DP], LT[D][DP]
+        case NSB200_FAM_GAUSS_DENSE:
+            n += 1 + DP + ((!dense_in_regs(G, DPL) && dense_in_smem(D, DP)) ? (size_t) D * DP : 0);  // c, mu, LT[D][DP]
+            break;
         case NSB200_FAM_GAUSS_MIX_DIAG: n += (size_t) K * (1 + 2 * (size_t) DP); break;  // logc, mean[DP], inv[DP]
-        case NSB200_FAM_SHELLS: n += (size_t) K * (2 + (size_t) DP); break;           // w, r, c[DP]
+        case NSB200_FAM_SHELLS: n += (size_t) K * (3 + (size_t) DP); break;              // w, r, lognorm, c[DP]
         default: break;
     }
     return n;
@@ -87,10 +106,11 @@ __host__ __device__ inline size_t model_smem_doubles(int family, int D, int DP, 
 
 // Cooperative (whole CTA) staging of the model into shared memory.  Padded dimensions get neutral
 // values.  Must be followed by __syncthreads().
-__device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, ModelSmem &out) {
+template <int G, int DPL>
+__device__ inline void stage_model(const NsModelDesc &m, double *smem, ModelSmem &out) {
+    constexpr int DP = G * DPL;
     const int D = m.D;
     out.D = D;
-    out.DP = DP;
     out.K = m.K;
     out.family = m.family;
     out.prior_kind = m.prior_kind;
@@ -109,7 +129,9 @@ __device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, M
             // src = [c, mu[D], Linv[D*D] row-major]; dst = [c, mu[DP], LT[j][i] = Linv[i][j]]
             if (threadIdx.x == 0) P[0] = src[0];
             for (int j = threadIdx.x; j < DP; j += blockDim.x) P[1 + j] = (j < D) ? src[1 + j] : 0.0;
-            if (dense_in_smem(D, DP)) {
+            if (dense_in_regs(G, DPL)) {
+                out.dense_global = src + 1 + D;  // rows are pulled into registers by the caller
+            } else if (dense_in_smem(D, DP)) {
                 double *LT = P + 1 + DP;
                 for (int e = threadIdx.x; e < D * DP; e += blockDim.x) {
                     int j = e / DP, i = e - j * DP;
@@ -133,12 +155,13 @@ __device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, M
             break;
         }
         case NSB200_FAM_SHELLS: {
-            for (int e = threadIdx.x; e < m.K * (2 + DP); e += blockDim.x) {
-                int k = e / (2 + DP), o = e - k * (2 + DP);
+            for (int e = threadIdx.x; e < m.K * (3 + DP); e += blockDim.x) {
+                int k = e / (3 + DP), o = e - k * (3 + DP);
                 const double *sk = src + (size_t) k * (2 + D);
                 double v;
                 if (o < 2) v = sk[o];
-                else { int j = o - 2; v = (j < D) ? sk[2 + j] : 0.0; }
+                else if (o == 2) v = log(sqrt(2.0 * 3.14159265358979323846 * (sk[0] * sk[0])));
+                else { int j = o - 3; v = (j < D) ? sk[2 + j] : 0.0; }
                 P[e] = v;
             }
             break;
@@ -147,152 +170,237 @@ __device__ inline void stage_model(const NsModelDesc &m, int DP, double *smem, M
     }
 }
 
-// Prior quantile transform for this lane's dimensions.
-template <int DPL>
-__device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp &g, const double (&u)[DPL],
-                                               double (&X)[DPL]) {
+// Per-thread registers of the dense factor (only meaningful for G == 32, DPL == 1).
+template <int G, int DPL>
+struct DenseRow {
+    static constexpr int N = dense_in_regs(G, DPL) ? 32 : 1;
+    double v[N];
+    __device__ __forceinline__ void load(const ModelSmem &sm, int lane) {
+        if (dense_in_regs(G, DPL)) {
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                v[j] = (sm.family == NSB200_FAM_GAUSS_DENSE && lane < sm.D && j <= lane)
+                           ? __ldg(sm.dense_global + (size_t) lane * sm.D + j)
+                           : 0.0;
+        }
+    }
+};
+
+// Prior quantile transform of P points for this lane's dimensions.
+template <int G, int DPL, int P>
+__device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp<G> &g, const double (&u)[P][DPL],
+                                               double (&X)[P][DPL]) {
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
-        const int j = s * g.G + g.lane;
+        const int j = s * G + g.lane;
         const double a = sm.prior_a[j], b = sm.prior_b[j];
-        if (sm.prior_kind == NSB200_PRIOR_UNIFORM) X[s] = u[s] * b + a;
-        else X[s] = (j < sm.D) ? ndtri(u[s]) * b + a : 0.0;
+        if (sm.prior_kind == NSB200_PRIOR_UNIFORM) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) X[p][s] = u[p][s] * b + a;
+        } else {
+#pragma unroll
+            for (int p = 0; p < P; ++p) X[p][s] = (j < sm.D) ? ndtri(u[p][s]) * b + a : 0.0;
+        }
     }
 }
 
-// log-likelihood of the transformed point held across the group.  `scratch` = DP doubles of shared
-// memory private to the chain.  Returns the same value in every lane of the group.
-template <int DPL>
-__device__ __forceinline__ double loglik_group(const ModelSmem &sm, const Grp &g, const double (&X)[DPL],
-                                               double *scratch) {
-    const int D = sm.D, DP = sm.DP, G = g.G;
-    const double *P = sm.params;
-    double r;
+// log-likelihood of the P transformed points held across the group.  `scratch` = DP*P doubles of
+// shared memory private to the chain.  Every lane of the group gets the same values.
+template <int G, int DPL, int P>
+__device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
+                                             const double (&X)[P][DPL], double *scratch, double (&out)[P]) {
+    constexpr int DP = G * DPL;
+    const int D = sm.D;
+    const double *Pm = sm.params;
+    const double kNan = __longlong_as_double(0x7FF8000000000000ll);
     switch (sm.family) {
         case NSB200_FAM_GAUSS_DENSE: {
-            const double *mu = P + 1;
-            const double *LT = P + 1 + DP;
+            const double *mu = Pm + 1;
+            // residuals r_j^(p) -> scratch[j][p]
 #pragma unroll
             for (int s = 0; s < DPL; ++s) {
                 const int j = s * G + g.lane;
-                scratch[j] = (j < D) ? X[s] - mu[j] : 0.0;
+                const double m = mu[j];
+#pragma unroll
+                for (int p = 0; p < P; ++p) scratch[j * P + p] = (j < D) ? X[p][s] - m : 0.0;
             }
             group_sync(g);
-            double z[DPL];
+            double q[P];
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) z[s] = 0.0;
-            // z_i = sum_{j<=i} Linv[i][j] r_j ; rows of slot s end at (s+1)G-1
-            if (sm.dense_global) {
+            for (int p = 0; p < P; ++p) q[p] = 0.0;
+            if (dense_in_regs(G, DPL)) {
+                // z_lane = sum_j Linv[lane][j] r_j with the row in registers; two partial sums per
+                // proposal shorten the dependent FMA chain.
+                double z0[P], z1[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p) z0[p] = z1[p] = 0.0;
+#pragma unroll
+                for (int j = 0; j < DenseRow<G, DPL>::N; j += 2) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        z0[p] = fma(row.v[j], scratch[j * P + p], z0[p]);
+                        z1[p] = fma(row.v[j + 1 < DenseRow<G, DPL>::N ? j + 1 : j],
+                                    (j + 1 < DenseRow<G, DPL>::N) ? scratch[(j + 1) * P + p] : 0.0, z1[p]);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const double z = z0[p] + z1[p];
+                    q[p] = z * z;
+                }
+            } else if (sm.dense_global) {
 #pragma unroll
                 for (int s = 0; s < DPL; ++s) {
                     const int i = s * G + g.lane;
                     if (i < D) {
-                        const double *row = sm.dense_global + (size_t) i * D;
-                        double acc = 0.0;
-                        for (int jj = 0; jj <= i; ++jj) acc = fma(__ldg(row + jj), scratch[jj], acc);
-                        z[s] = acc;
+                        const double *rw = sm.dense_global + (size_t) i * D;
+                        double acc[P];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) acc[p] = 0.0;
+                        for (int jj = 0; jj <= i; ++jj) {
+                            const double l = __ldg(rw + jj);
+#pragma unroll
+                            for (int p = 0; p < P; ++p) acc[p] = fma(l, scratch[jj * P + p], acc[p]);
+                        }
+#pragma unroll
+                        for (int p = 0; p < P; ++p) q[p] = fma(acc[p], acc[p], q[p]);
                     }
                 }
-            } else
+            } else {
+                const double *LT = Pm + 1 + DP;
+                // rows of slot s end at (s+1)G-1: column loop stops there (lower-triangular factor)
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) {
-                const int jend = min(D, (s + 1) * G);
-                const double *col = LT + s * G + g.lane;
-                double acc0 = 0.0, acc1 = 0.0;
-                int jj = 0;
-                for (; jj + 1 < jend; jj += 2) {
-                    acc0 = fma(col[(size_t) jj * DP], scratch[jj], acc0);
-                    acc1 = fma(col[(size_t) (jj + 1) * DP], scratch[jj + 1], acc1);
+                for (int s = 0; s < DPL; ++s) {
+                    const int jend = min(D, (s + 1) * G);
+                    const double *col = LT + s * G + g.lane;
+                    double a0[P], a1[P];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) a0[p] = a1[p] = 0.0;
+                    int jj = 0;
+                    for (; jj + 1 < jend; jj += 2) {
+                        const double l0 = col[jj * DP], l1 = col[(jj + 1) * DP];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) {
+                            a0[p] = fma(l0, scratch[jj * P + p], a0[p]);
+                            a1[p] = fma(l1, scratch[(jj + 1) * P + p], a1[p]);
+                        }
+                    }
+                    if (jj < jend) {
+                        const double l0 = col[jj * DP];
+#pragma unroll
+                        for (int p = 0; p < P; ++p) a0[p] = fma(l0, scratch[jj * P + p], a0[p]);
+                    }
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const double z = a0[p] + a1[p];
+                        q[p] = fma(z, z, q[p]);
+                    }
                 }
-                if (jj < jend) acc0 = fma(col[(size_t) jj * DP], scratch[jj], acc0);
-                z[s] = acc0 + acc1;
             }
-            double q = 0.0;
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) q = fma(z[s], z[s], q);
-            q = group_sum(g, q);
-            r = P[0] - 0.5 * q;
+            for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * group_sum(g, q[p]);
             break;
         }
         case NSB200_FAM_GAUSS_MIX_DIAG: {
-            r = 0.0;
             for (int k = 0; k < sm.K; ++k) {
-                const double *pk = P + (size_t) k * (1 + 2 * DP);
-                double q = 0.0;
+                const double *pk = Pm + (size_t) k * (1 + 2 * DP);
+                double q[P];
+#pragma unroll
+                for (int p = 0; p < P; ++p) q[p] = 0.0;
 #pragma unroll
                 for (int s = 0; s < DPL; ++s) {
                     const int j = s * G + g.lane;
-                    double zz = (X[s] - pk[1 + j]) * pk[1 + DP + j];
-                    q = fma(zz, zz, q);
+                    const double mean = pk[1 + j], inv = pk[1 + DP + j];
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const double zz = (X[p][s] - mean) * inv;
+                        q[p] = fma(zz, zz, q[p]);
+                    }
                 }
-                q = group_sum(g, q);
-                double gk = pk[0] - 0.5 * q;
-                r = (k == 0) ? gk : logaddexp(r, gk);
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const double gk = pk[0] - 0.5 * group_sum(g, q[p]);
+                    out[p] = (k == 0) ? gk : logaddexp(out[p], gk);
+                }
             }
             break;
         }
         case NSB200_FAM_EGGBOX: {
-            double y = 1.0;
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) {
-                const int j = s * G + g.lane;
-                if (j < D) y *= cos(0.5 * X[s]);
+            for (int p = 0; p < P; ++p) {
+                double y = 1.0;
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int j = s * G + g.lane;
+                    if (j < D) y *= cos(0.5 * X[p][s]);
+                }
+                y = 2.0 + group_prod(g, y);
+                const double y2 = y * y;
+                out[p] = y2 * y2 * y;
             }
-            y = 2.0 + group_prod(g, y);
-            double y2 = y * y;
-            r = y2 * y2 * y;
             break;
         }
         case NSB200_FAM_ROSENBROCK: {
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) scratch[s * G + g.lane] = X[s];
-            group_sync(g);
-            double y = 0.0;
+            for (int s = 0; s < DPL; ++s)
 #pragma unroll
-            for (int s = 0; s < DPL; ++s) {
-                const int j = s * G + g.lane;
-                if (j < D - 1) {
-                    double a = scratch[j + 1] - X[s] * X[s];
-                    double b = 1.0 - X[s];
-                    y += 100.0 * (a * a) + b * b;
-                }
-            }
-            r = -group_sum(g, y);
-            break;
-        }
-        case NSB200_FAM_SHELLS: {
-            r = 0.0;
-            for (int k = 0; k < sm.K; ++k) {
-                const double *pk = P + (size_t) k * (2 + DP);
-                double ssq = 0.0;
+                for (int p = 0; p < P; ++p) scratch[(s * G + g.lane) * P + p] = X[p][s];
+            group_sync(g);
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                double y = 0.0;
 #pragma unroll
                 for (int s = 0; s < DPL; ++s) {
                     const int j = s * G + g.lane;
-                    double dl = (j < D) ? X[s] - pk[2 + j] : 0.0;
-                    ssq = fma(dl, dl, ssq);
+                    if (j < D - 1) {
+                        const double a = scratch[(j + 1) * P + p] - X[p][s] * X[p][s];
+                        const double b = 1.0 - X[p][s];
+                        y += 100.0 * (a * a) + b * b;
+                    }
                 }
-                ssq = group_sum(g, ssq);
-                const double w = pk[0], rad = pk[1];
-                double e = sqrt(ssq) - rad;
-                double gk = -0.5 * (e * e) / (w * w) - log(sqrt(2.0 * 3.14159265358979323846 * (w * w)));
-                r = (k == 0) ? gk : logaddexp(r, gk);
+                out[p] = -group_sum(g, y);
+            }
+            break;
+        }
+        case NSB200_FAM_SHELLS: {
+            for (int k = 0; k < sm.K; ++k) {
+                const double *pk = Pm + (size_t) k * (3 + DP);
+                const double w = pk[0], rad = pk[1], lognorm = pk[2];
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    double ssq = 0.0;
+#pragma unroll
+                    for (int s = 0; s < DPL; ++s) {
+                        const int j = s * G + g.lane;
+                        const double dl = (j < D) ? X[p][s] - pk[3 + j] : 0.0;
+                        ssq = fma(dl, dl, ssq);
+                    }
+                    ssq = group_sum(g, ssq);
+                    const double e = sqrt(ssq) - rad;
+                    const double gk = -0.5 * (e * e) / (w * w) - lognorm;
+                    out[p] = (k == 0) ? gk : logaddexp(out[p], gk);
+                }
             }
             break;
         }
         default:
-            r = __longlong_as_double(0x7FF8000000000000ll);
+#pragma unroll
+            for (int p = 0; p < P; ++p) out[p] = kNan;
     }
-    if (r != r) r = -__longlong_as_double(0x7FF0000000000000ll);  // ops.py:323-325
-    return r;
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        if (out[p] != out[p]) out[p] = -__longlong_as_double(0x7FF0000000000000ll);  // ops.py:323-325
+    // the scratch is rewritten by the next call: make sure every lane is done reading it
+    group_sync(g);
 }
 
-// Model.forward at the U-space point held across the group.
-template <int DPL>
-__device__ __forceinline__ double forward_group(const ModelSmem &sm, const Grp &g, const double (&u)[DPL],
-                                                double *scratch) {
-    double X[DPL];
-    transform_dims<DPL>(sm, g, u, X);
-    return loglik_group<DPL>(sm, g, X, scratch);
+// Model.forward at P U-space points held across the group.
+template <int G, int DPL, int P>
+__device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
+                                              const double (&u)[P][DPL], double *scratch, double (&out)[P]) {
+    double X[P][DPL];
+    transform_dims<G, DPL, P>(sm, g, u, X);
+    loglik_group<G, DPL, P>(sm, g, row, X, scratch, out);
 }
 
 }  // namespace nsb

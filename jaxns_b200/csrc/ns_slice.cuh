@@ -8,14 +8,24 @@
 // (samplers/uni_slice_sampler.py:343-441, :114-273), resample_indicies (internals/random.py:55-60),
 // _single_uniform_sample (nested_samplers/common/uniform_sample.py:12-60),
 // UniformSampler._get_sample (samplers/uniform_samplers.py:42-85).
+//
+// Two facts about the reference's slice move make it GPU-friendly without changing its results:
+//  (1) the key stream of a slice (run_key chain, t_key draws, after_key) does not depend on any
+//      likelihood value, so lane L of a group precomputes the stream of slice base+L while its
+//      neighbours do the same for theirs, and the direction of the next slice can be drawn while the
+//      current one is still being evaluated;
+//  (2) a rejected proposal shrinks the bracket to its own t (times alpha), which is known before
+//      its likelihood is: the next P proposals of the shrink loop can be generated speculatively and
+//      evaluated together; the first accepted one wins and n_evals counts only up to it, exactly as
+//      the sequential loop would.
 #pragma once
 #include "ns_model.cuh"
+#include "ns_types.cuh"
 
 namespace nsb {
 
-// Number of uniforms per slice drawn ahead of the data (the key stream of a slice does not depend
-// on the likelihood values, so lane L of a group precomputes the stream of slice base+L while its
-// neighbours do the same for theirs; the shrink loop then only reads them).
+// Uniforms per slice drawn ahead by the lane-parallel precompute (shrink steps beyond that fall
+// back to walking the run_key chain inline).
 constexpr int kPre = 8;
 
 struct SliceArgs {
@@ -32,10 +42,14 @@ struct SliceArgs {
     double *ph_logL;
     long long N;
     long long chain_begin, chain_end;
-    int S, k, midpoint, G;
+    int S, k, midpoint;
     // optional packed-row output for the multi-GPU all-gather (row = [U[D], logL, nevals, k x (U[D], logL)])
     double *packed;
     long long packed_row_doubles;
+    // engine mode: key, contour and the current live buffer come from the device-resident control
+    // block, so the host never has to know them (and the launch is a no-op once the loop is done)
+    const DevCtl *ctl;
+    LiveSet live0, live1;
 };
 
 // jnp.linspace(0.5, 1., S)[j]
@@ -48,8 +62,8 @@ __device__ __forceinline__ double alpha_schedule(int j, int S) {
 }
 
 // _sample_direction: d = normal(key, (D,)); d /= ||d||
-template <int DPL>
-__device__ __forceinline__ void sample_direction(const Grp &g, int D, Key key, double (&d)[DPL]) {
+template <int G, int DPL>
+__device__ __forceinline__ void sample_direction(const Grp<G> &g, int D, Key key, double (&d)[DPL]) {
     if (D == 1) {
 #pragma unroll
         for (int s = 0; s < DPL; ++s) d[s] = (s == 0 && g.lane == 0) ? 1.0 : 0.0;
@@ -58,7 +72,7 @@ __device__ __forceinline__ void sample_direction(const Grp &g, int D, Key key, d
     double ss = 0.0;
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
-        const int j = s * g.G + g.lane;
+        const int j = s * G + g.lane;
         d[s] = (j < D) ? normal_from_bits(bits64(key, (uint64_t) j)) : 0.0;
         ss = fma(d[s], d[s], ss);
     }
@@ -68,14 +82,14 @@ __device__ __forceinline__ void sample_direction(const Grp &g, int D, Key key, d
 }
 
 // _slice_bounds: intersection of the line U0 + t d with the unit cube.
-template <int DPL>
-__device__ __forceinline__ void slice_bounds(const Grp &g, int D, const double (&U0)[DPL], const double (&d)[DPL],
+template <int G, int DPL>
+__device__ __forceinline__ void slice_bounds(const Grp<G> &g, int D, const double (&U0)[DPL], const double (&d)[DPL],
                                              double &left, double &right) {
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
     double r = kInf, l = -kInf;
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
-        const int j = s * g.G + g.lane;
+        const int j = s * G + g.lane;
         if (j < D) {
             const double t1 = (1.0 - U0[s]) / d[s];
             const double t0 = -U0[s] / d[s];
@@ -110,45 +124,64 @@ __device__ __forceinline__ long long seed_index(const double *live_logL, const d
 }
 
 // Dynamic shared memory layout of the sampler kernels:
-//   [model image][per chain: scratch[DP] | pre_u[G][kPre] | pre_keys[G][4 x u32]]
-__host__ __device__ inline size_t chain_smem_doubles(int DP, int G) { return (size_t) DP + (size_t) G * (kPre + 2); }
+//   [model image][per chain: scratch[DP][P] | pre_u[G][kPre] | pre_keys[G][4 x u32]]
+__host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool slice) {
+    return (size_t) G * DPL * P + (slice ? (size_t) G * (kPre + 2) : 0);
+}
 
-template <int DPL>
+template <int G, int DPL, int P>
 __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *smem) {
-    const int G = a.G, DP = G * DPL, D = a.model.D;
+    constexpr int DP = G * DPL;
+    const int D = a.model.D;
+    Key base_key = a.key;
+    const double *contour_ptr = a.contour;
+    const double *live_U = a.live_U;
+    const double *live_logL = a.live_logL;
+    if (a.ctl) {
+        if (!a.ctl->active) return;
+        const LiveSet &live = a.ctl->cur ? a.live1 : a.live0;
+        base_key = a.ctl->sample_key;
+        contour_ptr = &a.ctl->contour;
+        live_U = live.U;
+        live_logL = live.logL;
+    }
     ModelSmem sm;
-    stage_model(a.model, DP, smem, sm);
+    stage_model<G, DPL>(a.model, smem, sm);
     __syncthreads();
-    const Grp g = make_group(G);
-    const int chains_per_block = kThreadsPerBlock / G;
+    const Grp<G> g;
+    constexpr int chains_per_block = kThreadsPerBlock / G;
     const int local_chain = threadIdx.x / G;
     const long long chain = a.chain_begin + (long long) blockIdx.x * chains_per_block + local_chain;
     if (chain >= a.chain_end) return;
+    DenseRow<G, DPL> row;
+    row.load(sm, g.lane);
 
-    double *cs = smem + model_smem_doubles(sm.family, D, DP, sm.K) + (size_t) local_chain * chain_smem_doubles(DP, G);
+    double *cs = smem + model_smem_doubles(sm.family, D, G, DPL, sm.K) +
+                 (size_t) local_chain * chain_smem_doubles(G, DPL, P, true);
     double *scratch = cs;
-    double *pre_u = cs + DP;                                    // [G][kPre]
-    uint32_t *pre_k = (uint32_t *) (cs + DP + (size_t) G * kPre);  // [G][4]: after_key, run_key
+    double *pre_u = cs + DP * P;                                       // [G][kPre]
+    uint32_t *pre_k = (uint32_t *) (cs + DP * P + (size_t) G * kPre);  // [G][4]: after_key, run_key
 
-    const double contour = *a.contour;
+    const double contour = *contour_ptr;
     const int S = a.S, kph = a.k;
+    const bool midpoint = a.midpoint != 0;
 
     // ---- chain prelude (bases.py:64; uni_slice_sampler.py:343-358, :410-413)
-    const Key chain_key = split_child(a.key, (uint64_t) chain);
+    const Key chain_key = split_child(base_key, (uint64_t) chain);
     const Key sample_key = split_child(chain_key, 0);
     const Key seed_key = split_child(chain_key, 1);
     const double useed = uniform01(seed_key, 0);
-    const long long sidx = seed_index(a.live_logL, a.seed_table, a.N, contour, useed);
-    double U0[DPL], d[DPL], x[DPL];
+    const long long sidx = seed_index(live_logL, a.seed_table, a.N, contour, useed);
+    double U0[DPL], d[DPL];
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
-        U0[s] = (j < D) ? a.live_U[sidx * D + j] : 0.5;
+        U0[s] = (j < D) ? live_U[sidx * D + j] : 0.5;
     }
-    double logL0 = a.live_logL[sidx];
+    double logL0 = live_logL[sidx];
     const Key direction_key = split_child(sample_key, 0);
     const Key sample_key2 = split_child(sample_key, 1);
-    sample_direction<DPL>(g, D, direction_key, d);
+    sample_direction<G, DPL>(g, D, direction_key, d);
 
     const long long out_row = chain - a.chain_begin;
     long long nev = 0;
@@ -163,7 +196,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                 Key t_key = split_child(slice_key, 2);
                 const Key after_key = split_child(slice_key, 3);
                 pre_u[g.lane * kPre + 0] = uniform01(t_key, 0);
-#pragma unroll
+#pragma unroll 1
                 for (int p = 1; p < kPre; ++p) {
                     t_key = split_child(run_key, 1);  // :169 (child 2 = shrink_key unused)
                     run_key = split_child(run_key, 0);
@@ -183,41 +216,65 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
             const double alpha = alpha_schedule(j, S);
             const double *uq = pre_u + jl * kPre;
             const uint32_t *pk = pre_k + jl * 4;
+            // direction of the NEXT slice (:272): independent of this slice's evaluations, issued
+            // first so that its Threefry / erf_inv latency overlaps them
+            double dnext[DPL];
+            sample_direction<G, DPL>(g, D, Key{pk[0], pk[1]}, dnext);
             double left, right;
-            slice_bounds<DPL>(g, D, U0, d, left, right);
-            double t = left + uq[0] * (right - left);  // _pick_point_in_interval :83-85
-#pragma unroll
-            for (int s = 0; s < DPL; ++s) x[s] = fma(t, d[s], U0[s]);
-            double logL = forward_group<DPL>(sm, g, x, scratch);
-            int ne = 1;
+            slice_bounds<G, DPL>(g, D, U0, d, left, right);
             Key run_key = Key{pk[2], pk[3]};
-            // shrink loop (:160-196)
-            while (!((logL > contour) || ((logL0 == contour) && (logL == contour)))) {
-                if (t < 0.0) left = t;  // _shrink_interval :92-111
-                if (t > 0.0) right = t;
-                if (a.midpoint) {
-                    if (t < 0.0) left = alpha * left;
-                    if (t > 0.0) right = alpha * right;
-                }
-                double uu;
-                if (ne < kPre) {
-                    uu = uq[ne];
-                } else {
-                    const Key t_key = split_child(run_key, 1);
-                    run_key = split_child(run_key, 0);
-                    uu = uniform01(t_key, 0);
-                }
-                t = left + uu * (right - left);
+            int ne = 0;  // proposals generated so far in this slice
+            double logL_acc = 0.0;
+            for (;;) {
+                // ---- generate P proposals assuming each previous one is rejected (:92-111, :169-186)
+                double ts[P], x[P][DPL], logL[P];
+                double l = left, r = right;
 #pragma unroll
-                for (int s = 0; s < DPL; ++s) x[s] = fma(t, d[s], U0[s]);
-                logL = forward_group<DPL>(sm, g, x, scratch);
-                ne += 1;
+                for (int p = 0; p < P; ++p) {
+                    double uu;
+                    const int n = ne + p;
+                    if (n < kPre) {
+                        uu = uq[n];
+                    } else {
+                        const Key t_key = split_child(run_key, 1);
+                        run_key = split_child(run_key, 0);
+                        uu = uniform01(t_key, 0);
+                    }
+                    const double t = l + uu * (r - l);  // _pick_point_in_interval :83-85
+                    ts[p] = t;
+                    if (t < 0.0) l = midpoint ? alpha * t : t;  // _shrink_interval
+                    if (t > 0.0) r = midpoint ? alpha * t : t;
+#pragma unroll
+                    for (int s = 0; s < DPL; ++s) x[p][s] = fma(t, d[s], U0[s]);
+                }
+                forward_group<G, DPL, P>(sm, g, row, x, scratch, logL);
+                // ---- first accepted proposal wins (:160-166)
+                int hit = -1;
+#pragma unroll
+                for (int p = P - 1; p >= 0; --p) {
+                    const bool ok = (logL[p] > contour) || ((logL0 == contour) && (logL[p] == contour));
+                    if (ok) hit = p;
+                }
+                if (hit >= 0) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        if (p == hit) {
+#pragma unroll
+                            for (int s = 0; s < DPL; ++s) U0[s] = x[p][s];
+                            logL_acc = logL[p];
+                        }
+                    }
+                    ne += hit + 1;
+                    break;
+                }
+                ne += P;
+                left = l;
+                right = r;
             }
-#pragma unroll
-            for (int s = 0; s < DPL; ++s) U0[s] = x[s];
-            logL0 = logL;
+            logL0 = logL_acc;
             nev += ne;
-            sample_direction<DPL>(g, D, Key{pk[0], pk[1]}, d);  // :272
+#pragma unroll
+            for (int s = 0; s < DPL; ++s) d[s] = dnext[s];
             // phantom capture: cumulative_samples[-(k+1):-1] (:430-440)
             if (kph > 0 && j >= S - 1 - kph && j < S - 1) {
                 const long long slot = out_row * kph + (j - (S - 1 - kph));
@@ -257,10 +314,10 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     }
 }
 
-template <int DPL>
+template <int G, int DPL, int P>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) {
     extern __shared__ double smem[];
-    slice_chains_body<DPL>(a, smem);
+    slice_chains_body<G, DPL, P>(a, smem);
 }
 
 // ---- prior draws for the initial live set / uniform rejection sampler --------------------------
@@ -272,62 +329,64 @@ struct DrawArgs {
     double *out_logL;
     long long *out_nevals;
     long long begin, end;
-    int G;
     int uniform_sampler;  // 0: _single_uniform_sample ; 1: UniformSampler._get_sample
 };
 
 // Model.sample_U: uniform(split(key, 2)[1], (D,))
-template <int DPL>
-__device__ __forceinline__ void sample_U(const Grp &g, int D, Key key, double (&u)[DPL]) {
+template <int G, int DPL>
+__device__ __forceinline__ void sample_U(const Grp<G> &g, int D, Key key, double (&u)[1][DPL]) {
     const Key k = split_child(key, 1);
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
-        const int j = s * g.G + g.lane;
-        u[s] = (j < D) ? uniform01(k, (uint64_t) j) : 0.5;
+        const int j = s * G + g.lane;
+        u[0][s] = (j < D) ? uniform01(k, (uint64_t) j) : 0.5;
     }
 }
 
-template <int DPL>
+template <int G, int DPL>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
     extern __shared__ double smem[];
-    const int G = a.G, DP = G * DPL, D = a.model.D;
+    constexpr int DP = G * DPL;
+    const int D = a.model.D;
     ModelSmem sm;
-    stage_model(a.model, DP, smem, sm);
+    stage_model<G, DPL>(a.model, smem, sm);
     __syncthreads();
-    const Grp g = make_group(G);
-    const int per_block = kThreadsPerBlock / G;
+    const Grp<G> g;
+    constexpr int per_block = kThreadsPerBlock / G;
     const int local = threadIdx.x / G;
     const long long i = a.begin + (long long) blockIdx.x * per_block + local;
     if (i >= a.end) return;
-    double *scratch = smem + model_smem_doubles(sm.family, D, DP, sm.K) + (size_t) local * DP;
+    DenseRow<G, DPL> row;
+    row.load(sm, g.lane);
+    double *scratch = smem + model_smem_doubles(sm.family, D, G, DPL, sm.K) + (size_t) local * DP;
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
     const double contour = a.contour ? *a.contour : -kInf;
     const Key k0 = split_child(a.key, (uint64_t) i);
     Key key = split_child(k0, 0);
     Key sk = split_child(k0, 1);
-    double u[DPL];
-    sample_U<DPL>(g, D, sk, u);
-    double logL = forward_group<DPL>(sm, g, u, scratch);
+    double u[1][DPL], logL[1];
+    sample_U<G, DPL>(g, D, sk, u);
+    forward_group<G, DPL, 1>(sm, g, row, u, scratch, logL);
     long long ne = 1;
     for (;;) {
         bool done;
-        if (a.uniform_sampler) done = (logL > contour) || (logL == contour) || (ne >= 100);
-        else done = !(logL <= contour);
+        if (a.uniform_sampler) done = (logL[0] > contour) || (logL[0] == contour) || (ne >= 100);
+        else done = !(logL[0] <= contour);
         if (done) break;
         sk = split_child(key, 1);
         key = split_child(key, 0);
-        sample_U<DPL>(g, D, sk, u);
-        logL = forward_group<DPL>(sm, g, u, scratch);
+        sample_U<G, DPL>(g, D, sk, u);
+        forward_group<G, DPL, 1>(sm, g, row, u, scratch, logL);
         ne += 1;
     }
     const long long o = i - a.begin;
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
-        if (j < D) a.out_U[o * D + j] = u[s];
+        if (j < D) a.out_U[o * D + j] = u[0][s];
     }
     if (g.lane == 0) {
-        a.out_logL[o] = logL;
+        a.out_logL[o] = logL[0];
         a.out_nevals[o] = ne;
     }
 }
@@ -339,36 +398,38 @@ struct ForwardArgs {
     double *out_logL;
     double *out_X;
     long long n;
-    int G;
 };
 
-template <int DPL>
+template <int G, int DPL>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_forward(ForwardArgs a) {
     extern __shared__ double smem[];
-    const int G = a.G, DP = G * DPL, D = a.model.D;
+    constexpr int DP = G * DPL;
+    const int D = a.model.D;
     ModelSmem sm;
-    stage_model(a.model, DP, smem, sm);
+    stage_model<G, DPL>(a.model, smem, sm);
     __syncthreads();
-    const Grp g = make_group(G);
-    const int per_block = kThreadsPerBlock / G;
+    const Grp<G> g;
+    constexpr int per_block = kThreadsPerBlock / G;
     const int local = threadIdx.x / G;
     const long long i = (long long) blockIdx.x * per_block + local;
     if (i >= a.n) return;
-    double *scratch = smem + model_smem_doubles(sm.family, D, DP, sm.K) + (size_t) local * DP;
-    double u[DPL], X[DPL];
+    DenseRow<G, DPL> row;
+    row.load(sm, g.lane);
+    double *scratch = smem + model_smem_doubles(sm.family, D, G, DPL, sm.K) + (size_t) local * DP;
+    double u[1][DPL], X[1][DPL], logL[1];
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
-        u[s] = (j < D) ? a.U[i * D + j] : 0.5;
+        u[0][s] = (j < D) ? a.U[i * D + j] : 0.5;
     }
-    transform_dims<DPL>(sm, g, u, X);
-    const double logL = loglik_group<DPL>(sm, g, X, scratch);
+    transform_dims<G, DPL, 1>(sm, g, u, X);
+    loglik_group<G, DPL, 1>(sm, g, row, X, scratch, logL);
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
-        if (j < D && a.out_X) a.out_X[i * D + j] = X[s];
+        if (j < D && a.out_X) a.out_X[i * D + j] = X[0][s];
     }
-    if (g.lane == 0 && a.out_logL) a.out_logL[i] = logL;
+    if (g.lane == 0 && a.out_logL) a.out_logL[i] = logL[0];
 }
 
 }  // namespace nsb

@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -93,14 +94,40 @@ static int set_smem(KernelT kernel, size_t bytes) {
     return 0;
 }
 
-#define NSB_DISPATCH_DPL(DPLV, ...)                          \
-    switch (DPLV) {                                          \
-        case 1: { constexpr int kDPL = 1; __VA_ARGS__; } break; \
-        case 2: { constexpr int kDPL = 2; __VA_ARGS__; } break; \
-        case 4: { constexpr int kDPL = 4; __VA_ARGS__; } break; \
-        case 8: { constexpr int kDPL = 8; __VA_ARGS__; } break; \
-        default: return fail("unsupported DPL %d", DPLV);    \
+// Compile-time (G, DPL) instantiations: G < 32 only with DPL == 1.
+#define NSB_DISPATCH_GEOM(GEOM, ...)                                                \
+    if ((GEOM).G == 32) {                                                           \
+        switch ((GEOM).DPL) {                                                       \
+            case 1: { constexpr int kG = 32, kDPL = 1; __VA_ARGS__; } break;        \
+            case 2: { constexpr int kG = 32, kDPL = 2; __VA_ARGS__; } break;        \
+            case 4: { constexpr int kG = 32, kDPL = 4; __VA_ARGS__; } break;        \
+            case 8: { constexpr int kG = 32, kDPL = 8; __VA_ARGS__; } break;        \
+            default: return fail("unsupported DPL %d", (GEOM).DPL);                 \
+        }                                                                           \
+    } else {                                                                        \
+        switch ((GEOM).G) {                                                         \
+            case 1: { constexpr int kG = 1, kDPL = 1; __VA_ARGS__; } break;         \
+            case 2: { constexpr int kG = 2, kDPL = 1; __VA_ARGS__; } break;         \
+            case 4: { constexpr int kG = 4, kDPL = 1; __VA_ARGS__; } break;         \
+            case 8: { constexpr int kG = 8, kDPL = 1; __VA_ARGS__; } break;         \
+            case 16: { constexpr int kG = 16, kDPL = 1; __VA_ARGS__; } break;       \
+            default: return fail("unsupported group size %d", (GEOM).G);            \
+        }                                                                           \
     }
+
+// Number of proposals evaluated speculatively per shrink round (ns_slice.cuh).  NSB200_SPEC
+// overrides it for the D <= 32 instantiation (tuning knob; results do not depend on it).
+static int pick_spec(const Geometry &g) {
+    if (g.G == 32 && g.DPL == 1) {
+        const char *e = getenv("NSB200_SPEC");
+        if (e) {
+            const int v = atoi(e);
+            if (v == 1 || v == 2 || v == 4) return v;
+        }
+        return 2;
+    }
+    return 2;
+}
 
 // -------------------------------------------------------------------------------------------------
 // jax.random primitives
@@ -166,9 +193,9 @@ extern "C" int nsb200_random_normal(const uint32_t key[2], int64_t n, double *ou
 // -------------------------------------------------------------------------------------------------
 // model / samplers
 // -------------------------------------------------------------------------------------------------
-static size_t sampler_smem_bytes(const NsModelDesc &m, const Geometry &g, bool slice) {
-    const size_t per_chain = slice ? chain_smem_doubles(g.DP, g.G) : (size_t) g.DP;
-    return 8 * (model_smem_doubles(m.family, m.D, g.DP, m.K) + (kThreadsPerBlock / g.G) * per_chain);
+static size_t sampler_smem_bytes(const NsModelDesc &m, const Geometry &g, int P, bool slice) {
+    const size_t per_chain = chain_smem_doubles(g.G, g.DPL, P, slice);
+    return 8 * (model_smem_doubles(m.family, m.D, g.G, g.DPL, m.K) + (kThreadsPerBlock / g.G) * per_chain);
 }
 
 extern "C" int nsb200_forward_batch(const NsModelDesc *model, const double *U, int64_t n, double *out_logL,
@@ -178,12 +205,12 @@ extern "C" int nsb200_forward_batch(const NsModelDesc *model, const double *U, i
     if (!U) return fail("U is NULL");
     Geometry g;
     if (pick_geometry(model->D, g)) return 1;
-    ForwardArgs a{*model, U, out_logL, out_X, n, g.G};
-    const size_t smem = sampler_smem_bytes(*model, g, false);
+    ForwardArgs a{*model, U, out_logL, out_X, n};
+    const size_t smem = sampler_smem_bytes(*model, g, 1, false);
     const int per_block = kThreadsPerBlock / g.G;
-    NSB_DISPATCH_DPL(g.DPL, {
-        if (set_smem(k_forward<kDPL>, smem)) return 1;
-        k_forward<kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, (cudaStream_t) stream>>>(a);
+    NSB_DISPATCH_GEOM(g, {
+        if (set_smem(k_forward<kG, kDPL>, smem)) return 1;
+        k_forward<kG, kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, (cudaStream_t) stream>>>(a);
     });
     NSB_LAUNCH_CHECK();
     return 0;
@@ -213,12 +240,12 @@ static int launch_draw(const NsModelDesc *model, Key key, const double *contour,
     if (end <= begin) return 0;
     Geometry g;
     if (pick_geometry(model->D, g)) return 1;
-    DrawArgs a{*model, key, contour, out_U, out_logL, out_nevals, begin, end, g.G, uniform_sampler};
-    const size_t smem = sampler_smem_bytes(*model, g, false);
+    DrawArgs a{*model, key, contour, out_U, out_logL, out_nevals, begin, end, uniform_sampler};
+    const size_t smem = sampler_smem_bytes(*model, g, 1, false);
     const int per_block = kThreadsPerBlock / g.G;
-    NSB_DISPATCH_DPL(g.DPL, {
-        if (set_smem(k_draw<kDPL>, smem)) return 1;
-        k_draw<kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, st>>>(a);
+    NSB_DISPATCH_GEOM(g, {
+        if (set_smem(k_draw<kG, kDPL>, smem)) return 1;
+        k_draw<kG, kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, st>>>(a);
     });
     NSB_LAUNCH_CHECK();
     return 0;
@@ -243,19 +270,29 @@ extern "C" int nsb200_uniform_batch(const NsModelDesc *model, const uint32_t key
                        (long long *) out_nevals, 1, (cudaStream_t) stream);
 }
 
-static int launch_slice(const SliceArgs &a0, cudaStream_t st) {
-    SliceArgs a = a0;
+template <int G, int DPL, int P>
+static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st) {
+    const long long n = a.chain_end - a.chain_begin;
+    const size_t smem = sampler_smem_bytes(a.model, g, P, true);
+    if (set_smem(k_slice_chains<G, DPL, P>, smem)) return 1;
+    k_slice_chains<G, DPL, P><<<grid_for(n, kThreadsPerBlock / G), kThreadsPerBlock, smem, st>>>(a);
+    return 0;
+}
+
+static int launch_slice(const SliceArgs &a, cudaStream_t st) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
-    a.G = g.G;
-    const long long n = a.chain_end - a.chain_begin;
-    if (n <= 0) return 0;
-    const size_t smem = sampler_smem_bytes(a.model, g, true);
-    const int per_block = kThreadsPerBlock / g.G;
-    NSB_DISPATCH_DPL(g.DPL, {
-        if (set_smem(k_slice_chains<kDPL>, smem)) return 1;
-        k_slice_chains<kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, st>>>(a);
-    });
+    if (a.chain_end <= a.chain_begin) return 0;
+    const int P = pick_spec(g);
+    if (g.G == 32 && g.DPL == 1) {
+        int rc;
+        if (P == 1) rc = launch_slice_t<32, 1, 1>(a, g, st);
+        else if (P == 4) rc = launch_slice_t<32, 1, 4>(a, g, st);
+        else rc = launch_slice_t<32, 1, 2>(a, g, st);
+        if (rc) return rc;
+    } else {
+        NSB_DISPATCH_GEOM(g, { if (launch_slice_t<kG, kDPL, 2>(a, g, st)) return 1; });
+    }
     NSB_LAUNCH_CHECK();
     return 0;
 }
@@ -298,6 +335,7 @@ extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams 
     a.midpoint = p->midpoint_shrink;
     a.packed = nullptr;
     a.packed_row_doubles = 0;
+    a.ctl = nullptr;
     return launch_slice(a, (cudaStream_t) stream);
 }
 
@@ -418,40 +456,6 @@ extern "C" int nsb200_logsumexp(const double *x, int64_t n, double *out, void *w
 // -------------------------------------------------------------------------------------------------
 // engine
 // -------------------------------------------------------------------------------------------------
-// Slice kernel launched from the loop: key, contour and the current live buffer come from the
-// device-resident control block, so the host never has to know them.
-template <int DPL>
-__global__ void __launch_bounds__(kThreadsPerBlock)
-k_slice_chains_engine(NsModelDesc model, const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
-                      const double *seed_table, double *packed, long long row_doubles, long long N,
-                      long long begin, long long end, int S, int k, int midpoint, int G) {
-    extern __shared__ double smem[];
-    if (!ctl->active) return;
-    const LiveSet &live = ctl->cur ? live1 : live0;
-    SliceArgs a;
-    a.model = model;
-    a.key = ctl->sample_key;
-    a.contour = &ctl->contour;
-    a.live_U = live.U;
-    a.live_logL = live.logL;
-    a.seed_table = seed_table;
-    a.out_U = nullptr;
-    a.out_logL = nullptr;
-    a.out_nevals = nullptr;
-    a.ph_U = nullptr;
-    a.ph_logL = nullptr;
-    a.N = N;
-    a.chain_begin = begin;
-    a.chain_end = end;
-    a.S = S;
-    a.k = k;
-    a.midpoint = midpoint;
-    a.G = G;
-    a.packed = packed;
-    a.packed_row_doubles = row_doubles;
-    slice_chains_body<DPL>(a, smem);
-}
-
 __global__ void k_fill_f64(double *p, long long n, double v) {
     for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) p[i] = v;
 }
@@ -688,21 +692,25 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
     // this rank's chains -> its block of the gather buffer
-    Geometry g;
-    if (pick_geometry(D, g)) return 1;
     const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
+    SliceArgs a;
+    memset(&a, 0, sizeof(a));
+    a.model = e->cfg.model;
+    a.seed_table = e->seed_table;
+    a.N = e->N;
+    a.chain_begin = begin;
+    a.chain_end = end;
+    a.S = e->cfg.num_slices;
+    a.k = e->cfg.num_phantom;
+    a.midpoint = e->cfg.midpoint_shrink;
+    a.packed = e->packed + begin * e->row_doubles;
+    a.packed_row_doubles = e->row_doubles;
+    a.ctl = e->ctl;
+    a.live0 = e->live[0];
+    a.live1 = e->live[1];
     cudaEvent_t e0 = next_event(e), e1 = next_event(e);
     cudaEventRecord(e0, st);
-    {
-        const size_t smem = sampler_smem_bytes(e->cfg.model, g, true);
-        const int per_block = kThreadsPerBlock / g.G;
-        NSB_DISPATCH_DPL(g.DPL, {
-            if (set_smem(k_slice_chains_engine<kDPL>, smem)) return 1;
-            k_slice_chains_engine<kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, st>>>(
-                e->cfg.model, e->ctl, e->live[0], e->live[1], e->seed_table, e->packed + begin * e->row_doubles,
-                e->row_doubles, e->N, begin, end, e->cfg.num_slices, e->cfg.num_phantom, e->cfg.midpoint_shrink, g.G);
-        });
-    }
+    if (launch_slice(a, st)) return 1;
     cudaEventRecord(e1, st);
     NSB_LAUNCH_CHECK();
     e->slice_launches += 1;

@@ -1,0 +1,166 @@
+"""CPU tests of the host-side mirror of the reference interface and of the C-ABI library surface
+(no compute calls: there is no GPU here)."""
+import ctypes
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _model(D=4, uniform=False):
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd, likelihoods as lk
+
+    def prior_model():
+        if uniform:
+            x = yield j.Prior(tfpd.Uniform(low=np.zeros(D), high=np.ones(D)), name="x")
+        else:
+            x = yield j.Prior(tfpd.Normal(loc=np.zeros(D), scale=np.ones(D)), name="x")
+        return x
+
+    return j.Model(prior_model, lk.DenseGaussianLikelihood(np.ones(D), covariance_matrix=np.eye(D)))
+
+
+def test_library_exports_every_declared_symbol():
+    from jaxns_b200 import _lib
+    L = _lib.lib()
+    header = open(os.path.join(ROOT, "include", "nsb200.h")).read()
+    declared = set(re.findall(r"\b(nsb200_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(L, name) is not None
+    assert L.nsb200_abi_version() == 1
+    assert L.nsb200_workspace_bytes(_lib.WS_ARGSORT, 1000) > 0
+    assert L.nsb200_workspace_bytes(99, 1000) == -1
+
+
+def test_struct_layouts_match_header():
+    from jaxns_b200 import _lib
+    assert ctypes.sizeof(_lib.NsModelDesc) == 48
+    assert ctypes.sizeof(_lib.NsSliceParams) == 48
+    assert ctypes.sizeof(_lib.NsEvidenceCalc) == 64
+    assert ctypes.sizeof(_lib.NsTermCond) == 8 + 11 * 8
+    assert ctypes.sizeof(_lib.NsRegister) == 8 + 64 + 64 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8 + 8
+
+
+def test_no_cpu_fallback():
+    """The product path must fail loudly without CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    m = _model()
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.forward(np.full(4, 0.5))
+    import jaxns_b200 as j
+    ns = j.NestedSampler(model=m, num_live_points=20)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        ns(j.random.PRNGKey(0))
+
+
+def test_round_up_helpers():
+    """/root/reference/src/jaxns/nested_samplers/sharded/tests/test_sharded_static.py:4-7"""
+    from jaxns_b200.nested_sampler import round_up_max_samples, round_up_num_live_points
+    assert round_up_num_live_points(10, 0.5, 1) == 10
+    assert round_up_num_live_points(10, 0.5, 2) == 12
+    assert round_up_num_live_points(10, 0.5, 3) == 12
+    assert round_up_max_samples(1000, 7, 2) == 1008
+
+
+def test_nested_sampler_defaults():
+    """public.py:69-107"""
+    import jaxns_b200 as j
+    m = _model(D=8)
+    ns = j.NestedSampler(model=m)
+    assert (ns.num_slices, ns.k, ns.c, ns.max_samples, ns.num_live_points) == (40, 0, 240, 24000, 240)
+    ns = j.NestedSampler(model=m, difficult_model=True)
+    assert (ns.num_slices, ns.k, ns.c) == (80, 0, 800)
+    assert ns.nested_sampler.sampler.midpoint_shrink is False
+    ns = j.NestedSampler(model=m, parameter_estimation=True)
+    assert (ns.k, ns.c, ns.max_samples) == (8, 240, 240 * 9 * 100)
+    ns = j.NestedSampler(model=m, num_live_points=3200, parameter_estimation=True)
+    assert ns.c == 355  # int(3200 / 9)
+    ns = j.NestedSampler(model=_model(32), num_live_points=3200)
+    assert (ns.num_slices, ns.c, ns.max_samples) == (160, 3200, 320000)
+    assert j.DefaultNestedSampler is j.NestedSampler
+    with pytest.raises(ValueError):
+        j.NestedSampler(model=m, k=40)
+    with pytest.raises(ValueError):
+        j.NestedSampler(model=m, s=0)
+
+
+def test_slice_sampler_validation():
+    """uni_slice_sampler.py:305-325"""
+    import jaxns_b200 as j
+    m = _model()
+    with pytest.raises(ValueError, match="num_slices"):
+        j.UniDimSliceSampler(model=m, num_slices=0, num_phantom_save=0, midpoint_shrink=True, perfect=True)
+    with pytest.raises(ValueError, match="num_phantom_save"):
+        j.UniDimSliceSampler(model=m, num_slices=3, num_phantom_save=3, midpoint_shrink=True, perfect=True)
+    with pytest.raises(ValueError, match="perfect"):
+        j.UniDimSliceSampler(model=m, num_slices=3, num_phantom_save=0, midpoint_shrink=True, perfect=False)
+    with pytest.raises(NotImplementedError):
+        j.UniDimSliceSampler(model=m, num_slices=3, num_phantom_save=0, midpoint_shrink=True, perfect=True,
+                             adaptive_shrink=True)
+
+
+def test_model_descriptor_packing():
+    from jaxns_b200 import _consts
+    m = _model(D=3)
+    fam, D, pk, K, a, b, params = m.host_arrays()
+    assert (fam, D, pk, K) == (_consts.FAM_GAUSS_DENSE, 3, _consts.PRIOR_NORMAL, 0)
+    assert params.size == 1 + 3 + 9
+    np.testing.assert_allclose(params[0], -1.5 * np.log(2 * np.pi))
+    np.testing.assert_allclose(params[4:].reshape(3, 3), np.eye(3))
+    assert m.U_ndims == 3
+    mu = _model(D=2, uniform=True)
+    assert mu.host_arrays()[2] == _consts.PRIOR_UNIFORM
+
+
+def test_model_rejects_unregistered_likelihood():
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(low=0.0, high=1.0), name="x")
+        return x
+
+    with pytest.raises(NotImplementedError):
+        j.Model(prior_model, lambda x: -x ** 2)
+
+
+def test_termination_condition_algebra_and_host_mirror():
+    """types.py:26-74, termination.py:13-147"""
+    import jaxns_b200 as j
+    from jaxns_b200 import termination as T
+    from jaxns_b200.types import (EvidenceCalculation, TerminationConditionConjunction,
+                                  TerminationConditionDisjunction, TerminationRegister)
+    a = j.TerminationCondition(max_samples=100)
+    b = j.TerminationCondition(dlogZ=0.1)
+    assert isinstance(a & b, TerminationConditionConjunction) and isinstance(a | b, TerminationConditionDisjunction)
+    ninf = -math.inf
+    init = EvidenceCalculation(ninf, 0.0, 0.0, ninf, ninf, ninf, ninf, ninf)
+    reg = TerminationRegister(0, init, init, 0, ninf, 0.0, False, False, math.inf, math.inf, ninf)
+    # initial register: dlogZ compares nan < x -> False; efficiency 0.0 < 0.1 -> bit 6
+    assert T.determine_termination(b, reg) == (False, 0)
+    assert T.determine_termination(j.TerminationCondition(efficiency_threshold=0.1, dlogZ=0.0, max_samples=10), reg) == (True, 64)
+    reg2 = reg._replace(num_samples_used=100, plateau=True)
+    assert T.determine_termination(a, reg2) == (True, 1 + 128)
+    assert T.determine_termination(a | b, reg2) == (True, 1 + 128)
+    # reference quirk: a conjunction starts from done=False and ANDs, so it never fires
+    assert T.determine_termination(a & a, reg2) == (False, 0)
+    tc = T.to_c(j.TerminationCondition(dlogZ=0.5, max_samples=7, peak_XL_frac=0.1))
+    assert tc.mask == (1 << 3) | (1 << 4) | (1 << 10) and tc.dlogZ == 0.5 and tc.max_samples == 7.0
+
+
+def test_oracle_is_not_imported_by_product():
+    """The oracle is test infrastructure: nothing under jaxns_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "jaxns_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"

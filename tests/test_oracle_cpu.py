@@ -1,0 +1,186 @@
+"""CPU tests: pin the oracle against every golden vector / known answer available without JAX
+(SURVEY §8c), and check its own internal consistency (table route == O(N) scan, analytic log Z)."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy import special
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_threefry_random123_kats(oracle):
+    assert oracle.threefry2x32(0, 0, 0, 0) == (0x6b200159, 0x99ba4efe)
+    assert oracle.threefry2x32(0xffffffff, 0xffffffff, 0xffffffff, 0xffffffff) == (0x1cb996fc, 0xbb002be7)
+    assert oracle.threefry2x32(0x13198a2e, 0x03707344, 0x243f6a88, 0x85a308d3) == (0xc4923a9c, 0x483df7a0)
+
+
+def test_threefry_published_jax_words(oracle):
+    # legacy jax.random.split(PRNGKey(0)) (counts [0,1,2,3] -> x0=[0,1], x1=[2,3]) is widely published
+    a = oracle.threefry2x32(0, 0, 0, 2)
+    b = oracle.threefry2x32(0, 0, 1, 3)
+    assert [[a[0], b[0]], [a[1], b[1]]] == [[4146024105, 967050713], [2718843009, 1272950319]]
+    # partitionable layout
+    np.testing.assert_array_equal(oracle.split(oracle.PRNGKey(0), 2),
+                                  np.array([[1797259609, 2579123966], [928981903, 3453687069]], dtype=np.uint32))
+    np.testing.assert_array_equal(oracle.split(oracle.PRNGKey(42), 2),
+                                  np.array([[1832780943, 270669613], [64467757, 2916123636]], dtype=np.uint32))
+    assert oracle.uniform(oracle.PRNGKey(42), 1)[0] == 0.4267275666499091
+
+
+def test_golden_fixture_rng(oracle):
+    g = json.load(open(os.path.join(GOLDEN, "rng_vectors.json")))
+    for case in g["cases"]:
+        key = np.array(case["key"], dtype=np.uint32)
+        np.testing.assert_array_equal(oracle.split(key, 4), np.array(case["split4"], dtype=np.uint32))
+        np.testing.assert_array_equal(oracle.random_bits64(key, 4), np.array(case["bits64"], dtype=np.uint64))
+        np.testing.assert_array_equal(oracle.uniform(key, 4), np.array(case["uniform"]))
+        np.testing.assert_allclose(oracle.normal(key, 4), np.array(case["normal"]), rtol=1e-14)
+
+
+def test_ndtri_is_cephes(oracle):
+    p = np.concatenate([np.random.default_rng(0).uniform(size=5000), 10.0 ** -np.arange(1, 300, 7.),
+                        1 - 10.0 ** -np.arange(1, 16.)])
+    np.testing.assert_allclose(oracle.ndtri(p), special.ndtri(p), rtol=2e-15)
+    assert oracle.ndtri(0.0)[0] == -np.inf and oracle.ndtri(1.0)[0] == np.inf
+
+
+def test_erfinv_polynomial(oracle):
+    x = np.random.default_rng(1).uniform(-0.999, 0.999, size=5000)
+    np.testing.assert_allclose(oracle.erfinv(x), special.erfinv(x), rtol=5e-15)
+    # the tails inherit XLA's -log1p(-x*x) cancellation: accurate to ~1e-10 only
+    xt = 1 - 10.0 ** -np.arange(4, 15.)
+    np.testing.assert_allclose(oracle.erfinv(xt), special.erfinv(xt), rtol=2e-10)
+    assert oracle.erfinv(1.0)[0] == np.inf and oracle.erfinv(-1.0)[0] == -np.inf
+
+
+def test_tree_golden_vectors(oracle):
+    """/root/reference/src/jaxns/internals/tests/test_tree_structure.py:19-70"""
+    idx, n = oracle.count_crossed_edges([0, 0, 0, 1, 2, 3], [1, 2, 3, 4, 5, 6])
+    assert idx.tolist() == [0, 1, 2, 3, 4, 5] and n.tolist() == [3, 3, 3, 3, 2, 1]
+    idx, n = oracle.count_crossed_edges([0, 0, 0, 1, 3, 2], [1, 2, 3, 4, 6, 5])
+    assert idx.tolist() == [0, 1, 2, 3, 5, 4] and n.tolist() == [3, 3, 3, 3, 2, 1]
+    i1, n1 = oracle.count_crossed_edges([0, 0, 0, 1, 2, 3, 4, 5, 0, 0], [1, 2, 3, 4, 5, 6, 7, 8, np.inf, np.inf], 8)
+    i2, n2 = oracle.count_crossed_edges([0, 0, 0, 1, 2, 3, 4, 5], [1, 2, 3, 4, 5, 6, 7, 8])
+    assert n1[:8].tolist() == n2.tolist() and i1[:8].tolist() == i2.tolist() and n1[8:].tolist() == [0, 0]
+
+
+def test_tree_random_matches_naive(oracle):
+    """seeded random tree of test_tree_structure.py:73-103: fast count == O(N^2) definition"""
+    np.random.seed(42)
+    log_L = [0]
+    parent = []
+    for idx in range(10):
+        log_L.append(log_L[idx] + np.random.uniform(low=0, high=1 - log_L[idx]) ** 4)
+        parent.append(idx)
+    for idx in range(10):
+        for _ in range(5):
+            log_L.append(np.random.uniform(low=log_L[idx], high=1.))
+            parent.append(idx)
+    i1, n1 = oracle.count_crossed_edges(parent, log_L[1:])
+    i2, n2 = oracle.count_intervals_naive(parent, log_L[1:])
+    np.testing.assert_array_equal(i1, i2)
+    np.testing.assert_array_equal(n1, n2)
+
+
+def test_sender_quirk_vector(oracle):
+    """with sender = next_sample_idx - 1 a shell of m recovers N, N-1, .., N-m+2, N+1."""
+    N, m, shells = 6, 3, 4
+    sender, logL = [], []
+    nxt = 0
+    level = 0.0
+    live = [0] * N  # senders of live points
+    for s in range(shells):
+        for i in range(m):
+            sender.append(live[i])
+            logL.append(level)
+            level += 1.0
+        nxt += m
+        live = live[m:] + [nxt - 1] * m
+    for i in range(N):
+        sender.append(live[i])
+        logL.append(level)
+        level += 1.0
+    _, n = oracle.count_crossed_edges(sender, logL)
+    assert n.tolist() == [6, 5, 7, 6, 5, 7, 6, 5, 7, 6, 5, 7, 6, 5, 4, 3, 2, 1]
+
+
+def test_log_semiring_identities(oracle):
+    """/root/reference/src/jaxns/internals/tests/test_log_semiring.py: cumulative_logsumexp == log(cumsum(exp))"""
+    rng = np.random.default_rng(3)
+    u = rng.normal(size=50)
+    acc = -np.inf
+    out = []
+    for v in u:
+        acc = oracle.logaddexp(acc, v)
+        out.append(acc)
+    np.testing.assert_allclose(out, np.log(np.cumsum(np.exp(u))), rtol=1e-13)
+    assert oracle.logaddexp(-np.inf, -np.inf) == -np.inf
+    assert oracle.logaddexp(np.inf, np.inf) == np.inf
+    assert oracle.logaddexp(0.0, -np.inf) == 0.0
+
+
+def test_seed_table_equals_scan(oracle):
+    rng = np.random.default_rng(0)
+    ll = np.sort(rng.normal(size=300))
+    ll[100:104] = ll[100]  # ties
+    ctab = oracle.seed_table(300)
+    for t in range(3000):
+        c = ll[rng.integers(0, 299)] if t % 3 else rng.normal()
+        if t % 50 == 0:
+            c = ll[-1]  # no satisfying point -> index 0
+        u = rng.uniform()
+        assert oracle.seed_index_scan(ll, c, u) == oracle.seed_index_table(ll, ctab, c, u)
+    # uniformity over the satisfying suffix
+    idx = [oracle.seed_index_table(ll, ctab, ll[199], u) for u in rng.uniform(size=20000)]
+    assert min(idx) == 200 and max(idx) == 299
+    counts = np.bincount(np.array(idx) - 200, minlength=100)
+    assert abs(counts - 200).max() < 5 * np.sqrt(200)
+
+
+def test_evidence_scan_closed_form(oracle):
+    """constant n: E[X_i] = (n/(n+1))^i and Z telescopes for L == 1."""
+    n, M = 50.0, 400
+    st, per = oracle.evidence_scan(oracle.init_evidence_calc(), np.zeros(M), np.full(M, n), per_sample=True)
+    i = np.arange(1, M + 1)
+    np.testing.assert_allclose(per[:, 1], i * np.log(n / (n + 1)), rtol=1e-12)
+    np.testing.assert_allclose(per[:, 2], i * np.log(n / (n + 2)), rtol=1e-12)
+    # Z = sum X_{i-1}/(n+1) * mid, mid = 1 except the first (L_0 = 0 -> mid = 1/2)
+    X = (n / (n + 1)) ** np.arange(M)
+    Z = np.cumsum(X / (n + 1) * np.where(np.arange(M) == 0, 0.5, 1.0))
+    np.testing.assert_allclose(np.exp(per[:, 3]), Z, rtol=1e-12)
+
+
+def test_oracle_run_analytic_logZ(oracle):
+    """End-to-end oracle on BASELINE config 1 (2-D Gaussian, N=500): within 3 sigma of analytic."""
+    m = oracle.gauss_model(2)
+    ns = oracle.OracleNestedSampler(m, 500, 10, max_samples=50000)
+    errs, sig = [], []
+    for seed in range(5):
+        reason, st = ns.run(oracle.PRNGKey(seed))
+        r = ns.to_results(reason, st)
+        errs.append(r["log_Z_mean"] - oracle.gauss_analytic_logZ(2))
+        sig.append(r["log_Z_uncert"])
+        assert reason == 4 and abs(errs[-1]) < 3.5 * sig[-1]
+    assert abs(np.mean(errs)) < 3 * np.mean(sig) / np.sqrt(5)
+    assert abs(oracle.gauss_analytic_logZ(2) - (-77.641325)) < 1e-5
+    assert abs(oracle.gauss_analytic_logZ(32) - (-141.4292184)) < 1e-6
+
+
+def test_oracle_phantom_and_cap_overflow(oracle):
+    """k > 0 bookkeeping and the reference's clamped final append."""
+    m = oracle.gauss_model(2)
+    ns = oracle.OracleNestedSampler(m, 40, 6, num_phantom=2, max_samples=40 * 3 * 4)
+    reason, st = ns.run(oracle.PRNGKey(0), oracle.TermCond(max_samples=float(ns.max_samples)))
+    assert reason & 1
+    r = ns.to_results(reason, st)
+    assert r["total_phantom_samples"] == 2 * (r["total_num_samples"] - 40) // 3
+    assert np.all(st["n_evals"][:ns.max_samples][st["phantom"][:ns.max_samples]] == 0)
+    # k = 0: the loop stops one shell short of the cap, then the N = 2m live rows overflow the store and
+    # the clamped dynamic_update_slice overwrites the last shell
+    ns = oracle.OracleNestedSampler(m, 40, 6, num_phantom=0, max_samples=240)
+    reason, st = ns.run(oracle.PRNGKey(0), oracle.TermCond(max_samples=float(ns.max_samples)))
+    assert reason & 1 and st["num_samples"] == 260
+    r = ns.to_results(reason, st)
+    assert r["total_num_samples"] == 240
