@@ -102,8 +102,7 @@ class ClockSampler:
 def oracle_sample(num_live, iterations, seed=0, threads=None):
     """init + the first `iterations` shells of the same workload; returns (evals, seconds, threads)."""
     from oracle import oracle as o
-    if threads:
-        o.set_num_threads(threads)
+    o.set_num_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     om = o.gauss_model(D)
     ns = o.OracleNestedSampler(om, num_live, D * 5, 0, True, max_samples=num_live * 100)
     t0 = time.perf_counter()
@@ -114,12 +113,63 @@ def oracle_sample(num_live, iterations, seed=0, threads=None):
     return evals, dt, o.num_threads()
 
 
+def try_real_jaxns(num_live, seed):
+    """Plan A: the unmodified reference from baseline/_ref on the JAX CPU backend, if jax
+    and tfp happen to exist on this box.  Returns (evals, seconds, cores) or None."""
+    try:
+        os.environ.setdefault("XLA_FLAGS", f"--xla_force_host_platform_device_count={os.cpu_count()}")
+        os.environ.setdefault("JAX_PLATFORMS", "cpu")
+        sys.path.insert(0, os.path.join(ROOT, "baseline", "_ref"))
+        import jax  # noqa: F401
+        import tensorflow_probability.substrates.jax as tfp
+        from jax import numpy as jnp, random
+        from jaxns import Model, NestedSampler, Prior
+    except Exception:
+        return None
+    tfpd = tfp.distributions
+    p_loc, p_scale, mu, cov = workload_arrays()
+
+    def prior_model():
+        x = yield Prior(tfpd.MultivariateNormalTriL(loc=jnp.asarray(p_loc), scale_tril=jnp.diag(jnp.asarray(p_scale))))
+        return x
+
+    def log_likelihood(x):
+        return tfpd.MultivariateNormalTriL(loc=jnp.asarray(mu), scale_tril=jnp.linalg.cholesky(jnp.asarray(cov))).log_prob(x)
+
+    model = Model(prior_model=prior_model, log_likelihood=log_likelihood)
+    ns = NestedSampler(model=model, num_live_points=num_live)
+    run = jax.jit(lambda key: ns(key)).lower(random.PRNGKey(0)).compile()
+    t0 = time.perf_counter()
+    reason, state = run(random.PRNGKey(seed))
+    reason.block_until_ready()
+    dt = time.perf_counter() - t0
+    res = ns.to_results(reason, state)
+    return int(res.total_num_likelihood_evaluations), dt, os.cpu_count()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     num_live = BASE_LIVE * args.gpus
-    iters = 4
+    real = try_real_jaxns(num_live, 0) if os.environ.get("NSB200_TRY_JAXNS", "1") == "1" else None
+    if real is not None:
+        tot_e, tot_t = 0, 0.0
+        for s in range(args.steps):
+            e, t, cores = try_real_jaxns(num_live, s)
+            tot_e += e
+            tot_t += t
+        value = tot_e / tot_t
+        print(json.dumps({
+            "impl": "reference", "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"32-D correlated Gaussian, num_live_points={num_live}, s=5, k=0 (BASELINE configs[1])"},
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference",
+                             "sample": "whole runs, jaxns 2.6.9 on the JAX CPU backend"},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    iters = 20
     for _ in range(args.warmup):
         oracle_sample(num_live, 1)
     tot_e, tot_t = 0, 0.0
@@ -259,14 +309,20 @@ def run_native(args):
             pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                     "frac": achieved / tf.value if tf.value else None, "traffic": None,
-                    "kernel": "k_slice_chains_engine<1>",
+                    "kernel": "k_slice_chains<32,1,P> (fused slice chains)",
                     "kernel_share_of_step": slice_ms / tot_ms,
                     "peak_source": "FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
                                    f"figure; its hbm_gbs={peaks.get('hbm_gbs')} governs only the statistics kernels)",
                     "algorithmic_flops_per_eval": FLOPS_PER_EVAL}
-        # ---- CPU baseline on a bounded sample -----------------------------------------------------
+        # ---- CPU baseline on a bounded sample (rank 0, N=1 only) ------------------------------------
         cpu_iters = 40
-        ce, ct, cores = oracle_sample(num_live, cpu_iters, seed=0)
+        if world == 1:
+            ce, ct, cores = oracle_sample(num_live, cpu_iters, seed=0)
+            cpu_baseline = {"value": ce / ct, "unit": "evals/s", "cores": cores, "kind": "port",
+                            "sample": f"oracle (CPU restatement of jaxns 2.6.9): prior draws + first {cpu_iters} "
+                                      f"shells of the same run, {ce} evals in {ct:.1f}s"}
+        else:
+            cpu_baseline = None
         line = {
             "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_ms_max / args.steps,
@@ -282,9 +338,7 @@ def run_native(args):
                     "runs": n_e2e},
             "gpu_launches": launches,
             "roofline": roofline,
-            "cpu_baseline": {"value": ce / ct, "unit": "evals/s", "cores": cores, "kind": "port",
-                             "sample": f"oracle (CPU restatement of jaxns 2.6.9): prior draws + first {cpu_iters} "
-                                       f"shells of the same run, {ce} evals in {ct:.1f}s"},
+            "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line))
     if world > 1:
