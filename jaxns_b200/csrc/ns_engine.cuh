@@ -70,13 +70,16 @@ __global__ void k_finalize_ctl(DevCtl *ctl, long long count, long long capacity)
 // Rank of every element of the next live set under a stable ascending sort of
 // [new_0 .. new_{m-1}, survivor_m .. survivor_{N-1}]  (sharded_static.py:269-275): new rows come
 // first on ties.  packed rows: [U[D], logL, nevals, ...].
+constexpr int kRankLanes = 8;  // lanes cooperating on one element's count
+
 __global__ void __launch_bounds__(256) k_merge_rank(const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
                                                     const double *packed, long long row_doubles, int D,
                                                     long long m, long long N, unsigned *rank_out) {
     if (!ctl->active) return;
     __shared__ uint64_t tile[1024];
     const LiveSet &live = ctl->cur ? live1 : live0;
-    const long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = ((long long) blockIdx.x * blockDim.x + threadIdx.x) / kRankLanes;
+    const int sub = threadIdx.x % kRankLanes;
     const bool valid = e < N;
     const bool is_new = e < m;
     uint64_t key = 0;
@@ -89,16 +92,18 @@ __global__ void __launch_bounds__(256) k_merge_rank(const DevCtl *ctl, const Liv
         __syncthreads();
         if (valid) {
             if (is_new) {
-                for (int q = 0; q < tn; ++q) {
+                for (int q = sub; q < tn; q += kRankLanes) {
                     const uint64_t kq = tile[q];
                     cnt += (kq < key) || (kq == key && (t0 + q) < e);
                 }
             } else {
-                for (int q = 0; q < tn; ++q) cnt += (tile[q] <= key);
+                for (int q = sub; q < tn; q += kRankLanes) cnt += (tile[q] <= key);
             }
         }
     }
-    if (!valid) return;
+#pragma unroll
+    for (int o = kRankLanes >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (!valid || sub != 0) return;
     if (is_new) {
         // survivors strictly below (lower_bound over the sorted survivors)
         long long lo = m, hi = N;
@@ -247,7 +252,8 @@ __global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister 
     out.mark = m;
     out.fin = &s_fin;
     out.per_sample = nullptr;
-    evidence_scan_block(q, reg->evidence_calc, out, sh);
+    if (m + N <= 8 * (long long) blockDim.x) evidence_scan_block<8>(q, reg->evidence_calc, out, sh);
+    else evidence_scan_block<0>(q, reg->evidence_calc, out, sh);
     // sums of likelihood evaluations, plateau flag
     long long sum_new = 0, sum_live = 0;
     int not_plateau = 0;

@@ -206,14 +206,14 @@ __device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp<G>
 
 // log-likelihood of the P transformed points held across the group.  `scratch` = DP*P doubles of
 // shared memory private to the chain.  Every lane of the group gets the same values.
-template <int G, int DPL, int P>
+template <int G, int DPL, int P, int FAM>
 __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
                                              const double (&X)[P][DPL], double *scratch, double (&out)[P]) {
     constexpr int DP = G * DPL;
     const int D = sm.D;
     const double *Pm = sm.params;
     const double kNan = __longlong_as_double(0x7FF8000000000000ll);
-    switch (sm.family) {
+    switch (FAM) {  // compile-time: the kernels dispatch on the family once, outside the chain loop
         case NSB200_FAM_GAUSS_DENSE: {
             const double *mu = Pm + 1;
             // residuals r_j^(p) -> scratch[j][p]
@@ -395,12 +395,23 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
 }
 
 // Model.forward at P U-space points held across the group.
-template <int G, int DPL, int P>
+template <int G, int DPL, int P, int FAM>
 __device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
                                               const double (&u)[P][DPL], double *scratch, double (&out)[P]) {
     double X[P][DPL];
     transform_dims<G, DPL, P>(sm, g, u, X);
-    loglik_group<G, DPL, P>(sm, g, row, X, scratch, out);
+    loglik_group<G, DPL, P, FAM>(sm, g, row, X, scratch, out);
 }
+
+// Runtime family -> compile-time template argument, once per kernel.
+#define NSB_FAMILY_SWITCH(FAMILY, ...)                                                          \
+    switch (FAMILY) {                                                                           \
+        case NSB200_FAM_GAUSS_DENSE: { constexpr int kFam = NSB200_FAM_GAUSS_DENSE; __VA_ARGS__; } break;       \
+        case NSB200_FAM_GAUSS_MIX_DIAG: { constexpr int kFam = NSB200_FAM_GAUSS_MIX_DIAG; __VA_ARGS__; } break; \
+        case NSB200_FAM_EGGBOX: { constexpr int kFam = NSB200_FAM_EGGBOX; __VA_ARGS__; } break;                 \
+        case NSB200_FAM_ROSENBROCK: { constexpr int kFam = NSB200_FAM_ROSENBROCK; __VA_ARGS__; } break;         \
+        case NSB200_FAM_SHELLS: { constexpr int kFam = NSB200_FAM_SHELLS; __VA_ARGS__; } break;                 \
+        default: break;                                                                         \
+    }
 
 }  // namespace nsb

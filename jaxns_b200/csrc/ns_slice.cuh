@@ -129,7 +129,7 @@ __host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool
     return (size_t) G * DPL * P + (slice ? (size_t) G * (kPre + 2) : 0);
 }
 
-template <int G, int DPL, int P>
+template <int G, int DPL, int P, int FAM>
 __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *smem) {
     constexpr int DP = G * DPL;
     const int D = a.model.D;
@@ -247,7 +247,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 #pragma unroll
                     for (int s = 0; s < DPL; ++s) x[p][s] = fma(t, d[s], U0[s]);
                 }
-                forward_group<G, DPL, P>(sm, g, row, x, scratch, logL);
+                forward_group<G, DPL, P, FAM>(sm, g, row, x, scratch, logL);
                 // ---- first accepted proposal wins (:160-166)
                 int hit = -1;
 #pragma unroll
@@ -317,7 +317,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 template <int G, int DPL, int P>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) {
     extern __shared__ double smem[];
-    slice_chains_body<G, DPL, P>(a, smem);
+    NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam>(a, smem));
 }
 
 // ---- prior draws for the initial live set / uniform rejection sampler --------------------------
@@ -343,9 +343,8 @@ __device__ __forceinline__ void sample_U(const Grp<G> &g, int D, Key key, double
     }
 }
 
-template <int G, int DPL>
-__global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
-    extern __shared__ double smem[];
+template <int G, int DPL, int FAM>
+__device__ __forceinline__ void draw_body(const DrawArgs &a, double *smem) {
     constexpr int DP = G * DPL;
     const int D = a.model.D;
     ModelSmem sm;
@@ -366,7 +365,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
     Key sk = split_child(k0, 1);
     double u[1][DPL], logL[1];
     sample_U<G, DPL>(g, D, sk, u);
-    forward_group<G, DPL, 1>(sm, g, row, u, scratch, logL);
+    forward_group<G, DPL, 1, FAM>(sm, g, row, u, scratch, logL);
     long long ne = 1;
     for (;;) {
         bool done;
@@ -376,7 +375,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
         sk = split_child(key, 1);
         key = split_child(key, 0);
         sample_U<G, DPL>(g, D, sk, u);
-        forward_group<G, DPL, 1>(sm, g, row, u, scratch, logL);
+        forward_group<G, DPL, 1, FAM>(sm, g, row, u, scratch, logL);
         ne += 1;
     }
     const long long o = i - a.begin;
@@ -391,6 +390,12 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
     }
 }
 
+template <int G, int DPL>
+__global__ void __launch_bounds__(kThreadsPerBlock) k_draw(DrawArgs a) {
+    extern __shared__ double smem[];
+    NSB_FAMILY_SWITCH(a.model.family, draw_body<G, DPL, kFam>(a, smem));
+}
+
 // ---- vmap(Model.forward) / vmap(Model.transform) -----------------------------------------------
 struct ForwardArgs {
     NsModelDesc model;
@@ -400,9 +405,8 @@ struct ForwardArgs {
     long long n;
 };
 
-template <int G, int DPL>
-__global__ void __launch_bounds__(kThreadsPerBlock) k_forward(ForwardArgs a) {
-    extern __shared__ double smem[];
+template <int G, int DPL, int FAM>
+__device__ __forceinline__ void forward_body(const ForwardArgs &a, double *smem) {
     constexpr int DP = G * DPL;
     const int D = a.model.D;
     ModelSmem sm;
@@ -423,13 +427,19 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_forward(ForwardArgs a) {
         u[0][s] = (j < D) ? a.U[i * D + j] : 0.5;
     }
     transform_dims<G, DPL, 1>(sm, g, u, X);
-    loglik_group<G, DPL, 1>(sm, g, row, X, scratch, logL);
+    loglik_group<G, DPL, 1, FAM>(sm, g, row, X, scratch, logL);
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
         if (j < D && a.out_X) a.out_X[i * D + j] = X[0][s];
     }
     if (g.lane == 0 && a.out_logL) a.out_logL[i] = logL[0];
+}
+
+template <int G, int DPL>
+__global__ void __launch_bounds__(kThreadsPerBlock) k_forward(ForwardArgs a) {
+    extern __shared__ double smem[];
+    NSB_FAMILY_SWITCH(a.model.family, forward_body<G, DPL, kFam>(a, smem));
 }
 
 }  // namespace nsb

@@ -359,7 +359,10 @@ struct EvOut {
     double *per_sample;      // [8][M] field-major (nullable)
 };
 
-// Must be called by all threads of a CTA.  sh = 33 doubles.
+// Must be called by all threads of a CTA.  sh = 33 doubles.  CACHE > 0: every thread owns at most
+// CACHE elements and keeps their terms (3 log + 3 logaddexp each) in registers across the passes --
+// the per-iteration register update (m + N elements over 1024 threads) runs this way.
+template <int CACHE>
 __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double *sh) {
     const double kLog2 = 0.6931471805599453;
     const long long M = q.len_a + q.len_b;
@@ -371,37 +374,61 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         double nn;
         ev_get(q, b - 1, prev0, nn);
     }
-    // pass 1: cumsum of T, T2
-    double sT = 0.0, sT2 = 0.0;
-    {
+    constexpr int C = CACHE > 0 ? CACHE : 1;
+    EvTerms ct[C];
+    double cl[C];
+    if (CACHE > 0) {
         double prevL = prev0;
-        for (long long i = b; i < e; ++i) {
-            double logL, n;
-            ev_get(q, i, logL, n);
-            EvTerms t = ev_terms(logL, prevL, n);
-            sT += t.T;
-            sT2 += t.T2;
-            prevL = logL;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const long long i = b + c;
+            if (i < e) {
+                double logL, n;
+                ev_get(q, i, logL, n);
+                ct[c] = ev_terms(logL, prevL, n);
+                cl[c] = logL;
+                prevL = logL;
+            }
         }
     }
+#define NSB_EV_LOOP(BODY)                                             \
+    if (CACHE > 0) {                                                  \
+        _Pragma("unroll") for (int c = 0; c < C; ++c) {               \
+            const long long i = b + c;                                \
+            if (i < e) {                                              \
+                const EvTerms t = ct[c];                              \
+                const double logL = cl[c];                            \
+                BODY                                                  \
+            }                                                         \
+        }                                                             \
+    } else {                                                          \
+        double prevL = prev0;                                         \
+        for (long long i = b; i < e; ++i) {                           \
+            double logL, n;                                           \
+            ev_get(q, i, logL, n);                                    \
+            const EvTerms t = ev_terms(logL, prevL, n);               \
+            prevL = logL;                                             \
+            BODY                                                      \
+        }                                                             \
+    }
+    // pass 1: cumsum of T, T2
+    double sT = 0.0, sT2 = 0.0;
+    NSB_EV_LOOP({ (void) i; (void) logL; sT += t.T; sT2 += t.T2; })
     const double X0 = init.log_X_mean + block_scan_excl<OpAdd>(sT, sh, tot);
     const double X20 = init.log_X2_mean + block_scan_excl<OpAdd>(sT2, sh, tot);
     // pass 2: Z, dZ2, W = ZX / X
     const double kNegInf = OpLae::id();
     double sa = kNegInf, sb = kNegInf, sw = kNegInf;
     {
-        double prevL = prev0, lX = X0, lX2 = X20;
-        for (long long i = b; i < e; ++i) {
-            double logL, n;
-            ev_get(q, i, logL, n);
-            EvTerms t = ev_terms(logL, prevL, n);
+        double lX = X0, lX2 = X20;
+        NSB_EV_LOOP({
+            (void) i; (void) logL;
             sa = logaddexp(sa, lX + t.t + t.mid);
             sb = logaddexp(sb, lX2 + t.t2 + 2.0 * t.mid);
             sw = logaddexp(sw, (lX2 + t.tT + t.mid) - (lX + t.T));
             lX += t.T;
             lX2 += t.T2;
-            prevL = logL;
-        }
+        })
     }
     const double Z0 = logaddexp(init.log_Z_mean, block_scan_excl<OpLae>(sa, sh, tot));
     const double dZ20 = logaddexp(init.log_dZ2_mean, block_scan_excl<OpLae>(sb, sh, tot));
@@ -409,27 +436,21 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
     // pass 3: Z2
     double sc = kNegInf;
     {
-        double prevL = prev0, lX = X0, lX2 = X20, lW = W0;
-        for (long long i = b; i < e; ++i) {
-            double logL, n;
-            ev_get(q, i, logL, n);
-            EvTerms t = ev_terms(logL, prevL, n);
+        double lX = X0, lX2 = X20, lW = W0;
+        NSB_EV_LOOP({
+            (void) i; (void) logL;
             const double zx_prev = lX + lW;
             sc = logaddexp(sc, logaddexp(kLog2 + zx_prev + t.t + t.mid, lX2 + t.t2 + 2.0 * t.mid));
             lW = logaddexp(lW, (lX2 + t.tT + t.mid) - (lX + t.T));
             lX += t.T;
             lX2 += t.T2;
-            prevL = logL;
-        }
+        })
     }
     const double Z20 = logaddexp(init.log_Z2_mean, block_scan_excl<OpLae>(sc, sh, tot));
     // pass 4: outputs
     {
-        double prevL = prev0, lX = X0, lX2 = X20, lW = W0, lZ = Z0, ldZ2 = dZ20, lZ2 = Z20;
-        for (long long i = b; i < e; ++i) {
-            double logL, n;
-            ev_get(q, i, logL, n);
-            EvTerms t = ev_terms(logL, prevL, n);
+        double lX = X0, lX2 = X20, lW = W0, lZ = Z0, ldZ2 = dZ20, lZ2 = Z20;
+        NSB_EV_LOOP({
             const double dZ = lX + t.t + t.mid;
             const double x2t2m2 = lX2 + t.t2 + 2.0 * t.mid;
             const double zx_prev = lX + lW;
@@ -439,7 +460,6 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
             lW = logaddexp(lW, (lX2 + t.tT + t.mid) - (lX + t.T));
             lX += t.T;
             lX2 += t.T2;
-            prevL = logL;
             NsEvidenceCalc c;
             c.log_L = logL;
             c.log_X_mean = lX;
@@ -462,8 +482,9 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
             }
             if (out.mid && i == out.mark - 1) *out.mid = c;
             if (out.fin && i == M - 1) *out.fin = c;
-        }
+        })
     }
+#undef NSB_EV_LOOP
     if (M == 0 && threadIdx.x == 0) {
         if (out.fin) *out.fin = init;
         if (out.mid) *out.mid = init;
@@ -474,7 +495,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
 
 __global__ void __launch_bounds__(1024) k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out) {
     __shared__ double sh[33];
-    evidence_scan_block(q, init, out, sh);
+    evidence_scan_block<0>(q, init, out, sh);
 }
 
 // =================================================================================================

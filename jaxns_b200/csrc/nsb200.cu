@@ -649,7 +649,7 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     long long *tmpN = e->live[1].nevals;
     if (launch_draw(&e->cfg.model, sample_key, nullptr, 0, e->N, tmpU, tmpL, tmpN, 0, st)) return 1;
     k_pack_rows<<<592, 256, 0, st>>>(tmpU, tmpL, tmpN, e->N, D, e->packed, e->row_doubles);
-    k_merge_rank<<<grid_for(e->N, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
+    k_merge_rank<<<grid_for(e->N * kRankLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
                                                        e->N, e->N, e->rank);
     DeadStore nodead = e->dead;
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->N, e->N, 0,
@@ -722,7 +722,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
-    k_merge_rank<<<grid_for(e->N, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
+    k_merge_rank<<<grid_for(e->N * kRankLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
                                                        e->m, e->N, e->rank);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
