@@ -28,6 +28,9 @@ __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSe
     ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
     k = split_child(k, 0);
     ctl->key = split_child(k, 0);          // :510  key, ephemeral_key = split(state.key)
+    // the key chain does not depend on the data: the next body's sample_key is known already, so its
+    // chain streams can be generated concurrently with this body's slice kernel
+    ctl->next_sample_key = split_child(split_child(ctl->key, 0), 1);
     ctl->contour = live.logL[m - 1];
     ctl->disc_start = clampll(ctl->next_idx, 0, capacity - m);
     ctl->next_idx = (ctl->next_idx + m) % capacity;
@@ -222,8 +225,9 @@ __device__ inline void determine_termination(const NsTermCond &tc, NsRegister &r
 __global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0,
                                                         const LiveSet live1, const double *packed,
                                                         long long row_doubles, int D, long long m, long long N,
-                                                        NsTermCond tc, int init_only) {
-    __shared__ double sh[33];
+                                                        NsTermCond tc, int init_only, const double *tabT,
+                                                        const double *tabT2, const double *tabt, long long tab_n) {
+    __shared__ double sh[3][33];
     __shared__ NsEvidenceCalc s_mid, s_fin;
     __shared__ long long s_ll[2];
     __shared__ int s_flag;
@@ -247,6 +251,10 @@ __global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister 
     q.lb = cur.logL;
     q.len_b = N;
     q.n_start_b = (double) N;  // :296, n = N..1
+    q.tabT = tabT;
+    q.tabT2 = tabT2;
+    q.tabt = tabt;
+    q.tab_n = tab_n;
     EvOut out;
     out.mid = &s_mid;
     out.mark = m;

@@ -34,10 +34,12 @@ template <int G>
 struct Grp {
     unsigned mask;  // lanes of this group inside the warp (compile-time constant for G == 32)
     int lane;       // lane index inside the group
-    __device__ __forceinline__ Grp() {
+    // convergent = every group of the warp executes the same control flow (team mode): shuffles and
+    // syncs can then name the full warp, which keeps the mask a compile-time constant.
+    __device__ __forceinline__ explicit Grp(bool convergent = false) {
         const int wl = threadIdx.x & 31;
         lane = wl & (G - 1);
-        if (G == 32) mask = 0xFFFFFFFFu;
+        if (G == 32 || convergent) mask = 0xFFFFFFFFu;
         else mask = ((1u << (G & 31)) - 1u) << (wl & ~(G - 1));
     }
     __device__ __forceinline__ unsigned m() const { return G == 32 ? 0xFFFFFFFFu : mask; }

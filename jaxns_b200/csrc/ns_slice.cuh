@@ -50,6 +50,11 @@ struct SliceArgs {
     // block, so the host never has to know them (and the launch is a no-op once the loop is done)
     const DevCtl *ctl;
     LiveSet live0, live1;
+    // optional precomputed per-chain streams (k_chain_streams): directions [n][S][D], proposal
+    // uniforms [n][S][kPre] and the run_key after kPre-1 shrink steps [n][S]; n = chain_end - chain_begin
+    const double *pre_dirs;
+    const double *pre_us;
+    const uint2 *pre_rkeys;
 };
 
 // jnp.linspace(0.5, 1., S)[j]
@@ -129,7 +134,7 @@ __host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool
     return (size_t) G * DPL * P + (slice ? (size_t) G * (kPre + 2) : 0);
 }
 
-template <int G, int DPL, int P, int FAM>
+template <int G, int DPL, int P, int FAM, bool PRE>
 __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *smem) {
     constexpr int DP = G * DPL;
     const int D = a.model.D;
@@ -149,7 +154,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     stage_model<G, DPL>(a.model, smem, sm);
     __syncthreads();
     const Grp<G> g;
-    constexpr int chains_per_block = kThreadsPerBlock / G;
+    const int chains_per_block = blockDim.x / G;  // the slice kernel picks its CTA size at launch
     const int local_chain = threadIdx.x / G;
     const long long chain = a.chain_begin + (long long) blockIdx.x * chains_per_block + local_chain;
     if (chain >= a.chain_end) return;
@@ -179,16 +184,30 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         U0[s] = (j < D) ? live_U[sidx * D + j] : 0.5;
     }
     double logL0 = live_logL[sidx];
-    const Key direction_key = split_child(sample_key, 0);
-    const Key sample_key2 = split_child(sample_key, 1);
-    sample_direction<G, DPL>(g, D, direction_key, d);
-
     const long long out_row = chain - a.chain_begin;
     long long nev = 0;
+    Key sample_key2 = Key{0, 0};
+    // stream of slice 0 (PRE: fetched; otherwise derived below)
+    double unext = 0.0;           // lane p < kPre holds uniform p of the next slice
+    uint2 rknext = make_uint2(0, 0);
+    if (PRE) {
+        const long long sb = out_row * S;
+#pragma unroll
+        for (int s = 0; s < DPL; ++s) {
+            const int j = s * G + g.lane;
+            d[s] = (j < D) ? __ldg(a.pre_dirs + sb * D + j) : 0.0;
+        }
+        if (g.lane < kPre) unext = __ldg(a.pre_us + sb * kPre + g.lane);
+        rknext = __ldg(a.pre_rkeys + sb);
+    } else {
+        const Key direction_key = split_child(sample_key, 0);
+        sample_key2 = split_child(sample_key, 1);
+        sample_direction<G, DPL>(g, D, direction_key, d);
+    }
 
     for (int base = 0; base < S; base += G) {
         // ---- precompute the key stream of slices base .. base+G-1, one slice per lane
-        {
+        if (!PRE) {
             const int j = base + g.lane;
             if (j < S) {
                 const Key slice_key = split_child(sample_key2, (uint64_t) j);  // :420
@@ -214,15 +233,35 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         for (int jl = 0; jl < jmax; ++jl) {
             const int j = base + jl;
             const double alpha = alpha_schedule(j, S);
-            const double *uq = pre_u + jl * kPre;
-            const uint32_t *pk = pre_k + jl * 4;
-            // direction of the NEXT slice (:272): independent of this slice's evaluations, issued
-            // first so that its Threefry / erf_inv latency overlaps them
+            const double *uq;
+            Key run_key;
             double dnext[DPL];
-            sample_direction<G, DPL>(g, D, Key{pk[0], pk[1]}, dnext);
+            if (PRE) {
+                // this slice's uniforms were fetched one slice ago: park them in shared memory (the
+                // shrink loop indexes them), then issue the loads of the next slice's stream so that
+                // their DRAM/L2 latency hides behind this slice's evaluations
+                if (g.lane < kPre) pre_u[g.lane] = unext;
+                run_key = Key{rknext.x, rknext.y};
+                uq = pre_u;
+                const long long sn = out_row * S + j + 1;
+                const bool more = j + 1 < S;
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int jj = s * G + g.lane;
+                    dnext[s] = (more && jj < D) ? __ldg(a.pre_dirs + sn * D + jj) : 0.0;
+                }
+                if (more && g.lane < kPre) unext = __ldg(a.pre_us + sn * kPre + g.lane);
+                if (more) rknext = __ldg(a.pre_rkeys + sn);
+                group_sync(g);
+            } else {
+                uq = pre_u + jl * kPre;
+                const uint32_t *pk = pre_k + jl * 4;
+                // direction of the NEXT slice (:272): independent of this slice's evaluations
+                sample_direction<G, DPL>(g, D, Key{pk[0], pk[1]}, dnext);
+                run_key = Key{pk[2], pk[3]};
+            }
             double left, right;
             slice_bounds<G, DPL>(g, D, U0, d, left, right);
-            Key run_key = Key{pk[2], pk[3]};
             int ne = 0;  // proposals generated so far in this slice
             double logL_acc = 0.0;
             for (;;) {
@@ -317,7 +356,105 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 template <int G, int DPL, int P>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) {
     extern __shared__ double smem[];
-    NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam>(a, smem));
+    if (a.pre_dirs) {
+        NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, true>(a, smem));
+    } else {
+        NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, false>(a, smem));
+    }
+}
+
+// ---- data-independent per-chain streams ----------------------------------------------------------
+// Nothing in a chain's key tree depends on a likelihood value, so the directions of all S slices,
+// the first kPre proposal uniforms of every slice and the run_key to continue from can be produced
+// by a throughput-bound kernel (one warp per chain x 32 slices) instead of on the chain's critical
+// path.  Layouts match what the slice kernel reads: dirs [n][S][D], us [n][S][kPre], rkeys [n][S].
+struct StreamArgs {
+    Key key;
+    const DevCtl *ctl;  // engine mode: key = ctl->next_sample_key (streams of the FOLLOWING body)
+    long long chain_begin, chain_end;
+    int S, D;
+    double *dirs;
+    double *us;
+    uint2 *rkeys;
+};
+
+__global__ void __launch_bounds__(128) k_chain_streams(StreamArgs a) {
+    Key base_key = a.key;
+    if (a.ctl) base_key = a.ctl->next_sample_key;
+    const int lane = threadIdx.x & 31;
+    const int S = a.S, D = a.D;
+    const int n_chunks = (S + 31) / 32;
+    // persistent warps over (chain, 32-slice chunk) items: the grid is kept small on purpose (a few
+    // warps per SM) so that this throughput-bound kernel back-fills issue slots next to the
+    // latency-bound slice kernel instead of starving its warps
+    const long long n_items = (a.chain_end - a.chain_begin) * n_chunks;
+    const long long n_warps = ((long long) gridDim.x * blockDim.x) >> 5;
+    for (long long wid = ((long long) blockIdx.x * blockDim.x + threadIdx.x) >> 5; wid < n_items; wid += n_warps) {
+    const long long row = wid / n_chunks;
+    const int base = (int) (wid - row * n_chunks) * 32;
+    const long long chain = a.chain_begin + row;
+    const Key chain_key = split_child(base_key, (uint64_t) chain);
+    const Key sample_key = split_child(chain_key, 0);  // bases.py:64
+    const Key sample_key2 = split_child(sample_key, 1);  // uni_slice_sampler.py:410
+    // phase 1: lane L owns slice base + L
+    Key after_key = Key{0, 0};
+    {
+        const int j = base + lane;
+        if (j < S) {
+            const Key slice_key = split_child(sample_key2, (uint64_t) j);  // :420
+            Key run_key = split_child(slice_key, 0);                       // :201
+            Key t_key = split_child(slice_key, 2);
+            after_key = split_child(slice_key, 3);
+            double *u = a.us + (row * S + j) * kPre;
+            u[0] = uniform01(t_key, 0);
+#pragma unroll 1
+            for (int p = 1; p < kPre; ++p) {
+                t_key = split_child(run_key, 1);  // :169
+                run_key = split_child(run_key, 0);
+                u[p] = uniform01(t_key, 0);
+            }
+            a.rkeys[row * S + j] = make_uint2(run_key.a, run_key.b);
+        }
+    }
+    // phase 2: lanes = dimensions; direction of slice j+1 comes from after_key_j (:272), the first
+    // one from direction_key (:410-413)
+    const int jl0 = (base == 0) ? -1 : 0;
+#pragma unroll 1
+    for (int jl = jl0; jl < 32; ++jl) {
+        const int jdst = base + jl + 1;  // slice that uses this direction
+        if (jdst >= S) break;
+        Key k;
+        if (jl < 0) {
+            k = split_child(sample_key, 0);
+        } else {
+            k.a = __shfl_sync(0xFFFFFFFFu, after_key.a, jl);
+            k.b = __shfl_sync(0xFFFFFFFFu, after_key.b, jl);
+        }
+        double *dst = a.dirs + (row * S + jdst) * D;
+        if (D == 1) {
+            if (lane == 0) dst[0] = 1.0;
+            continue;
+        }
+        double v[8];  // D <= 256
+        double ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = lane + 32 * q;
+            v[q] = (j < D) ? normal_from_bits(bits64(k, (uint64_t) j)) : 0.0;
+            ss = fma(v[q], v[q], ss);
+            if (32 * (q + 1) >= D) break;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+        const double nrm = sqrt(ss);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int j = lane + 32 * q;
+            if (j < D) dst[j] = v[q] / nrm;
+            if (32 * (q + 1) >= D) break;
+        }
+    }
+    }
 }
 
 // ---- prior draws for the initial live set / uniform rejection sampler --------------------------

@@ -58,6 +58,57 @@ __device__ __forceinline__ double block_scan_excl(double v, double *sh, double &
     return Op::ap(sh[warp], exc);
 }
 
+// Same, K values per thread scanned together: the K combines of a step are independent, so their
+// latencies (logaddexp ~ 500 cycles) overlap instead of adding up over K separate scans.
+template <class Op, int K>
+__device__ __forceinline__ void block_scan_excl_k(const double (&v)[K], double (*sh)[33], double (&exc_out)[K]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    double inc[K], exc[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) inc[k] = v[k];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double y = __shfl_up_sync(0xFFFFFFFFu, inc[k], o);
+            if (lane >= o) inc[k] = Op::ap(y, inc[k]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        exc[k] = __shfl_up_sync(0xFFFFFFFFu, inc[k], 1);
+        if (lane == 0) exc[k] = Op::id();
+    }
+    __syncthreads();
+    if (lane == 31) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sh[k][warp] = inc[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double winc[K], w[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) w[k] = winc[k] = (lane < nw) ? sh[k][lane] : Op::id();
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                double y = __shfl_up_sync(0xFFFFFFFFu, winc[k], o);
+                if (lane >= o) winc[k] = Op::ap(y, winc[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double wexc = __shfl_up_sync(0xFFFFFFFFu, winc[k], 1);
+            if (lane == 0) wexc = Op::id();
+            sh[k][lane] = wexc;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) exc_out[k] = Op::ap(sh[k][warp], exc[k]);
+}
+
 // =================================================================================================
 // Stable LSD radix argsort on order-preserving u64 keys (8-bit digits, 8 passes).
 // =================================================================================================
@@ -322,6 +373,12 @@ struct EvSeq {
     const double *lb;
     long long len_b;
     double n_start_b;
+    // optional tables of the n-dependent terms for integer n in [1, tab_n]: T, T2 and t = -log(n+1)
+    // (t is valid up to tab_n + 1); built once per engine by k_ev_tables
+    const double *tabT;
+    const double *tabT2;
+    const double *tabt;
+    long long tab_n;
 };
 
 struct EvTerms {
@@ -339,9 +396,22 @@ __device__ __forceinline__ void ev_get(const EvSeq &q, long long i, double &logL
     }
 }
 
-__device__ __forceinline__ EvTerms ev_terms(double logL, double prevL, double n) {
+__device__ __forceinline__ EvTerms ev_terms(const EvSeq &q, double logL, double prevL, double n) {
     const double kLog2 = 0.6931471805599453, kLogHalf = -0.6931471805599453;
     EvTerms e;
+    if (q.tabT) {
+        const long long ni = (long long) n;
+        if ((double) ni == n && ni >= 1 && ni <= q.tab_n) {
+            const double tn = q.tabt[ni], tn1 = q.tabt[ni + 1];
+            e.mid = kLogHalf + logaddexp(logL, prevL);
+            e.T = q.tabT[ni];
+            e.T2 = q.tabT2[ni];
+            e.t = tn;
+            e.t2 = kLog2 + tn + tn1;
+            e.tT = e.T + tn1;
+            return e;
+        }
+    }
     const double ln = log(n), lnp1 = log(n + 1.0), lnp2 = log(n + 2.0);
     e.mid = kLogHalf + logaddexp(logL, prevL);
     e.T = -logaddexp(0.0, -ln);
@@ -350,6 +420,18 @@ __device__ __forceinline__ EvTerms ev_terms(double logL, double prevL, double n)
     e.t2 = kLog2 - lnp1 - lnp2;
     e.tT = e.T - lnp2;
     return e;
+}
+
+// T[n] = -logaddexp(0, -log n), T2[n] = -logaddexp(0, log 2 - log n), t[n] = -log(n + 1), n = 0 .. nmax+1
+__global__ void k_ev_tables(long long nmax, double *tabT, double *tabT2, double *tabt) {
+    const double kLog2 = 0.6931471805599453;
+    for (long long n = (long long) blockIdx.x * blockDim.x + threadIdx.x; n <= nmax + 1;
+         n += (long long) gridDim.x * blockDim.x) {
+        const double ln = log((double) n);
+        tabT[n] = -logaddexp(0.0, -ln);
+        tabT2[n] = -logaddexp(0.0, kLog2 - ln);
+        tabt[n] = -log((double) n + 1.0);
+    }
 }
 
 struct EvOut {
@@ -363,12 +445,11 @@ struct EvOut {
 // CACHE elements and keeps their terms (3 log + 3 logaddexp each) in registers across the passes --
 // the per-iteration register update (m + N elements over 1024 threads) runs this way.
 template <int CACHE>
-__device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double *sh) {
+__device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double (*sh)[33]) {
     const double kLog2 = 0.6931471805599453;
     const long long M = q.len_a + q.len_b;
     const long long per = (M + blockDim.x - 1) / blockDim.x;
     const long long b = min(M, (long long) threadIdx.x * per), e = min(M, b + per);
-    double tot;
     double prev0 = init.log_L;
     if (b > 0 && b < M) {
         double nn;
@@ -385,7 +466,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
             if (i < e) {
                 double logL, n;
                 ev_get(q, i, logL, n);
-                ct[c] = ev_terms(logL, prevL, n);
+                ct[c] = ev_terms(q, logL, prevL, n);
                 cl[c] = logL;
                 prevL = logL;
             }
@@ -406,7 +487,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         for (long long i = b; i < e; ++i) {                           \
             double logL, n;                                           \
             ev_get(q, i, logL, n);                                    \
-            const EvTerms t = ev_terms(logL, prevL, n);               \
+            const EvTerms t = ev_terms(q, logL, prevL, n);            \
             prevL = logL;                                             \
             BODY                                                      \
         }                                                             \
@@ -414,8 +495,10 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
     // pass 1: cumsum of T, T2
     double sT = 0.0, sT2 = 0.0;
     NSB_EV_LOOP({ (void) i; (void) logL; sT += t.T; sT2 += t.T2; })
-    const double X0 = init.log_X_mean + block_scan_excl<OpAdd>(sT, sh, tot);
-    const double X20 = init.log_X2_mean + block_scan_excl<OpAdd>(sT2, sh, tot);
+    double in2[2] = {sT, sT2}, ex2[2];
+    block_scan_excl_k<OpAdd, 2>(in2, sh, ex2);
+    const double X0 = init.log_X_mean + ex2[0];
+    const double X20 = init.log_X2_mean + ex2[1];
     // pass 2: Z, dZ2, W = ZX / X
     const double kNegInf = OpLae::id();
     double sa = kNegInf, sb = kNegInf, sw = kNegInf;
@@ -430,9 +513,11 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
             lX2 += t.T2;
         })
     }
-    const double Z0 = logaddexp(init.log_Z_mean, block_scan_excl<OpLae>(sa, sh, tot));
-    const double dZ20 = logaddexp(init.log_dZ2_mean, block_scan_excl<OpLae>(sb, sh, tot));
-    const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, block_scan_excl<OpLae>(sw, sh, tot));
+    double in3[3] = {sa, sb, sw}, ex3[3];
+    block_scan_excl_k<OpLae, 3>(in3, sh, ex3);
+    const double Z0 = logaddexp(init.log_Z_mean, ex3[0]);
+    const double dZ20 = logaddexp(init.log_dZ2_mean, ex3[1]);
+    const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, ex3[2]);
     // pass 3: Z2
     double sc = kNegInf;
     {
@@ -446,7 +531,9 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
             lX2 += t.T2;
         })
     }
-    const double Z20 = logaddexp(init.log_Z2_mean, block_scan_excl<OpLae>(sc, sh, tot));
+    double in1[1] = {sc}, ex1[1];
+    block_scan_excl_k<OpLae, 1>(in1, sh, ex1);
+    const double Z20 = logaddexp(init.log_Z2_mean, ex1[0]);
     // pass 4: outputs
     {
         double lX = X0, lX2 = X20, lW = W0, lZ = Z0, ldZ2 = dZ20, lZ2 = Z20;
@@ -494,7 +581,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
 }
 
 __global__ void __launch_bounds__(1024) k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out) {
-    __shared__ double sh[33];
+    __shared__ double sh[3][33];
     evidence_scan_block<0>(q, init, out, sh);
 }
 

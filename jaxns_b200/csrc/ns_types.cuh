@@ -12,6 +12,7 @@ struct DevCtl {
     long long iteration;
     // derived per iteration by k_iter_prologue
     Key sample_key;
+    Key next_sample_key;   // sample_key of the following iteration (data-independent key chain)
     double contour;
     long long disc_start;  // clamped write offset of the discarded shell
     long long ph_start;    // clamped write offset of the phantom rows

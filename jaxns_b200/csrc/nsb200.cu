@@ -124,7 +124,7 @@ static int pick_spec(const Geometry &g) {
             const int v = atoi(e);
             if (v == 1 || v == 2 || v == 4) return v;
         }
-        return 2;
+        return 1;
     }
     return 2;
 }
@@ -270,12 +270,26 @@ extern "C" int nsb200_uniform_batch(const NsModelDesc *model, const uint32_t key
                        (long long *) out_nevals, 1, (cudaStream_t) stream);
 }
 
+// CTA size of the slice kernel.  When the factor lives in registers (D <= 32) nothing big is staged
+// per CTA, so one chain per CTA gives the block scheduler the finest grain to balance the 148 SMs.
+static int slice_threads(const Geometry &g) {
+    int tpb = (g.G == 32 && g.DPL == 1) ? 32 : kThreadsPerBlock;
+    const char *e = getenv("NSB200_TPB");
+    if (e) {
+        const int v = atoi(e);
+        if (v == 32 || v == 64 || v == 128) tpb = v;
+    }
+    return tpb < g.G ? g.G : tpb;
+}
+
 template <int G, int DPL, int P>
 static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st) {
     const long long n = a.chain_end - a.chain_begin;
-    const size_t smem = sampler_smem_bytes(a.model, g, P, true);
+    const int tpb = slice_threads(g);
+    const size_t per_chain = chain_smem_doubles(g.G, g.DPL, P, true);
+    const size_t smem = 8 * (model_smem_doubles(a.model.family, a.model.D, g.G, g.DPL, a.model.K) + (tpb / g.G) * per_chain);
     if (set_smem(k_slice_chains<G, DPL, P>, smem)) return 1;
-    k_slice_chains<G, DPL, P><<<grid_for(n, kThreadsPerBlock / G), kThreadsPerBlock, smem, st>>>(a);
+    k_slice_chains<G, DPL, P><<<grid_for(n, tpb / G), tpb, smem, st>>>(a);
     return 0;
 }
 
@@ -432,6 +446,8 @@ extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *l
     q.lb = nullptr;
     q.len_b = 0;
     q.n_start_b = 0.0;
+    q.tabT = q.tabT2 = q.tabt = nullptr;
+    q.tab_n = 0;
     EvOut o;
     o.mid = nullptr;
     o.mark = -1;
@@ -463,6 +479,7 @@ __global__ void k_fill_f64(double *p, long long n, double v) {
 __global__ void k_init_ctl(DevCtl *ctl, Key key) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->key = key;
+    ctl->next_sample_key = split_child(split_child(key, 0), 1);  // sample_key of the first body
     ctl->next_idx = 0;
     ctl->num_samples = 0;
     ctl->iteration = 0;
@@ -508,6 +525,16 @@ struct NsEngine {
     double *seed_table = nullptr;
     double *packed = nullptr;
     unsigned *rank = nullptr;
+    // chain streams of this rank's chains (k_chain_streams), double buffered: the streams of body i+1
+    // are generated on `side` while the slice kernel of body i runs on the caller's stream
+    double *pre_dirs[2] = {nullptr, nullptr};
+    double *pre_us[2] = {nullptr, nullptr};
+    uint2 *pre_rkeys[2] = {nullptr, nullptr};
+    double *tabT = nullptr, *tabT2 = nullptr, *tabt = nullptr;  // n-dependent evidence terms, n <= N
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_keys = nullptr, ev_streams[2] = {nullptr, nullptr};
+    int pre_cur = 0;          // buffer holding the streams of the NEXT body to run
+    bool pre_ready = false;   // streams of the next body have been enqueued
     NsTermCond tc;
     std::vector<void *> allocs;
     // profiling
@@ -534,6 +561,10 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
     if (e->reg_host) cudaFreeHost(e->reg_host);
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+    if (e->ev_keys) cudaEventDestroy(e->ev_keys);
+    for (int b = 0; b < 2; ++b)
+        if (e->ev_streams[b]) cudaEventDestroy(e->ev_streams[b]);
+    if (e->side) cudaStreamDestroy(e->side);
     delete e;
 }
 
@@ -584,6 +615,21 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->seed_table, e->N);
     if (!rc) rc |= dev_alloc(e, &e->packed, (size_t) e->packed_rows * e->row_doubles);
     if (!rc) rc |= dev_alloc(e, &e->rank, e->N);
+    if (!rc) rc |= dev_alloc(e, &e->tabT, e->N + 2);
+    if (!rc) rc |= dev_alloc(e, &e->tabT2, e->N + 2);
+    if (!rc) rc |= dev_alloc(e, &e->tabt, e->N + 2);
+    if (g.G >= 8) {  // data-independent chain streams are generated off the chains' critical path
+        const size_t rows = (size_t) e->rows_per_rank * cfg->num_slices;
+        for (int b = 0; b < 2; ++b) {
+            if (!rc) rc |= dev_alloc(e, &e->pre_dirs[b], rows * D);
+            if (!rc) rc |= dev_alloc(e, &e->pre_us[b], rows * kPre);
+            if (!rc) rc |= dev_alloc(e, &e->pre_rkeys[b], rows);
+        }
+        if (!rc && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate failed");
+        if (!rc && cudaEventCreateWithFlags(&e->ev_keys, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+        for (int b = 0; b < 2; ++b)
+            if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+    }
     if (!rc && cudaMallocHost((void **) &e->reg_host, sizeof(NsRegister)) != cudaSuccess) rc = fail("cudaMallocHost failed");
     if (!rc && cudaMallocHost((void **) &e->ctl_host, sizeof(DevCtl)) != cudaSuccess) rc = fail("cudaMallocHost failed");
     if (rc) {
@@ -624,6 +670,8 @@ static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
     return t;
 }
 
+static int enqueue_streams(NsEngine *e, int buf);
+
 extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
                                   nsb200_stream_t stream) {
     if (!e || !key) return fail("NULL argument");
@@ -643,7 +691,15 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     const Key k0{key[0], key[1]};
     const Key key1 = split_child(k0, 0), sample_key = split_child(k0, 1);
     k_init_ctl<<<1, 1, 0, st>>>(e->ctl, key1);
+    if (e->pre_dirs[0]) {
+        // the side stream may still be writing streams from a previous run into these buffers
+        NSB_CUDA(cudaStreamSynchronize(e->side));
+        NSB_CUDA(cudaEventRecord(e->ev_keys, st));
+        e->pre_cur = 0;
+        if (enqueue_streams(e, 0)) return 1;
+    }
     if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
+    k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
     // N prior draws (replicated on every rank), packed, ranked (stable argsort) and scattered
     double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
     long long *tmpN = e->live[1].nevals;
@@ -659,7 +715,7 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     *e->reg_host = init_register_host();
     NSB_CUDA(cudaMemcpyAsync(e->reg, e->reg_host, sizeof(NsRegister), cudaMemcpyHostToDevice, st));
     k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 1);
+                                         e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N);
     NSB_LAUNCH_CHECK();
     e->all_launches += 9;
     e->initialised = true;
@@ -684,10 +740,54 @@ static void drain_events(NsEngine *e) {
     e->ev_used = 0;
 }
 
+// Enqueues, on the engine's side stream, the generation of the chain streams of the body whose
+// sample_key is ctl->next_sample_key (valid once ev_keys has fired) into buffer `buf`.
+static int enqueue_streams(NsEngine *e, int buf) {
+    NSB_CUDA(cudaStreamWaitEvent(e->side, e->ev_keys, 0));
+    const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
+    StreamArgs sa;
+    sa.key = Key{0, 0};
+    sa.ctl = e->ctl;
+    sa.chain_begin = begin;
+    sa.chain_end = end;
+    sa.S = e->cfg.num_slices;
+    sa.D = e->D;
+    sa.dirs = e->pre_dirs[buf];
+    sa.us = e->pre_us[buf];
+    sa.rkeys = e->pre_rkeys[buf];
+    const long long warps = (end - begin) * ((sa.S + 31) / 32);
+    int sms = 148, per_sm = 2;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    if (const char *pe = getenv("NSB200_GEN_CTAS_PER_SM")) per_sm = atoi(pe) > 0 ? atoi(pe) : per_sm;
+    long long ctas = (long long) sms * per_sm;
+    if (ctas * 4 > warps) ctas = (warps + 3) / 4;
+    k_chain_streams<<<(int) ctas, 128, 0, e->side>>>(sa);
+    NSB_LAUNCH_CHECK();
+    NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
+    e->all_launches += 1;
+    if (getenv("NSB200_DEBUG_OVERLAP")) {
+        static cudaEvent_t dbg = nullptr;
+        if (!dbg) cudaEventCreate(&dbg);
+        cudaEventRecord(dbg, e->side);
+        cudaEventSynchronize(dbg);
+        if (e->ev_used >= 2) {
+            cudaEventSynchronize(e->ev_pool[e->ev_used - 1]);
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, e->ev_pool[e->ev_used - 2], dbg);                      // slice start -> generator end
+            cudaEventElapsedTime(&b, e->ev_pool[e->ev_used - 2], e->ev_pool[e->ev_used - 1]);  // slice start -> slice end
+            fprintf(stderr, "overlap dbg: generator done %.3f ms after slice start; slice took %.3f ms\n", a, b);
+        }
+    }
+    return 0;
+}
+
 extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
+    // streams of THIS body were enqueued by the previous step (or by init) on the side stream; they
+    // read ctl->next_sample_key, which the prologue below overwrites: wait for them first
+    if (e->pre_dirs[0]) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->pre_cur], 0));
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
@@ -708,11 +808,22 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.ctl = e->ctl;
     a.live0 = e->live[0];
     a.live1 = e->live[1];
+    const int buf = e->pre_cur;
+    a.pre_dirs = e->pre_dirs[buf];
+    a.pre_us = e->pre_us[buf];
+    a.pre_rkeys = e->pre_rkeys[buf];
+    if (e->pre_dirs[0]) NSB_CUDA(cudaEventRecord(e->ev_keys, st));  // next_sample_key is valid from here on
     cudaEvent_t e0 = next_event(e), e1 = next_event(e);
     cudaEventRecord(e0, st);
     if (launch_slice(a, st)) return 1;
     cudaEventRecord(e1, st);
     NSB_LAUNCH_CHECK();
+    if (e->pre_dirs[0]) {
+        // streams of the NEXT body, enqueued AFTER the slice kernel so that its CTAs are placed first and
+        // the throughput-bound generator fills the issue slots the latency-bound chains leave idle
+        if (enqueue_streams(e, buf ^ 1)) return 1;
+        e->pre_cur = buf ^ 1;
+    }
     e->slice_launches += 1;
     e->all_launches += 3;
     return 0;
@@ -727,7 +838,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
     k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 0);
+                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N);
     NSB_LAUNCH_CHECK();
     e->all_launches += 3;
     return 0;
