@@ -275,6 +275,10 @@ def run_native(args):
     # ---- e2e through the public API with host buffers --------------------------------------------
     e2e_t, e2e_evals, h2d, d2h = 0.0, 0, 0, 0
     n_e2e = max(1, min(args.steps, 3))
+    cap = ns.nested_sampler.max_samples
+    pinned = {"log_L": torch.empty(cap, dtype=torch.float64).pin_memory(),
+              "log_dp": torch.empty(cap, dtype=torch.float64).pin_memory(),
+              "x": torch.empty((cap, D), dtype=torch.float64).pin_memory()}
     for s in range(n_e2e):
         flush.fill_(0.5)
         barrier()
@@ -283,8 +287,12 @@ def run_native(args):
         ns2 = j.NestedSampler(model=m2, num_live_points=num_live)
         reason, state = ns2(random.PRNGKey(s))
         res = ns2.to_results(reason, state)
-        host = {"log_L": res.log_L_samples.cpu(), "log_dp": res.log_dp_mean.cpu(),
-                "x": res.samples["x"].cpu(), "logZ": res.log_Z_mean}
+        nres = res.total_num_samples  # posterior samples + weights into the user's pinned host buffers
+        host = {"log_L": pinned["log_L"][:nres], "log_dp": pinned["log_dp"][:nres], "x": pinned["x"][:nres]}
+        host["log_L"].copy_(res.log_L_samples, non_blocking=True)
+        host["log_dp"].copy_(res.log_dp_mean, non_blocking=True)
+        host["x"].copy_(res.samples["x"], non_blocking=True)
+        host["logZ"] = res.log_Z_mean
         torch.cuda.synchronize()
         e2e_t += time.perf_counter() - t0
         e2e_evals += res.total_num_likelihood_evaluations

@@ -12,6 +12,15 @@
 
 namespace nsb {
 
+// Global scratch of the cluster-wide register update (k_iter_epilogue).
+struct EpiScratch {
+    double gpart[144];  // CTA aggregates of the three cluster scans
+    NsEvidenceCalc mid, fin;
+    unsigned long long sum_new, sum_live;
+    int not_plateau;
+    int pad;
+};
+
 __device__ __forceinline__ long long clampll(long long v, long long lo, long long hi) {
     return v < lo ? lo : (v > hi ? hi : v);
 }
@@ -19,10 +28,14 @@ __device__ __forceinline__ long long clampll(long long v, long long lo, long lon
 // body prologue: the three key splits of one loop body (sharded_static.py:491,248,510), the contour
 // (:250-251) and the dead-store bookkeeping of _add_samples_to_state (:54,76-78).
 __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSet live0, const LiveSet live1,
-                                long long m, long long kph, long long capacity, int intended_sender) {
+                                long long m, long long kph, long long capacity, int intended_sender,
+                                EpiScratch *epi) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->active = reg->done ? 0 : 1;
     if (!ctl->active) return;
+    epi->sum_new = 0;
+    epi->sum_live = 0;
+    epi->not_plateau = 0;
     const LiveSet &live = ctl->cur ? live1 : live0;
     Key k = split_child(ctl->key, 0);      // :491  key, ephemeral_key = split(state.key)
     ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
@@ -220,21 +233,22 @@ __device__ inline void determine_termination(const NsTermCond &tc, NsRegister &r
 }
 
 // Register update of _collect_shell (sharded_static.py:281-323) followed by the loop condition.
-// One CTA of 1024 threads.  `old` = live set before the merge (its first m rows are the discarded
-// shell), `cur` = merged live set.
-__global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0,
-                                                        const LiveSet live1, const double *packed,
-                                                        long long row_doubles, int D, long long m, long long N,
-                                                        NsTermCond tc, int init_only, const double *tabT,
-                                                        const double *tabT2, const double *tabt, long long tab_n) {
-    __shared__ double sh[3][33];
-    __shared__ NsEvidenceCalc s_mid, s_fin;
-    __shared__ long long s_ll[2];
-    __shared__ int s_flag;
+// One thread-block cluster (kEvCluster CTAs x kEvThreads threads on neighbouring SMs, hardware
+// cluster barrier between the scan phases).  `old` = live set before the merge (its first m rows are
+// the discarded shell), `cur` = merged live set.
+__global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
+k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet live1, const double *packed,
+                long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
+                const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ double sh[3][34];
     if (!init_only && !ctl->active) return;
+    const long long gtid = (long long) cluster.block_rank() * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long) blockDim.x * cluster.num_blocks();
     if (init_only) {
         // _main_ns_thread entry (:471-473): no_seed_points of the initial live set, then cond.
-        if (threadIdx.x == 0) {
+        if (gtid == 0) {
             const LiveSet &live = ctl->cur ? live1 : live0;
             reg->no_seed_points = live.logL[m - 1] >= live.logL[N - 1];
             determine_termination(tc, *reg);
@@ -256,27 +270,21 @@ __global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister 
     q.tabt = tabt;
     q.tab_n = tab_n;
     EvOut out;
-    out.mid = &s_mid;
+    out.mid = &epi->mid;
     out.mark = m;
-    out.fin = &s_fin;
+    out.fin = &epi->fin;
     out.per_sample = nullptr;
-    if (m + N <= 8 * (long long) blockDim.x) evidence_scan_block<8>(q, reg->evidence_calc, out, sh);
-    else evidence_scan_block<0>(q, reg->evidence_calc, out, sh);
+    if (m + N <= 8 * nthreads) evidence_scan_block<8>(q, reg->evidence_calc, out, sh, epi->gpart);
+    else evidence_scan_block<0>(q, reg->evidence_calc, out, sh, epi->gpart);
     // sums of likelihood evaluations, plateau flag
     long long sum_new = 0, sum_live = 0;
     int not_plateau = 0;
     const double l0 = cur.logL[0];
-    for (long long i = threadIdx.x; i < N; i += blockDim.x) {
+    for (long long i = gtid; i < N; i += nthreads) {
         sum_live += cur.nevals[i];
         not_plateau |= !(cur.logL[i] == l0);
         if (i < m) sum_new += __double_as_longlong(packed[i * row_doubles + D + 1]);
     }
-    if (threadIdx.x == 0) {
-        s_ll[0] = 0;
-        s_ll[1] = 0;
-        s_flag = 0;
-    }
-    __syncthreads();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sum_new += __shfl_xor_sync(0xFFFFFFFFu, sum_new, o);
@@ -284,20 +292,23 @@ __global__ void __launch_bounds__(1024) k_iter_epilogue(DevCtl *ctl, NsRegister 
         not_plateau |= __shfl_xor_sync(0xFFFFFFFFu, not_plateau, o);
     }
     if ((threadIdx.x & 31) == 0) {
-        atomicAdd((unsigned long long *) &s_ll[0], (unsigned long long) sum_new);
-        atomicAdd((unsigned long long *) &s_ll[1], (unsigned long long) sum_live);
-        if (not_plateau) atomicOr(&s_flag, 1);
+        atomicAdd(&epi->sum_new, (unsigned long long) sum_new);
+        atomicAdd(&epi->sum_live, (unsigned long long) sum_live);
+        if (not_plateau) atomicOr(&epi->not_plateau, 1);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    __threadfence();
+    cluster.sync();
+    if (gtid == 0) {
         NsRegister r = *reg;
+        const NsEvidenceCalc s_mid = epi->mid;
+        const NsEvidenceCalc s_fin = epi->fin;
         r.num_samples_used = ctl->num_samples;
         r.evidence_calc = s_mid;
         r.evidence_calc_with_remaining = s_fin;
-        r.num_likelihood_evaluations += s_ll[0];
+        r.num_likelihood_evaluations += (long long) *(volatile unsigned long long *) &epi->sum_new;
         r.log_L_contour = ctl->contour;
-        r.efficiency = (double) N / (double) s_ll[1];
-        r.plateau = s_flag ? 0 : 1;
+        r.efficiency = (double) N / (double) (long long) *(volatile unsigned long long *) &epi->sum_live;
+        r.plateau = (*(volatile int *) &epi->not_plateau) ? 0 : 1;
         const double lo = cur.logL[0], hi = cur.logL[N - 1];
         r.absolute_spread = fabs(hi - lo);
         r.relative_spread = 2.0 * r.absolute_spread / fabs(lo + hi);

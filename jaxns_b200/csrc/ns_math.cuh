@@ -153,72 +153,63 @@ __device__ __forceinline__ double normal_from_bits(uint64_t bits) {
     return 1.4142135623730951 * erfinv_xla(u);
 }
 
-// tfp special_math.ndtri == Cephes ndtri (Normal.quantile in the prior transform).  Central piece
-// (exp(-2) < p < 1 - exp(-2)) inline and branch-free so batched proposals interleave; the tails and
-// the p in {0, 1, NaN} edge cases are one shared out-of-line function.
-__constant__ double kNdtriP0[5] = {-5.99633501014107895267E1, 9.80010754185999661536E1, -5.66762857469070293439E1,
-                                   1.39312609387279679503E1, -1.23916583867381258016E0};
-__constant__ double kNdtriQ0[8] = {1.95448858338141759834E0, 4.67627912898881538453E0, 8.63602421390890590575E1,
-                                   -2.25462687854119370527E2, 2.00260212380060660359E2, -8.20372256168333339912E1,
-                                   1.59056225126211695515E1, -1.18331621121330003142E0};
-__constant__ double kNdtriP1[9] = {4.05544892305962419923E0, 3.15251094599893866154E1, 5.71628192246421288162E1,
-                                   4.40805073893200834700E1, 1.46849561928858024014E1, 2.18663306850790267539E0,
-                                   -1.40256079171354495875E-1, -3.50424626827848203418E-2, -8.57456785154685413611E-4};
-__constant__ double kNdtriQ1[8] = {1.57799883256466749731E1, 4.53907635128879210584E1, 4.13172038254672030440E1,
-                                   1.50425385692907503408E1, 2.50464946208309415979E0, -1.42182922854787788574E-1,
-                                   -3.80806407691578277194E-2, -9.33259480895457427372E-4};
-__constant__ double kNdtriP2[9] = {3.23774891776946035970E0, 6.91522889068984211695E0, 3.93881025292474443415E0,
-                                   1.33303460815807542389E0, 2.01485389549179081538E-1, 1.23716634817820021358E-2,
-                                   3.01581553508235416007E-4, 2.65806974686737550832E-6, 6.23974539184983293730E-9};
-__constant__ double kNdtriQ2[8] = {6.02427039364742014255E0, 3.67983563856160859403E0, 1.37702099489081330271E0,
-                                   2.16236993594496635890E-1, 1.34204006088543189037E-2, 3.28014464682127739104E-4,
-                                   2.89247864745380683936E-6, 6.79019408009981274425E-9};
+// Normal quantile for the prior transform (tfd.Normal.quantile -> tfp special_math.ndtri).
+// The reference evaluates Cephes' ndtri: central rational + a tail that needs two dependent logs, a
+// sqrt and two divisions (~1000 cycles of latency on B200, and with 32 lanes per chain some lane is
+// almost always in the tail).  This is 49 % of a chain's critical path, so the device code uses
+// Wichura's AS241 (PPND16) instead: same double-precision accuracy (it agrees with Cephes/scipy to
+// <= 1.1e-15 relative over (1e-300, 1 - 1e-16), tests/test_gpu_parity.py), but its tail is one log, one
+// sqrt and one division, and its central region is wider (|p - 0.5| <= 0.425).  Central part is
+// branch-free; the tail runs only if some lane of the group needs it (warp-uniform vote), so its log
+// overlaps the central division instead of following it.
+__constant__ double kPpndA[8] = {3.3871328727963666080, 1.3314166789178437745E+2, 1.9715909503065514427E+3,
+                                 1.3731693765509461125E+4, 4.5921953931549871457E+4, 6.7265770927008700853E+4,
+                                 3.3430575583588128105E+4, 2.5090809287301226727E+3};
+__constant__ double kPpndB[8] = {1.0, 4.2313330701600911252E+1, 6.8718700749205790830E+2, 5.3941960214247511077E+3,
+                                 2.1213794301586595867E+4, 3.9307895800092710610E+4, 2.8729085735721942674E+4,
+                                 5.2264952788528545610E+3};
+__constant__ double kPpndC[8] = {1.42343711074968357734, 4.63033784615654529590, 5.76949722146069140550,
+                                 3.64784832476320460504, 1.27045825245236838258, 2.41780725177450611770E-1,
+                                 2.27238449892691845833E-2, 7.74545014278341407640E-4};
+__constant__ double kPpndD[8] = {1.0, 2.05319162663775882187, 1.67638483018380384940, 6.89767334985100004550E-1,
+                                 1.48103976427480074590E-1, 1.51986665636164571966E-2, 5.47593808499534494600E-4,
+                                 1.05075007164441684324E-9};
+__constant__ double kPpndE[8] = {6.65790464350110377720, 5.46378491116411436990, 1.78482653991729133580,
+                                 2.96560571828504891230E-1, 2.65321895265761230930E-2, 1.24266094738807843860E-3,
+                                 2.71155556874348757815E-5, 2.01033439929228813265E-7};
+__constant__ double kPpndF[8] = {1.0, 5.99832206555887937690E-1, 1.36929880922735805310E-1, 1.48753612908506148525E-2,
+                                 7.86869131145613259100E-4, 1.84631831751005468180E-5, 1.42151175831644588870E-7,
+                                 2.04426310338993978564E-15};
 
-__device__ __noinline__ double ndtri_tail(double p) {
-    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
-    if (p == 0.0) return -kInf;
-    if (p == 1.0) return kInf;
-    if (!(p > 0.0 && p < 1.0)) return __longlong_as_double(0x7FF8000000000000ll);
-    const bool upper = p > 0.8646647167633873;  // -expm1(-2)
-    const double q = upper ? 1.0 - p : p;
-    const double z = sqrt(-2.0 * log(q));
-    const double rz = 1.0 / z;
-    const double first = z - log(z) * rz;
-    double num, den = 1.0;
-    if (z >= 8.0) {
-        num = kNdtriP2[0];
+__device__ __forceinline__ double horner8(const double *c, double x) {
+    double r = c[7];
 #pragma unroll
-        for (int i = 1; i < 9; ++i) num = num * rz + kNdtriP2[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) den = den * rz + kNdtriQ2[i];
-    } else {
-        num = kNdtriP1[0];
-#pragma unroll
-        for (int i = 1; i < 9; ++i) num = num * rz + kNdtriP1[i];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) den = den * rz + kNdtriQ1[i];
-    }
-    const double x = first - (num / den) * rz;
-    return upper ? x : -x;
+    for (int i = 6; i >= 0; --i) r = fma(r, x, c[i]);
+    return r;
 }
 
-__device__ __forceinline__ double ndtri(double p) {
-    const bool upper = p > 0.8646647167633873;
-    const double q = upper ? 1.0 - p : p;
-    if (q > 0.1353352832366127) {  // exp(-2): implies 0 < p < 1
-        const double w = q - 0.5;
-        const double ww = w * w;
-        double num = kNdtriP0[0];
-#pragma unroll
-        for (int i = 1; i < 5; ++i) num = num * ww + kNdtriP0[i];
-        double den = 1.0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) den = den * ww + kNdtriQ0[i];
-        double x = w + w * ww * (num / den);
-        x *= -2.5066282746310002;  // -sqrt(2 pi)
-        return upper ? x : -x;
+// `mask` = lanes that execute this call together (the chain's lane group).
+__device__ __forceinline__ double ndtri(double p, unsigned mask) {
+    const double q = p - 0.5;
+    const double r = fma(-q, q, 0.180625);
+    double x = q * horner8(kPpndA, r) / horner8(kPpndB, r);
+    const bool tail = !(fabs(q) <= 0.425);  // also true for NaN
+    if (__any_sync(mask, tail)) {
+        const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+        double pp = (q < 0.0) ? p : 1.0 - p;
+        pp = tail ? pp : 0.05;  // keep the non-tail lanes on the fast paths of log / sqrt
+        const double rr = sqrt(-log(pp));
+        const double a = rr - 1.6, b = rr - 5.0;
+        const double v1 = horner8(kPpndC, a) / horner8(kPpndD, a);
+        const double v2 = horner8(kPpndE, b) / horner8(kPpndF, b);
+        double v = (rr <= 5.0) ? v1 : v2;
+        v = (q < 0.0) ? -v : v;
+        if (p == 0.0) v = -kInf;
+        if (p == 1.0) v = kInf;
+        if (!(p >= 0.0 && p <= 1.0)) v = __longlong_as_double(0x7FF8000000000000ll);
+        x = tail ? v : x;
     }
-    return ndtri_tail(p);
+    return x;
 }
 
 // log1p(e) for e in [0, 1] with one log and one division (Kahan): libdevice's log1p costs ~300

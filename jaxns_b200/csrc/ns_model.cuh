@@ -201,7 +201,7 @@ __device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp<G>
             for (int p = 0; p < P; ++p) X[p][s] = u[p][s] * b + a;
         } else {
 #pragma unroll
-            for (int p = 0; p < P; ++p) X[p][s] = (j < sm.D) ? ndtri(u[p][s]) * b + a : 0.0;
+            for (int p = 0; p < P; ++p) X[p][s] = ndtri(u[p][s], g.m()) * b + a;  // padded dims: u = 0.5, b = 0
         }
     }
 }
@@ -233,22 +233,23 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
             if (dense_in_regs(G, DPL)) {
                 // z_lane = sum_j Linv[lane][j] r_j with the row in registers; two partial sums per
                 // proposal shorten the dependent FMA chain.
-                double z0[P], z1[P];
+                constexpr int NR = DenseRow<G, DPL>::N;
+                constexpr int NA = NR >= 4 ? 4 : 1;  // partial sums: 8-deep FMA chains instead of 32
+                double z[NA][P];
 #pragma unroll
-                for (int p = 0; p < P; ++p) z0[p] = z1[p] = 0.0;
+                for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int j = 0; j < DenseRow<G, DPL>::N; j += 2) {
+                    for (int p = 0; p < P; ++p) z[a][p] = 0.0;
 #pragma unroll
-                    for (int p = 0; p < P; ++p) {
-                        z0[p] = fma(row.v[j], scratch[j * P + p], z0[p]);
-                        z1[p] = fma(row.v[j + 1 < DenseRow<G, DPL>::N ? j + 1 : j],
-                                    (j + 1 < DenseRow<G, DPL>::N) ? scratch[(j + 1) * P + p] : 0.0, z1[p]);
-                    }
+                for (int j = 0; j < NR; ++j) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) z[j % NA][p] = fma(row.v[j], scratch[j * P + p], z[j % NA][p]);
                 }
 #pragma unroll
                 for (int p = 0; p < P; ++p) {
-                    const double z = z0[p] + z1[p];
-                    q[p] = z * z;
+                    double zz = z[0][p];
+                    if (NA == 4) zz = (z[0][p] + z[1][p]) + (z[2][p] + z[3][p]);
+                    q[p] = zz * zz;
                 }
             } else if (sm.dense_global) {
 #pragma unroll

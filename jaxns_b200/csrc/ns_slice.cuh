@@ -24,6 +24,21 @@
 
 namespace nsb {
 
+#ifdef NSB_PROFILE
+// cycle accounting of chain 0's critical path (debug builds only): g_prof[k] accumulates clock64 deltas
+__device__ unsigned long long g_prof[16];
+#define NSB_T0() long long _t0 = clock64()
+#define NSB_TICK(k)                               \
+    {                                             \
+        const long long _t1 = clock64();          \
+        prof[k] += (unsigned long long) (_t1 - _t0); \
+        _t0 = _t1;                                \
+    }
+#else
+#define NSB_T0()
+#define NSB_TICK(k)
+#endif
+
 // Uniforms per slice drawn ahead by the lane-parallel precompute (shrink steps beyond that fall
 // back to walking the run_key chain inline).
 constexpr int kPre = 8;
@@ -55,6 +70,7 @@ struct SliceArgs {
     const double *pre_dirs;
     const double *pre_us;
     const uint2 *pre_rkeys;
+    const double *alpha_tab;  // optional [S]: alpha_schedule(j, S) (saves an int->double division per slice)
 };
 
 // jnp.linspace(0.5, 1., S)[j]
@@ -134,8 +150,17 @@ __host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool
     return (size_t) G * DPL * P + (slice ? (size_t) G * (kPre + 2) : 0);
 }
 
-template <int G, int DPL, int P, int FAM, bool PRE>
+// W > 1 ("warp team"): the CTA is ONE chain run by W warps that execute the same program; in every
+// shrink round warp w evaluates the w-th speculative proposal and the W log-likelihoods are exchanged
+// through shared memory around one __syncthreads().  Unlike the in-warp batch (P) this adds real
+// parallelism: a config-2 sized problem leaves most warp slots and issue cycles idle, and the
+// kernel time is the latency of its longest chain, so halving the sequential rounds per slice is
+// worth more than the ~15 % of evaluations that are thrown away.  Results are unchanged (first
+// accepted proposal wins, n_evals counts up to it).  Requires G == 32, P == 1, PRE.
+template <int G, int DPL, int P, int FAM, bool PRE, int W = 1>
 __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *smem) {
+    static_assert(W == 1 || (G == 32 && P == 1 && PRE), "warp teams need G == 32, P == 1 and precomputed streams");
+    constexpr bool TEAM = W > 1;
     constexpr int DP = G * DPL;
     const int D = a.model.D;
     Key base_key = a.key;
@@ -154,10 +179,14 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     stage_model<G, DPL>(a.model, smem, sm);
     __syncthreads();
     const Grp<G> g;
-    const int chains_per_block = blockDim.x / G;  // the slice kernel picks its CTA size at launch
-    const int local_chain = threadIdx.x / G;
-    const long long chain = a.chain_begin + (long long) blockIdx.x * chains_per_block + local_chain;
+    const int wt = TEAM ? (int) (threadIdx.x >> 5) : 0;  // warp of the team = which proposal of a round it evaluates
+    const int chains_per_block = TEAM ? 1 : blockDim.x / G;  // the slice kernel picks its CTA size at launch
+    const int local_chain = TEAM ? wt : threadIdx.x / G;     // index of this lane group's private smem slot
+    const long long chain = a.chain_begin + (long long) blockIdx.x * chains_per_block + (TEAM ? 0 : local_chain);
     if (chain >= a.chain_end) return;
+    double *res = smem + model_smem_doubles(a.model.family, D, G, DPL, a.model.K) +
+                  (size_t) (TEAM ? W : 0) * chain_smem_doubles(G, DPL, P, true);  // [2][W] exchange buffer (TEAM)
+    int par = 0;
     DenseRow<G, DPL> row;
     row.load(sm, g.lane);
 
@@ -186,6 +215,11 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     double logL0 = live_logL[sidx];
     const long long out_row = chain - a.chain_begin;
     long long nev = 0;
+#ifdef NSB_PROFILE
+    unsigned long long prof[16];
+    for (int k = 0; k < 16; ++k) prof[k] = 0;
+#endif
+    NSB_T0();
     Key sample_key2 = Key{0, 0};
     // stream of slice 0 (PRE: fetched; otherwise derived below)
     double unext = 0.0;           // lane p < kPre holds uniform p of the next slice
@@ -205,6 +239,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         sample_direction<G, DPL>(g, D, direction_key, d);
     }
 
+    NSB_TICK(0)  // chain prelude
     for (int base = 0; base < S; base += G) {
         // ---- precompute the key stream of slices base .. base+G-1, one slice per lane
         if (!PRE) {
@@ -232,7 +267,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         const int jmax = min(G, S - base);
         for (int jl = 0; jl < jmax; ++jl) {
             const int j = base + jl;
-            const double alpha = alpha_schedule(j, S);
+            const double alpha = a.alpha_tab ? __ldg(a.alpha_tab + j) : alpha_schedule(j, S);
             const double *uq;
             Key run_key;
             double dnext[DPL];
@@ -260,10 +295,65 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                 sample_direction<G, DPL>(g, D, Key{pk[0], pk[1]}, dnext);
                 run_key = Key{pk[2], pk[3]};
             }
+            NSB_TICK(1)  // stream fetch / direction
             double left, right;
             slice_bounds<G, DPL>(g, D, U0, d, left, right);
+            NSB_TICK(2)  // bounds
             int ne = 0;  // proposals generated so far in this slice
             double logL_acc = 0.0;
+            if (TEAM) {
+                for (;;) {
+                    double ts[W];
+                    double l = left, r = right;
+#pragma unroll
+                    for (int p = 0; p < W; ++p) {
+                        double uu;
+                        const int n = ne + p;
+                        if (n < kPre) {
+                            uu = uq[n];
+                        } else {
+                            const Key t_key = split_child(run_key, 1);
+                            run_key = split_child(run_key, 0);
+                            uu = uniform01(t_key, 0);
+                        }
+                        const double t = l + uu * (r - l);
+                        ts[p] = t;
+                        if (t < 0.0) l = midpoint ? alpha * t : t;
+                        if (t > 0.0) r = midpoint ? alpha * t : t;
+                    }
+                    double tmine = ts[0];
+#pragma unroll
+                    for (int p = 1; p < W; ++p) tmine = (wt == p) ? ts[p] : tmine;
+                    double x1[1][DPL], l1[1];
+#pragma unroll
+                    for (int s = 0; s < DPL; ++s) x1[0][s] = fma(tmine, d[s], U0[s]);
+                    forward_group<G, DPL, 1, FAM>(sm, g, row, x1, scratch, l1);
+                    if (g.lane == 0) res[par * W + wt] = l1[0];
+                    __syncthreads();
+                    int hit = -1;
+                    double l_hit = 0.0, t_hit = 0.0;
+#pragma unroll
+                    for (int p = W - 1; p >= 0; --p) {
+                        const double lp = res[par * W + p];
+                        if ((lp > contour) || ((logL0 == contour) && (lp == contour))) {
+                            hit = p;
+                            l_hit = lp;
+                            t_hit = ts[p];
+                        }
+                    }
+                    par ^= 1;
+                    if (hit >= 0) {
+#pragma unroll
+                        for (int s = 0; s < DPL; ++s) U0[s] = fma(t_hit, d[s], U0[s]);
+                        logL_acc = l_hit;
+                        ne += hit + 1;
+                        break;
+                    }
+                    ne += W;
+                    left = l;
+                    right = r;
+                }
+            } else
             for (;;) {
                 // ---- generate P proposals assuming each previous one is rejected (:92-111, :169-186)
                 double ts[P], x[P][DPL], logL[P];
@@ -286,7 +376,19 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 #pragma unroll
                     for (int s = 0; s < DPL; ++s) x[p][s] = fma(t, d[s], U0[s]);
                 }
+                NSB_TICK(3)  // proposal generation
+#ifdef NSB_PROFILE
+                {
+                    double Xp[P][DPL];
+                    transform_dims<G, DPL, P>(sm, g, x, Xp);
+                    NSB_TICK(4)  // prior transform
+                    loglik_group<G, DPL, P, FAM>(sm, g, row, Xp, scratch, logL);
+                    NSB_TICK(5)  // likelihood
+                    prof[8] += 1;
+                }
+#else
                 forward_group<G, DPL, P, FAM>(sm, g, row, x, scratch, logL);
+#endif
                 // ---- first accepted proposal wins (:160-166)
                 int hit = -1;
 #pragma unroll
@@ -310,12 +412,16 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                 left = l;
                 right = r;
             }
+            NSB_TICK(6)  // accept logic / loop overhead
             logL0 = logL_acc;
             nev += ne;
+#ifdef NSB_PROFILE
+            prof[9] += 1;
+#endif
 #pragma unroll
             for (int s = 0; s < DPL; ++s) d[s] = dnext[s];
             // phantom capture: cumulative_samples[-(k+1):-1] (:430-440)
-            if (kph > 0 && j >= S - 1 - kph && j < S - 1) {
+            if (kph > 0 && j >= S - 1 - kph && j < S - 1 && wt == 0) {
                 const long long slot = out_row * kph + (j - (S - 1 - kph));
 #pragma unroll
                 for (int s = 0; s < DPL; ++s) {
@@ -335,6 +441,12 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         }
         group_sync(g);  // pre_u / pre_k are rewritten by the next chunk
     }
+    NSB_TICK(7)
+#ifdef NSB_PROFILE
+    if (chain == a.chain_begin && g.lane == 0 && wt == 0)
+        for (int k = 0; k < 16; ++k) atomicAdd(&g_prof[k], prof[k]);
+#endif
+    if (wt != 0) return;
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
@@ -361,6 +473,18 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) 
     } else {
         NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, false>(a, smem));
     }
+}
+
+// One chain per CTA, W warps per chain (see slice_chains_body).  Register budget: 2 warps x 1600
+// chains must all be resident (21.6 warps per SM), hence the occupancy hint.
+template <int DPL, int W>
+__global__ void __launch_bounds__(32 * W, 22 / W) k_slice_chains_team(SliceArgs a) {
+    extern __shared__ double smem[];
+    NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<32, DPL, 1, kFam, true, W>(a, smem));
+}
+
+__global__ void k_alpha_table(int S, double *out) {
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < S; j += gridDim.x * blockDim.x) out[j] = alpha_schedule(j, S);
 }
 
 // ---- data-independent per-chain streams ----------------------------------------------------------

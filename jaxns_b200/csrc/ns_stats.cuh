@@ -7,6 +7,8 @@
 // cumulative_op_static/dynamic (internals/cumulative_ops.py:50-130), LogSpace.sum
 // (internals/log_semiring.py:187-190), jnp.argsort call sites sharded_static.py:174,274.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "ns_math.cuh"
 #include "../../include/nsb200.h"
 
@@ -61,7 +63,7 @@ __device__ __forceinline__ double block_scan_excl(double v, double *sh, double &
 // Same, K values per thread scanned together: the K combines of a step are independent, so their
 // latencies (logaddexp ~ 500 cycles) overlap instead of adding up over K separate scans.
 template <class Op, int K>
-__device__ __forceinline__ void block_scan_excl_k(const double (&v)[K], double (*sh)[33], double (&exc_out)[K]) {
+__device__ __forceinline__ void block_scan_excl_k(const double (&v)[K], double (*sh)[34], double (&exc_out)[K]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
     double inc[K], exc[K];
 #pragma unroll
@@ -102,11 +104,53 @@ __device__ __forceinline__ void block_scan_excl_k(const double (&v)[K], double (
             double wexc = __shfl_up_sync(0xFFFFFFFFu, winc[k], 1);
             if (lane == 0) wexc = Op::id();
             sh[k][lane] = wexc;
+            if (lane == 31) sh[k][32] = winc[k];  // CTA aggregate
         }
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) exc_out[k] = Op::ap(sh[k][warp], exc[k]);
+}
+
+// Exclusive scan across all threads of a thread-block CLUSTER (1..16 CTAs on neighbouring SMs):
+// CTA-level scan, CTA aggregates exchanged through `gpart` ([ranks][K] doubles of global memory)
+// around one hardware cluster barrier, prefix of the lower-ranked CTAs folded in by warp 0.
+template <class Op, int K>
+__device__ __forceinline__ void cluster_scan_excl_k(const double (&v)[K], double (*sh)[34], double *gpart,
+                                                    double (&out)[K]) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+    double exc[K];
+    block_scan_excl_k<Op, K>(v, sh, exc);
+    if (nranks == 1) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = exc[k];
+        return;
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) gpart[rank * K + k] = sh[k][32];
+    }
+    cluster.sync();
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x < 32) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            double inc = ((unsigned) lane < nranks) ? gpart[lane * K + k] : Op::id();
+#pragma unroll
+            for (int o = 1; o < 16; o <<= 1) {
+                double y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= o) inc = Op::ap(y, inc);
+            }
+            double e = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+            if (lane == 0) e = Op::id();
+            if ((unsigned) lane == rank) sh[k][33] = e;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) out[k] = Op::ap(sh[k][33], exc[k]);
 }
 
 // =================================================================================================
@@ -444,12 +488,19 @@ struct EvOut {
 // Must be called by all threads of a CTA.  sh = 33 doubles.  CACHE > 0: every thread owns at most
 // CACHE elements and keeps their terms (3 log + 3 logaddexp each) in registers across the passes --
 // the per-iteration register update (m + N elements over 1024 threads) runs this way.
+// `gpart` = 3 * 16 * 3 doubles of global scratch for the cluster-level scans (nullptr is fine for a
+// single CTA).
 template <int CACHE>
-__device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double (*sh)[33]) {
+__device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double (*sh)[34],
+                                           double *gpart) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
     const double kLog2 = 0.6931471805599453;
     const long long M = q.len_a + q.len_b;
-    const long long per = (M + blockDim.x - 1) / blockDim.x;
-    const long long b = min(M, (long long) threadIdx.x * per), e = min(M, b + per);
+    const long long nthreads = (long long) blockDim.x * cluster.num_blocks();
+    const long long gtid = (long long) cluster.block_rank() * blockDim.x + threadIdx.x;
+    const long long per = (M + nthreads - 1) / nthreads;
+    const long long b = min(M, gtid * per), e = min(M, b + per);
     double prev0 = init.log_L;
     if (b > 0 && b < M) {
         double nn;
@@ -496,7 +547,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
     double sT = 0.0, sT2 = 0.0;
     NSB_EV_LOOP({ (void) i; (void) logL; sT += t.T; sT2 += t.T2; })
     double in2[2] = {sT, sT2}, ex2[2];
-    block_scan_excl_k<OpAdd, 2>(in2, sh, ex2);
+    cluster_scan_excl_k<OpAdd, 2>(in2, sh, gpart, ex2);
     const double X0 = init.log_X_mean + ex2[0];
     const double X20 = init.log_X2_mean + ex2[1];
     // pass 2: Z, dZ2, W = ZX / X
@@ -514,7 +565,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in3[3] = {sa, sb, sw}, ex3[3];
-    block_scan_excl_k<OpLae, 3>(in3, sh, ex3);
+    cluster_scan_excl_k<OpLae, 3>(in3, sh, gpart + 48, ex3);
     const double Z0 = logaddexp(init.log_Z_mean, ex3[0]);
     const double dZ20 = logaddexp(init.log_dZ2_mean, ex3[1]);
     const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, ex3[2]);
@@ -532,10 +583,11 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in1[1] = {sc}, ex1[1];
-    block_scan_excl_k<OpLae, 1>(in1, sh, ex1);
+    cluster_scan_excl_k<OpLae, 1>(in1, sh, gpart + 96, ex1);
     const double Z20 = logaddexp(init.log_Z2_mean, ex1[0]);
-    // pass 4: outputs
-    {
+    // pass 4: outputs (skipped by threads that own neither a requested position nor per-sample rows)
+    const bool wanted = out.per_sample || (out.mid && out.mark - 1 >= b && out.mark - 1 < e) || (out.fin && M - 1 >= b && M - 1 < e);
+    if (wanted) {
         double lX = X0, lX2 = X20, lW = W0, lZ = Z0, ldZ2 = dZ20, lZ2 = Z20;
         NSB_EV_LOOP({
             const double dZ = lX + t.t + t.mid;
@@ -572,17 +624,21 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
 #undef NSB_EV_LOOP
-    if (M == 0 && threadIdx.x == 0) {
+    if (M == 0 && gtid == 0) {
         if (out.fin) *out.fin = init;
         if (out.mid) *out.mid = init;
-    } else if (out.mid && out.mark == 0 && threadIdx.x == 0) {
+    } else if (out.mid && out.mark == 0 && gtid == 0) {
         *out.mid = init;
     }
 }
 
-__global__ void __launch_bounds__(1024) k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out) {
-    __shared__ double sh[3][33];
-    evidence_scan_block<0>(q, init, out, sh);
+constexpr int kEvCluster = 8;    // CTAs per cluster (portable maximum)
+constexpr int kEvThreads = 512;  // threads per CTA
+
+__global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
+k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out, double *gpart) {
+    __shared__ double sh[3][34];
+    evidence_scan_block<0>(q, init, out, sh, gpart);
 }
 
 // =================================================================================================

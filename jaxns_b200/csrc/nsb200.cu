@@ -293,10 +293,48 @@ static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st
     return 0;
 }
 
+// Warps per chain (slice_chains_body W): 2 when the problem is too small to fill the GPU with one warp
+// per chain (the case where chain latency, not throughput, sets the kernel time).  NSB200_TEAM=1/2
+// overrides.
+static int pick_team(const SliceArgs &a, const Geometry &g) {
+    if (!(g.G == 32 && a.pre_dirs)) return 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+    const long long n = a.chain_end - a.chain_begin;
+    int W = (n * 2 <= (long long) sms * 24) ? 2 : 1;
+    if (const char *e = getenv("NSB200_TEAM")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 2) W = v;
+    }
+    return W;
+}
+
+template <int DPL, int W>
+static int launch_team_t(const SliceArgs &a, cudaStream_t st) {
+    const long long n = a.chain_end - a.chain_begin;
+    const size_t smem = 8 * (model_smem_doubles(a.model.family, a.model.D, 32, DPL, a.model.K) +
+                             W * chain_smem_doubles(32, DPL, 1, true) + 2 * W);
+    if (set_smem(k_slice_chains_team<DPL, W>, smem)) return 1;
+    k_slice_chains_team<DPL, W><<<(unsigned) n, 32 * W, smem, st>>>(a);
+    return 0;
+}
+
 static int launch_slice(const SliceArgs &a, cudaStream_t st) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
     if (a.chain_end <= a.chain_begin) return 0;
+    if (pick_team(a, g) == 2) {
+        int rc;
+        switch (g.DPL) {
+            case 1: rc = launch_team_t<1, 2>(a, st); break;
+            case 2: rc = launch_team_t<2, 2>(a, st); break;
+            case 4: rc = launch_team_t<4, 2>(a, st); break;
+            default: rc = launch_team_t<8, 2>(a, st); break;
+        }
+        if (rc) return rc;
+        NSB_LAUNCH_CHECK();
+        return 0;
+    }
     const int P = pick_spec(g);
     if (g.G == 32 && g.DPL == 1) {
         int rc;
@@ -367,7 +405,7 @@ extern "C" int64_t nsb200_workspace_bytes(int32_t op, int64_t n) {
     switch (op) {
         case NSB200_WS_ARGSORT: return (int64_t) sort_workspace_bytes(n > 0 ? n : 1);
         case NSB200_WS_COUNT_CROSSED_EDGES: return (int64_t) tree_workspace_bytes(n);
-        case NSB200_WS_EVIDENCE_STATS: return 256;
+        case NSB200_WS_EVIDENCE_STATS: return 144 * 8 + 256;
         case NSB200_WS_LOGSUMEXP: return 256;
         default: return -1;
     }
@@ -433,11 +471,10 @@ static NsEvidenceCalc init_evidence_calc() {
 extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *log_L, const double *num_live_points,
                                      int64_t M, NsEvidenceCalc *out_final, double *out_per_sample, void *workspace,
                                      int64_t workspace_bytes, nsb200_stream_t stream) {
-    (void) workspace;
-    (void) workspace_bytes;
     if (M < 0) return fail("M < 0");
     if (M > 0 && (!log_L || !num_live_points)) return fail("NULL input");
     if (!out_final) return fail("out_final is NULL");
+    if (!workspace || workspace_bytes < 144 * 8 + 256) return fail("workspace too small (nsb200_workspace_bytes(NSB200_WS_EVIDENCE_STATS, M))");
     EvSeq q;
     q.la = log_L;
     q.na = num_live_points;
@@ -453,7 +490,8 @@ extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *l
     o.mark = -1;
     o.fin = out_final;
     o.per_sample = out_per_sample;
-    k_evidence_stats<<<1, 1024, 0, (cudaStream_t) stream>>>(q, init ? *init : init_evidence_calc(), o);
+    double *gpart = (double *) align256((size_t) workspace);
+    k_evidence_stats<<<kEvCluster, kEvThreads, 0, (cudaStream_t) stream>>>(q, init ? *init : init_evidence_calc(), o, gpart);
     NSB_LAUNCH_CHECK();
     return 0;
 }
@@ -531,6 +569,8 @@ struct NsEngine {
     double *pre_us[2] = {nullptr, nullptr};
     uint2 *pre_rkeys[2] = {nullptr, nullptr};
     double *tabT = nullptr, *tabT2 = nullptr, *tabt = nullptr;  // n-dependent evidence terms, n <= N
+    EpiScratch *epi = nullptr;
+    double *alpha_tab = nullptr;
     cudaStream_t side = nullptr;
     cudaEvent_t ev_keys = nullptr, ev_streams[2] = {nullptr, nullptr};
     int pre_cur = 0;          // buffer holding the streams of the NEXT body to run
@@ -615,6 +655,8 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->seed_table, e->N);
     if (!rc) rc |= dev_alloc(e, &e->packed, (size_t) e->packed_rows * e->row_doubles);
     if (!rc) rc |= dev_alloc(e, &e->rank, e->N);
+    if (!rc) rc |= dev_alloc(e, &e->epi, 1);
+    if (!rc) rc |= dev_alloc(e, &e->alpha_tab, cfg->num_slices);
     if (!rc) rc |= dev_alloc(e, &e->tabT, e->N + 2);
     if (!rc) rc |= dev_alloc(e, &e->tabT2, e->N + 2);
     if (!rc) rc |= dev_alloc(e, &e->tabt, e->N + 2);
@@ -700,6 +742,7 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     }
     if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
     k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
+    k_alpha_table<<<4, 256, 0, st>>>(e->cfg.num_slices, e->alpha_tab);
     // N prior draws (replicated on every rank), packed, ranked (stable argsort) and scattered
     double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
     long long *tmpN = e->live[1].nevals;
@@ -714,12 +757,38 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     // create_init_termination_register + the loop-entry no_seed_points and first cond
     *e->reg_host = init_register_host();
     NSB_CUDA(cudaMemcpyAsync(e->reg, e->reg_host, sizeof(NsRegister), cudaMemcpyHostToDevice, st));
-    k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N);
+    k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
+                                         e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N, e->epi);
     NSB_LAUNCH_CHECK();
     e->all_launches += 9;
     e->initialised = true;
     return 0;
+}
+
+// NSB200_TRACE=1: device timeline of a few iterations (debug aid for DESIGN.md numbers)
+struct TraceMark { cudaEvent_t ev; const char *name; };
+static std::vector<TraceMark> g_trace;
+static bool trace_on(NsEngine *e) {
+    static int on = -1;
+    if (on < 0) on = getenv("NSB200_TRACE") ? 1 : 0;
+    return on && e->slice_launches >= 60 && e->slice_launches < 64;
+}
+static void trace_mark(NsEngine *e, const char *name, cudaStream_t s) {
+    if (!trace_on(e)) return;
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    cudaEventRecord(ev, s);
+    g_trace.push_back({ev, name});
+}
+static void trace_dump() {
+    if (g_trace.empty()) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 1; i < g_trace.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_trace[0].ev, g_trace[i].ev);
+        fprintf(stderr, "trace %8.1f us  %s\n", ms * 1e3, g_trace[i].name);
+    }
+    g_trace.clear();
 }
 
 static cudaEvent_t next_event(NsEngine *e) {
@@ -764,20 +833,8 @@ static int enqueue_streams(NsEngine *e, int buf) {
     k_chain_streams<<<(int) ctas, 128, 0, e->side>>>(sa);
     NSB_LAUNCH_CHECK();
     NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
+    trace_mark(e, "  generator end (side)", e->side);
     e->all_launches += 1;
-    if (getenv("NSB200_DEBUG_OVERLAP")) {
-        static cudaEvent_t dbg = nullptr;
-        if (!dbg) cudaEventCreate(&dbg);
-        cudaEventRecord(dbg, e->side);
-        cudaEventSynchronize(dbg);
-        if (e->ev_used >= 2) {
-            cudaEventSynchronize(e->ev_pool[e->ev_used - 1]);
-            float a = 0, b = 0;
-            cudaEventElapsedTime(&a, e->ev_pool[e->ev_used - 2], dbg);                      // slice start -> generator end
-            cudaEventElapsedTime(&b, e->ev_pool[e->ev_used - 2], e->ev_pool[e->ev_used - 1]);  // slice start -> slice end
-            fprintf(stderr, "overlap dbg: generator done %.3f ms after slice start; slice took %.3f ms\n", a, b);
-        }
-    }
     return 0;
 }
 
@@ -787,8 +844,10 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     const int D = e->D;
     // streams of THIS body were enqueued by the previous step (or by init) on the side stream; they
     // read ctl->next_sample_key, which the prologue below overwrites: wait for them first
+    trace_mark(e, "step_begin enqueue", st);
     if (e->pre_dirs[0]) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->pre_cur], 0));
-    k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender);
+    trace_mark(e, "after wait streams", st);
+    k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
     // this rank's chains -> its block of the gather buffer
@@ -808,6 +867,7 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.ctl = e->ctl;
     a.live0 = e->live[0];
     a.live1 = e->live[1];
+    a.alpha_tab = e->alpha_tab;
     const int buf = e->pre_cur;
     a.pre_dirs = e->pre_dirs[buf];
     a.pre_us = e->pre_us[buf];
@@ -815,8 +875,10 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     if (e->pre_dirs[0]) NSB_CUDA(cudaEventRecord(e->ev_keys, st));  // next_sample_key is valid from here on
     cudaEvent_t e0 = next_event(e), e1 = next_event(e);
     cudaEventRecord(e0, st);
+    trace_mark(e, "slice start", st);
     if (launch_slice(a, st)) return 1;
     cudaEventRecord(e1, st);
+    trace_mark(e, "slice end", st);
     NSB_LAUNCH_CHECK();
     if (e->pre_dirs[0]) {
         // streams of the NEXT body, enqueued AFTER the slice kernel so that its CTAs are placed first and
@@ -837,9 +899,11 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
                                                        e->m, e->N, e->rank);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
-    k_iter_epilogue<<<1, 1024, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N);
+    k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
+                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi);
     NSB_LAUNCH_CHECK();
+    trace_mark(e, "epilogue end", st);
+    if (e->slice_launches == 64) trace_dump();
     e->all_launches += 3;
     return 0;
 }
@@ -989,3 +1053,14 @@ extern "C" int nsb200_bench_fp64_fma(int64_t iters, double *out_tflops) {
     *out_tflops = best;
     return 0;
 }
+
+#ifdef NSB_PROFILE
+extern "C" int nsb200_debug_profile(unsigned long long *out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, nsb::g_prof, 16 * 8);
+    if (reset) {
+        unsigned long long z[16] = {0};
+        cudaMemcpyToSymbol(nsb::g_prof, z, 16 * 8);
+    }
+    return 0;
+}
+#endif

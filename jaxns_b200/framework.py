@@ -159,17 +159,19 @@ class Model:
         return random.uniform(random.split(key, 2)[1], self._D)
 
     def log_prob_prior(self, U):
-        """Prior log density of the transformed point (framework/model.py:178-187); host-side helper
-        used only for NestedSamplerResults.log_posterior_density."""
+        """Prior log density of the transformed point (framework/model.py:178-187), evaluated on the device
+        (post-processing for NestedSamplerResults.log_posterior_density; small torch reductions)."""
+        import math
         X = self._forward_batch(U, True)[1]
-        Xh = X.detach().cpu().numpy()
-        out = np.zeros(Xh.shape[:-1])
-        o = 0
-        for p in self._priors:
-            n = p.dist.event_size()
-            out = out + p.dist.log_prob(Xh[..., o:o + n])
-            o += n
-        return torch.from_numpy(np.asarray(out)).cuda()
+        a = self._dev[0]
+        b = self._dev[1]
+        if self._prior_kind == distributions.Uniform.prior_kind:
+            inside = (X >= a) & (X <= a + b)
+            lp = torch.where(inside, -torch.log(b).expand_as(X), torch.full_like(X, -math.inf))
+        else:
+            z = (X - a) / b
+            lp = -0.5 * z * z - torch.log(b) - 0.5 * math.log(2.0 * math.pi)
+        return lp.sum(dim=-1)
 
     def sanity_check(self, key, S: int):
         from jaxns_b200 import random

@@ -32,9 +32,12 @@ def compute_evidence_stats(log_L: torch.Tensor, num_live_points: torch.Tensor, n
     cinit = _lib.NsEvidenceCalc(*[float(v) for v in init])
     out_final = torch.empty(8, dtype=torch.float64, device="cuda")
     per = torch.empty((8, M), dtype=torch.float64, device="cuda") if per_sample else None
-    _lib.check(_lib.lib().nsb200_evidence_stats(ctypes.byref(cinit), _lib.ptr(log_L), _lib.ptr(n), ctypes.c_int64(M),
-                                                 _lib.ptr(out_final), _lib.ptr(per), ctypes.c_void_p(0),
-                                                 ctypes.c_int64(0), _lib.stream_arg()))
+    L = _lib.lib()
+    ws_bytes = L.nsb200_workspace_bytes(_lib.WS_EVIDENCE_STATS, M)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    _lib.check(L.nsb200_evidence_stats(ctypes.byref(cinit), _lib.ptr(log_L), _lib.ptr(n), ctypes.c_int64(M),
+                                       _lib.ptr(out_final), _lib.ptr(per), _lib.ptr(ws), ctypes.c_int64(ws_bytes),
+                                       _lib.stream_arg()))
     final = EvidenceCalculation(*out_final.cpu().tolist())
     if not per_sample:
         return final, None
