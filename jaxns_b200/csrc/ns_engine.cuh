@@ -41,9 +41,13 @@ __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSe
     ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
     k = split_child(k, 0);
     ctl->key = split_child(k, 0);          // :510  key, ephemeral_key = split(state.key)
-    // the key chain does not depend on the data: the next body's sample_key is known already, so its
-    // chain streams can be generated concurrently with this body's slice kernel
-    ctl->next_sample_key = split_child(split_child(ctl->key, 0), 1);
+    // the key chain does not depend on the data: the sample_key of the body after next is known already,
+    // so its chain streams can be generated two bodies ahead, in the gaps this body leaves on the GPU
+    {
+        const Key k2 = split_child(split_child(split_child(ctl->key, 0), 0), 0);  // state key of body + 2
+        ctl->stream_key[(ctl->body + 2) % 3] = split_child(split_child(k2, 0), 1);
+        ctl->body += 1;
+    }
     ctl->contour = live.logL[m - 1];
     ctl->disc_start = clampll(ctl->next_idx, 0, capacity - m);
     ctl->next_idx = (ctl->next_idx + m) % capacity;
@@ -239,7 +243,8 @@ __device__ inline void determine_termination(const NsTermCond &tc, NsRegister &r
 __global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
 k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet live1, const double *packed,
                 long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
-                const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi) {
+                const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi,
+                volatile long long *progress) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ double sh[3][34];
@@ -252,6 +257,12 @@ k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet
             const LiveSet &live = ctl->cur ? live1 : live0;
             reg->no_seed_points = live.logL[m - 1] >= live.logL[N - 1];
             determine_termination(tc, *reg);
+            if (progress) {
+                progress[1] = reg->done;
+                __threadfence_system();
+                progress[0] = 0;
+                __threadfence_system();
+            }
         }
         return;
     }
@@ -318,6 +329,14 @@ k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet
         determine_termination(tc, r);
         *reg = r;
         ctl->cur ^= 1;
+        if (progress) {
+            // host-mapped pinned words: the host keeps a few bodies in flight and polls these instead of
+            // synchronising the stream (progress[0] = bodies completed, progress[1] = done flag)
+            progress[1] = r.done;
+            __threadfence_system();
+            progress[0] = r.iteration;
+            __threadfence_system();
+        }
     }
 }
 

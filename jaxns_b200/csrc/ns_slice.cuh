@@ -102,26 +102,41 @@ __device__ __forceinline__ void sample_direction(const Grp<G> &g, int D, Key key
     for (int s = 0; s < DPL; ++s) d[s] = d[s] / nrm;
 }
 
+// Exact min over the lanes in `mask` of NON-NEGATIVE doubles (+inf allowed): for such values the IEEE
+// bit pattern orders like an unsigned integer, so two REDUX.MIN instructions (high word, then low
+// word among the lanes that hold the winning high word) replace a 5-step 64-bit shuffle butterfly.
+__device__ __forceinline__ double group_min_nonneg(unsigned mask, double v) {
+    const unsigned hi = (unsigned) __double2hiint(v), lo = (unsigned) __double2loint(v);
+    const unsigned mhi = __reduce_min_sync(mask, hi);
+    const unsigned mlo = __reduce_min_sync(mask, hi == mhi ? lo : 0xFFFFFFFFu);
+    return __hiloint2double((int) mhi, (int) mlo);
+}
+
 // _slice_bounds: intersection of the line U0 + t d with the unit cube.
 template <int G, int DPL>
 __device__ __forceinline__ void slice_bounds(const Grp<G> &g, int D, const double (&U0)[DPL], const double (&d)[DPL],
                                              double &left, double &right) {
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
-    double r = kInf, l = -kInf;
+    double r = kInf, nl = kInf;  // right bound and MINUS the left bound, both >= 0
 #pragma unroll
     for (int s = 0; s < DPL; ++s) {
         const int j = s * G + g.lane;
         if (j < D) {
-            const double t1 = (1.0 - U0[s]) / d[s];
-            const double t0 = -U0[s] / d[s];
+            const double t1 = fast_div(1.0 - U0[s], d[s]);
+            const double t0 = fast_div(-U0[s], d[s]);
             if (t1 >= 0.0) r = fmin(r, t1);
-            if (t1 <= 0.0) l = fmax(l, t1);
+            if (t1 <= 0.0) nl = fmin(nl, -t1);
             if (t0 >= 0.0) r = fmin(r, t0);
-            if (t0 <= 0.0) l = fmax(l, t0);
+            if (t0 <= 0.0) nl = fmin(nl, -t0);
         }
     }
-    right = group_min(g, r);
-    left = group_max(g, l);
+    if (G > 1) {
+        // -0.0 would order above every positive number as an integer: canonicalise the zeros
+        r = group_min_nonneg(g.m(), r + 0.0);
+        nl = group_min_nonneg(g.m(), nl + 0.0);
+    }
+    right = r;
+    left = -nl;
 }
 
 // Seed choice: first index with log_L > contour, then lower_bound in the logaddexp table.
@@ -301,6 +316,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
             NSB_TICK(2)  // bounds
             int ne = 0;  // proposals generated so far in this slice
             double logL_acc = 0.0;
+            double u_ahead = uq[0];
             if (TEAM) {
                 for (;;) {
                     double ts[W];
@@ -362,7 +378,9 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                 for (int p = 0; p < P; ++p) {
                     double uu;
                     const int n = ne + p;
-                    if (n < kPre) {
+                    if (P == 1 && n < kPre) {
+                        uu = u_ahead;  // loaded while the previous proposal was being evaluated
+                    } else if (n < kPre) {
                         uu = uq[n];
                     } else {
                         const Key t_key = split_child(run_key, 1);
@@ -376,6 +394,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 #pragma unroll
                     for (int s = 0; s < DPL; ++s) x[p][s] = fma(t, d[s], U0[s]);
                 }
+                if (P == 1) u_ahead = uq[min(ne + 1, kPre - 1)];  // next proposal's uniform: hide the smem latency
                 NSB_TICK(3)  // proposal generation
 #ifdef NSB_PROFILE
                 {
@@ -494,7 +513,8 @@ __global__ void k_alpha_table(int S, double *out) {
 // path.  Layouts match what the slice kernel reads: dirs [n][S][D], us [n][S][kPre], rkeys [n][S].
 struct StreamArgs {
     Key key;
-    const DevCtl *ctl;  // engine mode: key = ctl->next_sample_key (streams of the FOLLOWING body)
+    const DevCtl *ctl;  // engine mode: key = ctl->stream_key[key_slot]
+    int key_slot;
     long long chain_begin, chain_end;
     int S, D;
     double *dirs;
@@ -502,9 +522,9 @@ struct StreamArgs {
     uint2 *rkeys;
 };
 
-__global__ void __launch_bounds__(128) k_chain_streams(StreamArgs a) {
+__global__ void __launch_bounds__(1024) k_chain_streams(StreamArgs a) {
     Key base_key = a.key;
-    if (a.ctl) base_key = a.ctl->next_sample_key;
+    if (a.ctl) base_key = a.ctl->stream_key[a.key_slot];
     const int lane = threadIdx.x & 31;
     const int S = a.S, D = a.D;
     const int n_chunks = (S + 31) / 32;

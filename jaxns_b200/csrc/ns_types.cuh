@@ -12,7 +12,8 @@ struct DevCtl {
     long long iteration;
     // derived per iteration by k_iter_prologue
     Key sample_key;
-    Key next_sample_key;   // sample_key of the following iteration (data-independent key chain)
+    Key stream_key[3];     // sample_key of the bodies whose chain streams live in buffers 0..2 (key chain is data-independent)
+    long long body;        // index of the next body to run
     double contour;
     long long disc_start;  // clamped write offset of the discarded shell
     long long ph_start;    // clamped write offset of the phantom rows

@@ -301,7 +301,8 @@ static int pick_team(const SliceArgs &a, const Geometry &g) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     const long long n = a.chain_end - a.chain_begin;
-    int W = (n * 2 <= (long long) sms * 24) ? 2 : 1;
+    int W = 1;  // measured slower on B200 so far (register spills at 2 warps x 1600 chains): opt-in only
+    (void) n;
     if (const char *e = getenv("NSB200_TEAM")) {
         const int v = atoi(e);
         if (v == 1 || v == 2) W = v;
@@ -517,7 +518,13 @@ __global__ void k_fill_f64(double *p, long long n, double v) {
 __global__ void k_init_ctl(DevCtl *ctl, Key key) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->key = key;
-    ctl->next_sample_key = split_child(split_child(key, 0), 1);  // sample_key of the first body
+    ctl->body = 0;
+    ctl->stream_key[0] = split_child(split_child(key, 0), 1);  // sample_key of body 0
+    {
+        const Key k1 = split_child(split_child(split_child(key, 0), 0), 0);  // state key of body 1
+        ctl->stream_key[1] = split_child(split_child(k1, 0), 1);
+    }
+    ctl->stream_key[2] = Key{0, 0};
     ctl->next_idx = 0;
     ctl->num_samples = 0;
     ctl->iteration = 0;
@@ -560,21 +567,22 @@ struct NsEngine {
     NsRegister *reg = nullptr;       // device
     NsRegister *reg_host = nullptr;  // pinned
     DevCtl *ctl_host = nullptr;      // pinned
+    volatile long long *progress = nullptr;  // pinned + mapped: [0] bodies completed, [1] done
+    long long *progress_dev = nullptr;
     double *seed_table = nullptr;
     double *packed = nullptr;
     unsigned *rank = nullptr;
-    // chain streams of this rank's chains (k_chain_streams), double buffered: the streams of body i+1
-    // are generated on `side` while the slice kernel of body i runs on the caller's stream
-    double *pre_dirs[2] = {nullptr, nullptr};
-    double *pre_us[2] = {nullptr, nullptr};
-    uint2 *pre_rkeys[2] = {nullptr, nullptr};
+    // chain streams of this rank's chains (k_chain_streams), triple buffered: the streams of body i+2
+    // are generated on `side` in the gap between the slice kernels of bodies i and i+1
+    double *pre_dirs[3] = {nullptr, nullptr, nullptr};
+    double *pre_us[3] = {nullptr, nullptr, nullptr};
+    uint2 *pre_rkeys[3] = {nullptr, nullptr, nullptr};
     double *tabT = nullptr, *tabT2 = nullptr, *tabt = nullptr;  // n-dependent evidence terms, n <= N
     EpiScratch *epi = nullptr;
     double *alpha_tab = nullptr;
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_keys = nullptr, ev_streams[2] = {nullptr, nullptr};
-    int pre_cur = 0;          // buffer holding the streams of the NEXT body to run
-    bool pre_ready = false;   // streams of the next body have been enqueued
+    cudaEvent_t ev_keys = nullptr, ev_streams[3] = {nullptr, nullptr, nullptr};
+    long long body = 0;       // host mirror of the next body index (its streams live in buffer body % 3)
     NsTermCond tc;
     std::vector<void *> allocs;
     // profiling
@@ -600,9 +608,10 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
     for (void *p : e->allocs) cudaFree(p);
     if (e->reg_host) cudaFreeHost(e->reg_host);
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
+    if (e->progress) cudaFreeHost((void *) e->progress);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->ev_keys) cudaEventDestroy(e->ev_keys);
-    for (int b = 0; b < 2; ++b)
+    for (int b = 0; b < 3; ++b)
         if (e->ev_streams[b]) cudaEventDestroy(e->ev_streams[b]);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
@@ -662,18 +671,28 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->tabt, e->N + 2);
     if (g.G >= 8) {  // data-independent chain streams are generated off the chains' critical path
         const size_t rows = (size_t) e->rows_per_rank * cfg->num_slices;
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 3; ++b) {
             if (!rc) rc |= dev_alloc(e, &e->pre_dirs[b], rows * D);
             if (!rc) rc |= dev_alloc(e, &e->pre_us[b], rows * kPre);
             if (!rc) rc |= dev_alloc(e, &e->pre_rkeys[b], rows);
         }
         if (!rc && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate failed");
         if (!rc && cudaEventCreateWithFlags(&e->ev_keys, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
-        for (int b = 0; b < 2; ++b)
+        for (int b = 0; b < 3; ++b)
             if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     }
     if (!rc && cudaMallocHost((void **) &e->reg_host, sizeof(NsRegister)) != cudaSuccess) rc = fail("cudaMallocHost failed");
     if (!rc && cudaMallocHost((void **) &e->ctl_host, sizeof(DevCtl)) != cudaSuccess) rc = fail("cudaMallocHost failed");
+    if (!rc) {
+        void *hp = nullptr;
+        if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) != cudaSuccess) rc = fail("cudaHostAlloc(mapped) failed");
+        else {
+            e->progress = (volatile long long *) hp;
+            e->progress[0] = -1;
+            e->progress[1] = 0;
+            if (cudaHostGetDevicePointer((void **) &e->progress_dev, hp, 0) != cudaSuccess) rc = fail("cudaHostGetDevicePointer failed");
+        }
+    }
     if (rc) {
         nsb200_engine_destroy(e);
         return 1;
@@ -720,6 +739,8 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
     e->tc = effective_term_cond(e, term_cond);
+    e->progress[0] = -1;
+    e->progress[1] = 0;
     e->slice_ms = 0.0;
     e->slice_launches = 0;
     e->all_launches = 0;
@@ -737,8 +758,9 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
         // the side stream may still be writing streams from a previous run into these buffers
         NSB_CUDA(cudaStreamSynchronize(e->side));
         NSB_CUDA(cudaEventRecord(e->ev_keys, st));
-        e->pre_cur = 0;
-        if (enqueue_streams(e, 0)) return 1;
+        e->body = 0;
+        if (enqueue_streams(e, 0)) return 1;  // bodies 0 and 1; body b + 2 follows the slice kernel of body b
+        if (enqueue_streams(e, 1)) return 1;
     }
     if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
     k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
@@ -758,7 +780,7 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     *e->reg_host = init_register_host();
     NSB_CUDA(cudaMemcpyAsync(e->reg, e->reg_host, sizeof(NsRegister), cudaMemcpyHostToDevice, st));
     k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N, e->epi);
+                                         e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     NSB_LAUNCH_CHECK();
     e->all_launches += 9;
     e->initialised = true;
@@ -810,13 +832,14 @@ static void drain_events(NsEngine *e) {
 }
 
 // Enqueues, on the engine's side stream, the generation of the chain streams of the body whose
-// sample_key is ctl->next_sample_key (valid once ev_keys has fired) into buffer `buf`.
+// sample_key is ctl->stream_key[buf] (valid once ev_keys has fired) into buffer `buf`.
 static int enqueue_streams(NsEngine *e, int buf) {
     NSB_CUDA(cudaStreamWaitEvent(e->side, e->ev_keys, 0));
     const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
     StreamArgs sa;
     sa.key = Key{0, 0};
     sa.ctl = e->ctl;
+    sa.key_slot = buf;
     sa.chain_begin = begin;
     sa.chain_end = end;
     sa.S = e->cfg.num_slices;
@@ -825,12 +848,21 @@ static int enqueue_streams(NsEngine *e, int buf) {
     sa.us = e->pre_us[buf];
     sa.rkeys = e->pre_rkeys[buf];
     const long long warps = (end - begin) * ((sa.S + 31) / 32);
-    int sms = 148, per_sm = 2;
+    // The generator is throughput-bound, the chains are latency-bound: sharing an SM starves the chains.
+    // So the generator gets its own SMs: a few persistent CTAs of 1024 threads that each claim (almost) all
+    // shared memory of an SM, launched just before the slice kernel, whose CTAs then cannot land there.
+    int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    if (const char *pe = getenv("NSB200_GEN_CTAS_PER_SM")) per_sm = atoi(pe) > 0 ? atoi(pe) : per_sm;
-    long long ctas = (long long) sms * per_sm;
-    if (ctas * 4 > warps) ctas = (warps + 3) / 4;
-    k_chain_streams<<<(int) ctas, 128, 0, e->side>>>(sa);
+    int gen_sms = (sms * 43) / 100;  // measured optimum on B200 at config 2 (64 of 148): see DESIGN.md
+    if (const char *pe = getenv("NSB200_GEN_SMS")) gen_sms = atoi(pe) > 0 ? atoi(pe) : gen_sms;
+    if ((long long) gen_sms * 32 > warps) gen_sms = (int) ((warps + 31) / 32);
+    static bool attr_set = false;
+    const size_t gen_smem = 200 * 1024;
+    if (!attr_set) {
+        NSB_CUDA(cudaFuncSetAttribute(k_chain_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gen_smem));
+        attr_set = true;
+    }
+    k_chain_streams<<<gen_sms, 1024, gen_smem, e->side>>>(sa);
     NSB_LAUNCH_CHECK();
     NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
     trace_mark(e, "  generator end (side)", e->side);
@@ -842,10 +874,9 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
-    // streams of THIS body were enqueued by the previous step (or by init) on the side stream; they
-    // read ctl->next_sample_key, which the prologue below overwrites: wait for them first
+    // streams of THIS body were enqueued two steps ago (or by init) on the side stream
     trace_mark(e, "step_begin enqueue", st);
-    if (e->pre_dirs[0]) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->pre_cur], 0));
+    if (e->pre_dirs[0]) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->body % 3], 0));
     trace_mark(e, "after wait streams", st);
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
@@ -868,11 +899,15 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.live0 = e->live[0];
     a.live1 = e->live[1];
     a.alpha_tab = e->alpha_tab;
-    const int buf = e->pre_cur;
+    const int buf = (int) (e->body % 3);
     a.pre_dirs = e->pre_dirs[buf];
     a.pre_us = e->pre_us[buf];
     a.pre_rkeys = e->pre_rkeys[buf];
-    if (e->pre_dirs[0]) NSB_CUDA(cudaEventRecord(e->ev_keys, st));  // next_sample_key is valid from here on
+    if (e->pre_dirs[0]) {
+        // streams of body + 2: generated on dedicated SMs while this body's chains run on the others
+        NSB_CUDA(cudaEventRecord(e->ev_keys, st));
+        if (enqueue_streams(e, (int) ((e->body + 2) % 3))) return 1;
+    }
     cudaEvent_t e0 = next_event(e), e1 = next_event(e);
     cudaEventRecord(e0, st);
     trace_mark(e, "slice start", st);
@@ -880,12 +915,7 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     cudaEventRecord(e1, st);
     trace_mark(e, "slice end", st);
     NSB_LAUNCH_CHECK();
-    if (e->pre_dirs[0]) {
-        // streams of the NEXT body, enqueued AFTER the slice kernel so that its CTAs are placed first and
-        // the throughput-bound generator fills the issue slots the latency-bound chains leave idle
-        if (enqueue_streams(e, buf ^ 1)) return 1;
-        e->pre_cur = buf ^ 1;
-    }
+    e->body += 1;
     e->slice_launches += 1;
     e->all_launches += 3;
     return 0;
@@ -900,7 +930,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
     k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi);
+                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     NSB_LAUNCH_CHECK();
     trace_mark(e, "epilogue end", st);
     if (e->slice_launches == 64) trace_dump();
@@ -948,23 +978,26 @@ extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTer
     if (!e) return fail("NULL engine");
     if (e->cfg.world_size != 1) return fail("engine_run requires world_size == 1");
     if (nsb200_engine_init(e, key, term_cond, stream)) return 1;
-    NsRegister r;
-    if (nsb200_engine_register(e, &r, stream)) return 1;
-    // Steps are no-ops on the device once the register says done, so the host may run ahead: it
-    // enqueues a few bodies between polls instead of synchronising after each one.
-    const int lookahead = 4;
+    // Steps are no-ops on the device once the register says done, so the host runs ahead: it keeps
+    // `depth` bodies in flight and polls two host-mapped words the epilogue writes, never the stream.
+    long long depth = 4;
+    if (const char *de = getenv("NSB200_DEPTH")) depth = atoll(de) > 0 ? atoll(de) : depth;
     long long launched = 0;
-    while (!r.done && (max_iterations < 0 || launched < max_iterations)) {
-        long long burst = lookahead;
-        if (max_iterations >= 0 && launched + burst > max_iterations) burst = max_iterations - launched;
-        for (long long b = 0; b < burst; ++b) {
+    for (;;) {
+        const long long completed = e->progress[0];
+        if (completed >= 0 && e->progress[1]) break;                                 // loop condition false
+        if (max_iterations >= 0 && launched >= max_iterations) {
+            if (completed >= launched) break;
+        } else if (completed >= 0 ? (launched - completed < depth) : (launched < 1)) {
             if (nsb200_engine_step(e, stream)) return 1;
+            ++launched;
+            continue;
         }
-        launched += burst;
-        if (nsb200_engine_register(e, &r, stream)) return 1;
+        if (cudaStreamQuery((cudaStream_t) stream) == cudaErrorLaunchFailure) return fail("kernel failed during the run");
     }
+    NsRegister r;
     if (nsb200_engine_finalize(e, stream)) return 1;
-    NSB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    if (nsb200_engine_register(e, &r, stream)) return 1;  // synchronises the stream
     if (out_register) *out_register = r;
     return 0;
 }
