@@ -279,13 +279,13 @@ def run_native(args):
     pinned = {"log_L": torch.empty(cap, dtype=torch.float64).pin_memory(),
               "log_dp": torch.empty(cap, dtype=torch.float64).pin_memory(),
               "x": torch.empty((cap, D), dtype=torch.float64).pin_memory()}
-    for s in range(n_e2e):
+    for s in range(-1, n_e2e):  # s = -1: untimed warm-up of the public-API path (lazy CUDA module loads, allocator)
         flush.fill_(0.5)
         barrier()
         t0 = time.perf_counter()
         m2 = make_model()  # host numpy -> device copies happen inside (Model.desc)
         ns2 = j.NestedSampler(model=m2, num_live_points=num_live)
-        reason, state = ns2(random.PRNGKey(s))
+        reason, state = ns2(random.PRNGKey(max(s, 0)))
         res = ns2.to_results(reason, state)
         nres = res.total_num_samples  # posterior samples + weights into the user's pinned host buffers
         host = {"log_L": pinned["log_L"][:nres], "log_dp": pinned["log_dp"][:nres], "x": pinned["x"][:nres]}
@@ -294,8 +294,9 @@ def run_native(args):
         host["x"].copy_(res.samples["x"], non_blocking=True)
         host["logZ"] = res.log_Z_mean
         torch.cuda.synchronize()
-        e2e_t += time.perf_counter() - t0
-        e2e_evals += res.total_num_likelihood_evaluations
+        if s >= 0:
+            e2e_t += time.perf_counter() - t0
+            e2e_evals += res.total_num_likelihood_evaluations
         fam, D_, pk, K, a, b, params = m2.host_arrays()
         h2d = int(a.nbytes + b.nbytes + params.nbytes + 8)
         d2h = int(sum(v.numel() * v.element_size() for v in host.values() if hasattr(v, "numel")) + 8 * 8)

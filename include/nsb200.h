@@ -258,6 +258,10 @@ int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTermCond *term
                       int64_t max_iterations, NsRegister *out_register, nsb200_stream_t stream);
 /* Final live-set append (sharded_static.py:834-838). */
 int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream);
+/* Non-blocking progress of the enqueued bodies: *completed = bodies whose register update has run on the
+ * device (-1 before the init pass finished), *done = loop condition false.  Lets a host-driven loop keep a
+ * few bodies in flight without synchronising the stream. */
+int nsb200_engine_progress(NsEngine *e, int64_t *completed, int32_t *done);
 /* Blocks on `stream`, then copies the register / fills the view. */
 int nsb200_engine_register(NsEngine *e, NsRegister *out, nsb200_stream_t stream);
 int nsb200_engine_state(NsEngine *e, NsStateView *out, nsb200_stream_t stream);

@@ -84,7 +84,7 @@ EXPORTS = (
     "nsb200_logsumexp", "nsb200_engine_create", "nsb200_engine_destroy", "nsb200_engine_init",
     "nsb200_engine_step", "nsb200_engine_step_begin", "nsb200_engine_step_end", "nsb200_engine_gather_buffer",
     "nsb200_engine_run", "nsb200_engine_finalize", "nsb200_engine_register", "nsb200_engine_state",
-    "nsb200_engine_slice_profile", "nsb200_bench_fp64_fma",
+    "nsb200_engine_slice_profile", "nsb200_bench_fp64_fma", "nsb200_engine_progress",
 )
 
 

@@ -963,6 +963,15 @@ extern "C" int nsb200_engine_register(NsEngine *e, NsRegister *out, nsb200_strea
     return 0;
 }
 
+extern "C" int nsb200_engine_progress(NsEngine *e, int64_t *completed, int32_t *done) {
+    if (!e) return fail("NULL engine");
+    const long long c = e->progress[0];
+    const long long d = e->progress[1];
+    if (completed) *completed = c;
+    if (done) *done = (c >= 0 && d) ? 1 : 0;
+    return 0;
+}
+
 extern "C" int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;

@@ -187,25 +187,36 @@ class ShardedStaticNestedSampler:
                                            ctypes.byref(reg), stream))
         else:
             _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
-            _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
             gather = self._gather_tensor(eng) if world > 1 else None
             host_tc = self._effective_host_cond(term_cond) if not plain else None
-            lookahead = 4 if plain else 1
-            while True:
-                if plain:
-                    done = bool(reg.done)
-                else:
-                    done = termination.determine_termination(host_tc, termination.register_from_c(reg))[0] or bool(reg.done)
-                if done:
-                    break
-                for _ in range(lookahead):
-                    _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
-                    if world > 1:
-                        import torch.distributed as dist
-                        rows = gather.shape[0] // world
-                        dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
-                    _lib.check(L.nsb200_engine_step_end(eng.h, stream))
+
+            def one_body():
+                _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
+                if world > 1:
+                    import torch.distributed as dist
+                    rows = gather.shape[0] // world
+                    dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+                _lib.check(L.nsb200_engine_step_end(eng.h, stream))
+
+            if plain:
+                # Bodies are no-ops on the device once the register says done, so they are enqueued in bursts
+                # between blocking reads of the register.  The register is replicated and deterministic, so every
+                # rank sees `done` after the same burst and the all-gathers stay matched across ranks (an
+                # asynchronous poll would let ranks launch different numbers of collectives).
+                burst = 4
                 _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                while not reg.done:
+                    for _ in range(burst):
+                        one_body()
+                    _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+            else:
+                _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                while True:
+                    done_now = termination.determine_termination(host_tc, termination.register_from_c(reg))[0] or bool(reg.done)
+                    if done_now:
+                        break
+                    one_body()
+                    _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
             _lib.check(L.nsb200_engine_finalize(eng.h, stream))
         register = termination.register_from_c(reg)
         if plain:
