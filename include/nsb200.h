@@ -34,7 +34,9 @@ enum {
     NSB200_FAM_GAUSS_MIX_DIAG = 1, /* K x [logc, mean[D], inv_sigma[D]], combined with logaddexp       */
     NSB200_FAM_EGGBOX = 2,         /* (2 + prod_j cos(x_j / 2))^5, no params                           */
     NSB200_FAM_ROSENBROCK = 3,     /* -sum_i 100 (x_{i+1} - x_i^2)^2 + (1 - x_i)^2, no params          */
-    NSB200_FAM_SHELLS = 4          /* K x [w, r, c[D]] Gaussian shells combined with logaddexp         */
+    NSB200_FAM_SHELLS = 4,         /* K x [w, r, c[D]] Gaussian shells combined with logaddexp         */
+    NSB200_FAM_EXTERNAL = 5        /* likelihood evaluated by the caller on the device between the
+                                      propose / accept kernels (nsb200_split_*); no params          */
 };
 
 /* ---- prior quantile transforms U in [0,1]^D -> X (framework/wrapped_tfp_distribution.py:77-84) */
@@ -197,6 +199,40 @@ int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams *p, const u
                        const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
                        double *ph_U, double *ph_logL, nsb200_stream_t stream);
 
+/* ---- B1 for likelihoods the library cannot fuse: the slice step split around a caller-evaluated
+ * batched likelihood (BASELINE north_star).  Same chains as nsb200_slice_batch
+ * (samplers/bases.py:63-75, samplers/uni_slice_sampler.py:114-273,343-441) when the likelihood
+ * values agree.  Protocol, all on one stream, n = chain_end - chain_begin:
+ *     nsb200_split_begin(...)            -> prop_U / prop_X [n,D]: first proposal of every chain
+ *     repeat:  prop_logL[n] = vmap(log_likelihood)(prop_X)        (caller; XLA / torch on the device)
+ *              nsb200_split_accept(...)  -> accept or shrink (NaN -> -inf, framework/ops.py:323-325),
+ *                                           next proposal, *n_active += chains still running
+ *     until n_active == 0, then nsb200_split_finish(...) -> the Sample / phantom arrays.
+ * `model` supplies the prior transform only (family is ignored, NSB200_FAM_EXTERNAL allowed).
+ * Finished chains keep their final point in prop_U (their prop_logL is ignored), so shapes are
+ * static.  `workspace` holds the chain state between calls. */
+int64_t nsb200_split_workspace_bytes(int32_t D, int64_t n_chains, int32_t num_phantom);
+int nsb200_split_begin(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                       const double *contour, const double *live_U, const double *live_logL,
+                       const double *seed_table, void *workspace, int64_t workspace_bytes, double *prop_U,
+                       double *prop_X, nsb200_stream_t stream);
+/* n_active: DEVICE counter (uint64) incremented by every chain that still needs evaluations, or NULL. */
+int nsb200_split_accept(const NsModelDesc *model, const NsSliceParams *p, const double *contour,
+                        const double *prop_logL, void *workspace, int64_t workspace_bytes, double *prop_U,
+                        double *prop_X, uint64_t *n_active, nsb200_stream_t stream);
+int nsb200_split_finish(const NsModelDesc *model, const NsSliceParams *p, void *workspace,
+                        int64_t workspace_bytes, double *out_U, double *out_logL, int64_t *out_nevals,
+                        double *ph_U, double *ph_logL, nsb200_stream_t stream);
+/* Redraw round `round` (0 = first draw) of _single_uniform_sample (common/uniform_sample.py:12-60) for
+ * prior draws [begin, end) of split(sample_key, N); rows with need[i - begin] == 0 are left untouched
+ * (need == NULL: all rows).  out_U / out_X [end - begin, D] (out_X optional). */
+int nsb200_init_propose(const NsModelDesc *model, const uint32_t sample_key[2], int64_t N, int64_t begin,
+                        int64_t end, int32_t round, const uint8_t *need, double *out_U, double *out_X,
+                        nsb200_stream_t stream);
+/* vmap(Model.transform)(U) alone (framework/model.py:155-159): U [n,D] -> X [n,D]. */
+int nsb200_transform_batch(const NsModelDesc *model, const double *U, int64_t n, double *out_X,
+                           nsb200_stream_t stream);
+
 /* get_samples with UniformSampler (samplers/uniform_samplers.py:42-85, max_likelihood_evals=100). */
 int nsb200_uniform_batch(const NsModelDesc *model, const uint32_t key[2], const double *contour,
                          int64_t num_samples, int64_t chain_begin, int64_t chain_end, double *out_U,
@@ -256,6 +292,19 @@ int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *rows_per_ran
  * then appends the final live set (sharded_static.py:834-838).  Synchronises `stream`. */
 int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
                       int64_t max_iterations, NsRegister *out_register, nsb200_stream_t stream);
+/* Engine with model.family == NSB200_FAM_EXTERNAL: the caller evaluates every likelihood.
+ *   init:  U/logL/nevals [N] = the initial live points (nsb200_init_propose rounds + caller's likelihood),
+ *          every rank passes the same N rows (create_init_state, common/initialisation.py:20-84);
+ *   body:  nsb200_engine_step_begin (discard + append only), nsb200_engine_split_begin, the
+ *          likelihood / nsb200_engine_split_accept rounds until *n_active == 0, nsb200_engine_split_finish
+ *          (packs this rank's rows into the gather buffer), [all-gather], nsb200_engine_step_end. */
+int nsb200_engine_init_external(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
+                                const double *U, const double *log_L, const int64_t *num_likelihood_evaluations,
+                                nsb200_stream_t stream);
+int nsb200_engine_split_begin(NsEngine *e, double *prop_U, double *prop_X, nsb200_stream_t stream);
+int nsb200_engine_split_accept(NsEngine *e, const double *prop_logL, double *prop_U, double *prop_X,
+                               uint64_t *n_active, nsb200_stream_t stream);
+int nsb200_engine_split_finish(NsEngine *e, nsb200_stream_t stream);
 /* Final live-set append (sharded_static.py:834-838). */
 int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream);
 /* Non-blocking progress of the enqueued bodies: *completed = bodies whose register update has run on the

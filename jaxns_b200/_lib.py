@@ -85,6 +85,9 @@ EXPORTS = (
     "nsb200_engine_step", "nsb200_engine_step_begin", "nsb200_engine_step_end", "nsb200_engine_gather_buffer",
     "nsb200_engine_run", "nsb200_engine_finalize", "nsb200_engine_register", "nsb200_engine_state",
     "nsb200_engine_slice_profile", "nsb200_bench_fp64_fma", "nsb200_engine_progress",
+    "nsb200_split_workspace_bytes", "nsb200_split_begin", "nsb200_split_accept", "nsb200_split_finish",
+    "nsb200_init_propose", "nsb200_transform_batch", "nsb200_engine_init_external", "nsb200_engine_split_begin",
+    "nsb200_engine_split_accept", "nsb200_engine_split_finish",
 )
 
 
@@ -105,6 +108,8 @@ def lib():
         L.nsb200_workspace_bytes.restype = ctypes.c_int64
         L.nsb200_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64]
         L.nsb200_engine_destroy.restype = None
+        L.nsb200_split_workspace_bytes.restype = ctypes.c_int64
+        L.nsb200_split_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32]
         _lib = L
     return _lib
 

@@ -11,6 +11,7 @@
 
 #include "ns_engine.cuh"
 #include "ns_slice.cuh"
+#include "ns_split.cuh"
 
 using namespace nsb;
 
@@ -65,9 +66,11 @@ static int pick_geometry(int D, Geometry &g) {
     return 0;
 }
 
-static int check_model(const NsModelDesc *m) {
+static int check_model(const NsModelDesc *m, bool allow_external = false) {
     if (!m) return fail("model is NULL");
-    if (m->family < 0 || m->family > NSB200_FAM_SHELLS) return fail("unknown likelihood family %d", m->family);
+    if (m->family == NSB200_FAM_EXTERNAL && !allow_external)
+        return fail("family EXTERNAL is evaluated by the caller: use the nsb200_split_* / nsb200_engine_split_* entry points");
+    if (m->family < 0 || m->family > NSB200_FAM_EXTERNAL) return fail("unknown likelihood family %d", m->family);
     if (m->prior_kind != NSB200_PRIOR_UNIFORM && m->prior_kind != NSB200_PRIOR_NORMAL)
         return fail("unknown prior kind %d", m->prior_kind);
     if (!m->prior_a || !m->prior_b) return fail("model prior arrays are NULL");
@@ -393,6 +396,161 @@ extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams 
 }
 
 // -------------------------------------------------------------------------------------------------
+// split slice step around a caller-evaluated likelihood (ns_split.cuh)
+// -------------------------------------------------------------------------------------------------
+// The split kernels only use the prior part of the model: strip the likelihood so that no
+// family-specific shared memory is staged.
+static NsModelDesc prior_only(const NsModelDesc &m) {
+    NsModelDesc p = m;
+    p.family = NSB200_FAM_EXTERNAL;
+    p.K = 0;
+    p.params = nullptr;
+    p.n_params = 0;
+    return p;
+}
+
+static int launch_split_step(const SplitArgs &a, int mode, cudaStream_t st) {
+    Geometry g;
+    if (pick_geometry(a.model.D, g)) return 1;
+    const long long n = a.chain_end - a.chain_begin;
+    if (n <= 0) return 0;
+    const size_t smem = 8 * model_smem_doubles(a.model.family, a.model.D, g.G, g.DPL, 0);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_GEOM(g, {
+        if (set_smem(k_split_step<kG, kDPL>, smem)) return 1;
+        k_split_step<kG, kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, st>>>(a, mode);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+static int check_slice_params(const NsSliceParams *p) {
+    if (!p) return fail("params is NULL");
+    if (p->num_slices < 1) return fail("num_slices should be >= 1, got %d", p->num_slices);
+    if (p->num_phantom < 0) return fail("num_phantom_save should be >= 0, got %d", p->num_phantom);
+    if (p->num_phantom >= p->num_slices)
+        return fail("num_phantom_save should be < num_slices, got %d >= %d", p->num_phantom, p->num_slices);
+    if (p->chain_begin < 0 || p->chain_end > p->num_samples || p->chain_begin > p->chain_end)
+        return fail("bad chain range [%lld, %lld) of %lld", (long long) p->chain_begin, (long long) p->chain_end,
+                    (long long) p->num_samples);
+    return 0;
+}
+
+extern "C" int64_t nsb200_split_workspace_bytes(int32_t D, int64_t n_chains, int32_t num_phantom) {
+    if (D < 1 || n_chains < 0 || num_phantom < 0) return -1;
+    return (int64_t) split_workspace_bytes(D, n_chains, num_phantom);
+}
+
+static int split_args(const NsModelDesc *model, const NsSliceParams *p, void *workspace, int64_t workspace_bytes,
+                      SplitArgs &a) {
+    if (check_model(model, true)) return 1;
+    if (check_slice_params(p)) return 1;
+    if (!workspace) return fail("workspace is NULL");
+    const long long n = p->chain_end - p->chain_begin;
+    if (workspace_bytes < (int64_t) split_workspace_bytes(model->D, n, p->num_phantom))
+        return fail("workspace too small: %lld < %zu", (long long) workspace_bytes,
+                    split_workspace_bytes(model->D, n, p->num_phantom));
+    memset(&a, 0, sizeof(a));
+    a.model = prior_only(*model);
+    a.N = p->num_live;
+    a.chain_begin = p->chain_begin;
+    a.chain_end = p->chain_end;
+    a.S = p->num_slices;
+    a.k = p->num_phantom;
+    a.midpoint = p->midpoint_shrink;
+    a.state = split_state_view(workspace, model->D, n, p->num_phantom);
+    return 0;
+}
+
+extern "C" int nsb200_split_begin(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                                  const double *contour, const double *live_U, const double *live_logL,
+                                  const double *seed_table, void *workspace, int64_t workspace_bytes, double *prop_U,
+                                  double *prop_X, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
+    if (p->num_live < 1) return fail("num_live must be >= 1");
+    if (!key || !contour || !live_U || !live_logL || !seed_table) return fail("input pointer is NULL");
+    if (!prop_U) return fail("prop_U is NULL");
+    a.key = Key{key[0], key[1]};
+    a.contour = contour;
+    a.live_U = live_U;
+    a.live_logL = live_logL;
+    a.seed_table = seed_table;
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    return launch_split_step(a, 0, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_split_accept(const NsModelDesc *model, const NsSliceParams *p, const double *contour,
+                                   const double *prop_logL, void *workspace, int64_t workspace_bytes, double *prop_U,
+                                   double *prop_X, uint64_t *n_active, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
+    if (!contour || !prop_logL) return fail("input pointer is NULL");
+    if (!prop_U) return fail("prop_U is NULL");
+    a.contour = contour;
+    a.prop_logL = prop_logL;
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    a.active = (unsigned long long *) n_active;
+    return launch_split_step(a, 1, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_split_finish(const NsModelDesc *model, const NsSliceParams *p, void *workspace,
+                                   int64_t workspace_bytes, double *out_U, double *out_logL, int64_t *out_nevals,
+                                   double *ph_U, double *ph_logL, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
+    if (!out_U || !out_logL || !out_nevals) return fail("output pointer is NULL");
+    if (p->num_phantom > 0 && (!ph_U || !ph_logL)) return fail("phantom outputs are NULL but num_phantom > 0");
+    const long long n = p->chain_end - p->chain_begin;
+    if (n <= 0) return 0;
+    k_split_finish<<<296, 256, 0, (cudaStream_t) stream>>>(nullptr, a.state, n, model->D, p->num_phantom, out_U, out_logL,
+                                                            (long long *) out_nevals, ph_U, ph_logL, nullptr, 0);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_init_propose(const NsModelDesc *model, const uint32_t sample_key[2], int64_t N, int64_t begin,
+                                   int64_t end, int32_t round, const uint8_t *need, double *out_U, double *out_X,
+                                   nsb200_stream_t stream) {
+    if (check_model(model, true)) return 1;
+    if (!sample_key || !out_U) return fail("NULL pointer");
+    if (begin < 0 || end > N || begin > end) return fail("bad range [%lld, %lld) of %lld", (long long) begin, (long long) end, (long long) N);
+    if (round < 0) return fail("round must be >= 0");
+    if (end == begin) return 0;
+    Geometry g;
+    if (pick_geometry(model->D, g)) return 1;
+    InitProposeArgs a{prior_only(*model), Key{sample_key[0], sample_key[1]}, begin, end, round, need, out_U, out_X};
+    const size_t smem = 8 * model_smem_doubles(a.model.family, a.model.D, g.G, g.DPL, 0);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_GEOM(g, {
+        if (set_smem(k_init_propose<kG, kDPL>, smem)) return 1;
+        k_init_propose<kG, kDPL><<<grid_for(end - begin, per_block), kThreadsPerBlock, smem, (cudaStream_t) stream>>>(a);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_transform_batch(const NsModelDesc *model, const double *U, int64_t n, double *out_X,
+                                      nsb200_stream_t stream) {
+    if (check_model(model, true)) return 1;
+    if (n <= 0) return 0;
+    if (!U || !out_X) return fail("NULL pointer");
+    Geometry g;
+    if (pick_geometry(model->D, g)) return 1;
+    const NsModelDesc pm = prior_only(*model);
+    const size_t smem = 8 * model_smem_doubles(pm.family, pm.D, g.G, g.DPL, 0);
+    const int per_block = kThreadsPerBlock / g.G;
+    NSB_DISPATCH_GEOM(g, {
+        if (set_smem(k_transform<kG, kDPL>, smem)) return 1;
+        k_transform<kG, kDPL><<<grid_for(n, per_block), kThreadsPerBlock, smem, (cudaStream_t) stream>>>(pm, U, n, out_X);
+    });
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------------
 // statistics
 // -------------------------------------------------------------------------------------------------
 static size_t tree_workspace_bytes(long long M) {
@@ -591,6 +749,10 @@ struct NsEngine {
     double slice_ms = 0.0;
     long long slice_launches = 0, all_launches = 0;
     bool initialised = false;
+    // family EXTERNAL: chain state of the split slice step (ns_split.cuh) for this rank's chains
+    bool external = false;
+    void *split_ws = nullptr;
+    size_t split_ws_bytes = 0;
 };
 
 template <typename T>
@@ -619,7 +781,7 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
 
 extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!cfg || !out) return fail("NULL argument");
-    if (check_model(&cfg->model)) return 1;
+    if (check_model(&cfg->model, true)) return 1;
     Geometry g;
     if (pick_geometry(cfg->model.D, g)) return 1;
     if (cfg->num_live_points < 2) return fail("num_live_points must be >= 2");
@@ -644,6 +806,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     e->rows_per_rank = e->m / cfg->world_size;
     e->row_doubles = (e->D + 2) + e->k * (e->D + 1);
     e->packed_rows = e->N > e->m ? e->N : e->m;  // the init pass packs all N prior draws
+    e->external = cfg->model.family == NSB200_FAM_EXTERNAL;
     const size_t D = e->D;
     int rc = 0;
     for (int b = 0; b < 2 && !rc; ++b) {
@@ -669,7 +832,12 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->tabT, e->N + 2);
     if (!rc) rc |= dev_alloc(e, &e->tabT2, e->N + 2);
     if (!rc) rc |= dev_alloc(e, &e->tabt, e->N + 2);
-    if (g.G >= 8) {  // data-independent chain streams are generated off the chains' critical path
+    if (e->external) {
+        e->split_ws_bytes = split_workspace_bytes(e->D, e->rows_per_rank, (int) e->k);
+        char *ws = nullptr;
+        if (!rc) rc |= dev_alloc(e, &ws, e->split_ws_bytes);
+        e->split_ws = ws;
+    } else if (g.G >= 8) {  // data-independent chain streams are generated off the chains' critical path
         const size_t rows = (size_t) e->rows_per_rank * cfg->num_slices;
         for (int b = 0; b < 3; ++b) {
             if (!rc) rc |= dev_alloc(e, &e->pre_dirs[b], rows * D);
@@ -733,8 +901,8 @@ static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
 
 static int enqueue_streams(NsEngine *e, int buf);
 
-extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
-                                  nsb200_stream_t stream) {
+static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond, nsb200_stream_t stream,
+                              const double *extU, const double *extL, const long long *extN) {
     if (!e || !key) return fail("NULL argument");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
@@ -766,9 +934,15 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
     k_alpha_table<<<4, 256, 0, st>>>(e->cfg.num_slices, e->alpha_tab);
     // N prior draws (replicated on every rank), packed, ranked (stable argsort) and scattered
-    double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
-    long long *tmpN = e->live[1].nevals;
-    if (launch_draw(&e->cfg.model, sample_key, nullptr, 0, e->N, tmpU, tmpL, tmpN, 0, st)) return 1;
+    const double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
+    const long long *tmpN = e->live[1].nevals;
+    if (extU) {  // caller-evaluated initial live points (family EXTERNAL)
+        tmpU = extU;
+        tmpL = extL;
+        tmpN = extN;
+    } else if (launch_draw(&e->cfg.model, sample_key, nullptr, 0, e->N, e->live[1].U, e->live[1].logL, e->live[1].nevals, 0, st)) {
+        return 1;
+    }
     k_pack_rows<<<592, 256, 0, st>>>(tmpU, tmpL, tmpN, e->N, D, e->packed, e->row_doubles);
     k_merge_rank<<<grid_for(e->N * kRankLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
                                                        e->N, e->N, e->rank);
@@ -785,6 +959,19 @@ extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTe
     e->all_launches += 9;
     e->initialised = true;
     return 0;
+}
+
+extern "C" int nsb200_engine_init(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
+                                  nsb200_stream_t stream) {
+    if (e && e->external) return fail("family EXTERNAL: use nsb200_engine_init_external with caller-evaluated live points");
+    return engine_init_common(e, key, term_cond, stream, nullptr, nullptr, nullptr);
+}
+
+extern "C" int nsb200_engine_init_external(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
+                                           const double *U, const double *log_L,
+                                           const int64_t *num_likelihood_evaluations, nsb200_stream_t stream) {
+    if (!U || !log_L || !num_likelihood_evaluations) return fail("initial live points are NULL");
+    return engine_init_common(e, key, term_cond, stream, U, log_L, (const long long *) num_likelihood_evaluations);
 }
 
 // NSB200_TRACE=1: device timeline of a few iterations (debug aid for DESIGN.md numbers)
@@ -881,6 +1068,11 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
+    if (e->external) {  // the chains are run by the caller through nsb200_engine_split_*
+        e->body += 1;
+        e->all_launches += 2;
+        return 0;
+    }
     // this rank's chains -> its block of the gather buffer
     const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
     SliceArgs a;
@@ -941,8 +1133,64 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
 extern "C" int nsb200_engine_step(NsEngine *e, nsb200_stream_t stream) {
     if (!e) return fail("NULL engine");
     if (e->cfg.world_size != 1) return fail("engine_step requires world_size == 1; use step_begin / all-gather / step_end");
+    if (e->external) return fail("family EXTERNAL: drive the body with step_begin / engine_split_* / step_end");
     if (nsb200_engine_step_begin(e, stream)) return 1;
     return nsb200_engine_step_end(e, stream);
+}
+
+// ---- engine bodies with a caller-evaluated likelihood ---------------------------------------------
+static int engine_split_args(NsEngine *e, SplitArgs &a) {
+    if (!e || !e->initialised) return fail("engine not initialised");
+    if (!e->external) return fail("engine_split_* requires model.family == NSB200_FAM_EXTERNAL");
+    const long long begin = e->rows_per_rank * e->cfg.rank;
+    memset(&a, 0, sizeof(a));
+    a.model = prior_only(e->cfg.model);
+    a.seed_table = e->seed_table;
+    a.N = e->N;
+    a.chain_begin = begin;
+    a.chain_end = begin + e->rows_per_rank;
+    a.S = e->cfg.num_slices;
+    a.k = e->cfg.num_phantom;
+    a.midpoint = e->cfg.midpoint_shrink;
+    a.ctl = e->ctl;
+    a.live0 = e->live[0];
+    a.live1 = e->live[1];
+    a.state = split_state_view(e->split_ws, e->D, e->rows_per_rank, (int) e->k);
+    return 0;
+}
+
+extern "C" int nsb200_engine_split_begin(NsEngine *e, double *prop_U, double *prop_X, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (engine_split_args(e, a)) return 1;
+    if (!prop_U) return fail("prop_U is NULL");
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    e->all_launches += 1;
+    return launch_split_step(a, 0, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_engine_split_accept(NsEngine *e, const double *prop_logL, double *prop_U, double *prop_X,
+                                          uint64_t *n_active, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (engine_split_args(e, a)) return 1;
+    if (!prop_logL || !prop_U) return fail("NULL pointer");
+    a.prop_logL = prop_logL;
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    a.active = (unsigned long long *) n_active;
+    e->all_launches += 1;
+    return launch_split_step(a, 1, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_engine_split_finish(NsEngine *e, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (engine_split_args(e, a)) return 1;
+    k_split_finish<<<296, 256, 0, (cudaStream_t) stream>>>(e->ctl, a.state, e->rows_per_rank, e->D, (int) e->k, nullptr, nullptr,
+                                                            nullptr, nullptr, nullptr,
+                                                            e->packed + a.chain_begin * e->row_doubles, e->row_doubles);
+    NSB_LAUNCH_CHECK();
+    e->all_launches += 1;
+    return 0;
 }
 
 extern "C" int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *rows_per_rank, int64_t *row_doubles) {
@@ -986,6 +1234,7 @@ extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTer
                                  int64_t max_iterations, NsRegister *out_register, nsb200_stream_t stream) {
     if (!e) return fail("NULL engine");
     if (e->cfg.world_size != 1) return fail("engine_run requires world_size == 1");
+    if (e->external) return fail("family EXTERNAL: the caller drives the loop (engine_init_external / step_begin / engine_split_* / step_end)");
     if (nsb200_engine_init(e, key, term_cond, stream)) return 1;
     // Steps are no-ops on the device once the register says done, so the host runs ahead: it keeps
     // `depth` bodies in flight and polls two host-mapped words the epilogue writes, never the stream.

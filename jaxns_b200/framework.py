@@ -3,8 +3,9 @@ Model / Prior with the reference's signatures (/root/reference/src/jaxns/framewo
 framework/prior.py:65-161, framework/ops.py:21-36,240-326) for registered likelihood families.
 
 `prior_model` stays a generator function that yields Prior objects and returns the likelihood
-inputs; `log_likelihood` must be a RegisteredLikelihood (jaxns_b200.likelihoods).  Arbitrary traced
-JAX likelihoods are SURVEY §8(f) row 1 and raise NotImplementedError.
+inputs.  `log_likelihood` is either a RegisteredLikelihood (jaxns_b200.likelihoods: fused into the
+slice kernel) or any batched device callable (wrapped in ExternalLikelihood): then the slice step is
+split into propose / accept kernels around the call, still entirely on the GPU.
 """
 import ctypes
 from typing import Callable, List, Optional
@@ -13,7 +14,7 @@ import numpy as np
 import torch
 
 from jaxns_b200 import _lib, distributions
-from jaxns_b200.likelihoods import RegisteredLikelihood
+from jaxns_b200.likelihoods import ExternalLikelihood, RegisteredLikelihood
 
 __all__ = ["Prior", "Model"]
 
@@ -43,9 +44,7 @@ class Model:
         if params is not None:
             raise NotImplementedError("Parametrised models are out of the hot-path scope (SURVEY §2.1).")
         if not isinstance(log_likelihood, RegisteredLikelihood):
-            raise NotImplementedError(
-                "log_likelihood must be a registered family (jaxns_b200.likelihoods.*); arbitrary traced "
-                "likelihoods need the split propose/accept path (SURVEY §8f row 1).")
+            log_likelihood = ExternalLikelihood(log_likelihood)
         self.prior_model = prior_model
         self.log_likelihood = log_likelihood
         self._priors: List[Prior] = []
@@ -61,9 +60,14 @@ class Model:
         except StopIteration as stop:
             ret = stop.value
         ret = ret if isinstance(ret, tuple) else (ret,)
-        if [getattr(r, "index", None) for r in ret] != list(range(len(self._priors))):
+        self.is_external = isinstance(log_likelihood, ExternalLikelihood)
+        if not all(isinstance(r, _Var) for r in ret):
+            raise NotImplementedError("prior_model must return (a tuple of) its yielded variables.")
+        if not self.is_external and [r.index for r in ret] != list(range(len(self._priors))):
             raise NotImplementedError("prior_model must return its yielded variables in order: the registered "
                                       "likelihood consumes their concatenation.")
+        offs = np.concatenate([[0], np.cumsum([p.dist.event_size() for p in self._priors])]).astype(int)
+        self._ret_slices = [(int(offs[r.index]), int(offs[r.index + 1])) for r in ret]
         kinds = {p.dist.prior_kind for p in self._priors}
         if len(kinds) != 1:
             raise NotImplementedError("Mixing Uniform and Normal priors in one model is not supported yet.")
@@ -112,15 +116,32 @@ class Model:
                                 a.data_ptr(), b.data_ptr(), p.data_ptr(), int(self._params_host.size))
 
     # -- reference methods ----------------------------------------------------------------------
-    def _forward_batch(self, U: torch.Tensor, want_X: bool):
+    def call_likelihood(self, X: torch.Tensor) -> torch.Tensor:
+        """External likelihood at transformed points X [n, D] -> log L [n] (float64, contiguous, NaN -> -inf as
+        framework/ops.py:323-325); the callable sees one [n, size] tensor per variable prior_model returns."""
+        out = self.log_likelihood.fn(*[X[:, a:b] for a, b in self._ret_slices])
+        out = torch.as_tensor(out, dtype=torch.float64, device=X.device).reshape(-1)
+        if out.numel() != X.shape[0]:
+            raise ValueError(f"log_likelihood must return one value per row: got {out.numel()} for {X.shape[0]} rows")
+        return torch.nan_to_num(out, nan=-float("inf"), posinf=float("inf"), neginf=-float("inf")).contiguous()
+
+    def _forward_batch(self, U: torch.Tensor, want_X: bool, want_L: bool = True):
         _lib.require_cuda()
         U = torch.as_tensor(U, dtype=torch.float64, device="cuda")
         batched = U.dim() == 2
         U2 = U.reshape(-1, self._D).contiguous()
         n = U2.shape[0]
+        d = self.desc()
+        if self.is_external:
+            X = torch.empty_like(U2)
+            _lib.check(_lib.lib().nsb200_transform_batch(ctypes.byref(d), _lib.ptr(U2), ctypes.c_int64(n), _lib.ptr(X),
+                                                          _lib.stream_arg()))
+            logL = self.call_likelihood(X) if want_L else None
+            if not batched:
+                return (logL[0] if want_L else None), (X[0] if want_X else None)
+            return logL, (X if want_X else None)
         logL = torch.empty(n, dtype=torch.float64, device="cuda")
         X = torch.empty_like(U2) if want_X else None
-        d = self.desc()
         _lib.check(_lib.lib().nsb200_forward_batch(ctypes.byref(d), _lib.ptr(U2), ctypes.c_int64(n), _lib.ptr(logL),
                                                     _lib.ptr(X), _lib.stream_arg()))
         if not batched:
@@ -138,7 +159,7 @@ class Model:
 
     def transform(self, U):
         """U -> X dict keyed by prior names (framework/model.py:155-159)."""
-        X = self._forward_batch(U, True)[1]
+        X = self._forward_batch(U, True, False)[1]
         out, o = {}, 0
         for i, p in enumerate(self._priors):
             n = p.dist.event_size()
@@ -151,7 +172,7 @@ class Model:
         return {}
 
     def prepare_input(self, U):
-        return (self._forward_batch(U, True)[1],)
+        return (self._forward_batch(U, True, False)[1],)
 
     def sample_U(self, key):
         """uniform(split(key, 2)[1], (D,)) (framework/model.py:122-138, context.py:107-109)."""
@@ -162,7 +183,7 @@ class Model:
         """Prior log density of the transformed point (framework/model.py:178-187), evaluated on the device
         (post-processing for NestedSamplerResults.log_posterior_density; small torch reductions)."""
         import math
-        X = self._forward_batch(U, True)[1]
+        X = self._forward_batch(U, True, False)[1]
         a = self._dev[0]
         b = self._dev[1]
         if self._prior_kind == distributions.Uniform.prior_kind:

@@ -29,6 +29,23 @@ class RegisteredLikelihood:
         raise RuntimeError("Registered likelihoods are evaluated on the device; use Model.forward(U).")
 
 
+class ExternalLikelihood(RegisteredLikelihood):
+    """An arbitrary user likelihood: a BATCHED device callable `fn(*variables) -> log_L[n]` over torch CUDA
+    float64 tensors (each variable [n, size], in the order prior_model returns them) -- the analogue of the
+    reference's vmap(log_likelihood) compiled by XLA (framework/ops.py:302-326).  The slice step is split
+    into propose / accept kernels around this call (include/nsb200.h nsb200_split_*); nothing runs on the CPU.
+    Model wraps any plain callable in this class."""
+    family = _consts.FAM_EXTERNAL
+
+    def __init__(self, fn):
+        if not callable(fn):
+            raise TypeError("log_likelihood must be a RegisteredLikelihood or a callable")
+        self.fn = fn
+
+    def __call__(self, *args):
+        return self.fn(*args)
+
+
 class DenseGaussianLikelihood(RegisteredLikelihood):
     family = _consts.FAM_GAUSS_DENSE
 

@@ -182,7 +182,10 @@ class ShardedStaticNestedSampler:
             tc = _lib.NsTermCond()  # device stops only on plateau / no seed points; host decides the rest
         reg = _lib.NsRegister()
         world = len(self.devices) if self._world > 1 else 1
-        if plain and world == 1:
+        if getattr(self.model, "is_external", False):
+            host_tc = self._effective_host_cond(term_cond) if not plain else None
+            self._run_external(eng, key, tc, reg, stream, world, host_tc)
+        elif plain and world == 1:
             _lib.check(L.nsb200_engine_run(eng.h, _lib.key_arg(key), ctypes.byref(tc), ctypes.c_int64(-1),
                                            ctypes.byref(reg), stream))
         else:
@@ -232,6 +235,84 @@ class ShardedStaticNestedSampler:
         self.last_profile = dict(slice_ms=ms.value, slice_launches=nsl.value, all_launches=nall.value,
                                  iterations=int(reg.iteration))
         return termination_reason, register, state
+
+    def _initial_points_external(self, key):
+        """create_init_state's prior draws (common/initialisation.py:47-60, common/uniform_sample.py:12-60) with the
+        caller's likelihood: round r redraws the rows whose log L is still -inf."""
+        from jaxns_b200 import random
+        L = _lib.lib()
+        N, D = self.num_live_points, self.model.U_ndims
+        sample_key = random.split(key, 2)[1]
+        d = self.model.desc()
+        U = torch.empty((N, D), dtype=torch.float64, device="cuda")
+        X = torch.empty((N, D), dtype=torch.float64, device="cuda")
+        nev = torch.ones(N, dtype=torch.int64, device="cuda")
+        st = _lib.stream_arg()
+        _lib.check(L.nsb200_init_propose(ctypes.byref(d), _lib.key_arg(sample_key), ctypes.c_int64(N), ctypes.c_int64(0),
+                                         ctypes.c_int64(N), ctypes.c_int32(0), ctypes.c_void_p(0), _lib.ptr(U),
+                                         _lib.ptr(X), st))
+        logL = self.model.call_likelihood(X)
+        rnd = 0
+        while True:
+            need = torch.isneginf(logL)  # `while log_L <= -inf` (uniform_sample.py:40-43)
+            if not bool(need.any().item()):
+                break
+            rnd += 1
+            if rnd > 10000:
+                raise RuntimeError("could not draw initial live points with finite log-likelihood")
+            need8 = need.to(torch.uint8).contiguous()
+            _lib.check(L.nsb200_init_propose(ctypes.byref(d), _lib.key_arg(sample_key), ctypes.c_int64(N),
+                                             ctypes.c_int64(0), ctypes.c_int64(N), ctypes.c_int32(rnd), _lib.ptr(need8),
+                                             _lib.ptr(U), _lib.ptr(X), st))
+            logL = torch.where(need, self.model.call_likelihood(X), logL)
+            nev += need.to(torch.int64)
+        return U, logL.contiguous(), nev
+
+    def _run_external(self, eng, key, tc, reg, stream, world, host_tc):
+        """The loop with a caller-evaluated likelihood: every body is step_begin (discard + append), the split
+        slice rounds around model.call_likelihood, the all-gather (world > 1) and step_end."""
+        L = _lib.lib()
+        U0, logL0, nev0 = self._initial_points_external(key)
+        _lib.check(L.nsb200_engine_init_external(eng.h, _lib.key_arg(key), ctypes.byref(tc), _lib.ptr(U0), _lib.ptr(logL0),
+                                                 _lib.ptr(nev0), stream))
+        gather = self._gather_tensor(eng) if world > 1 else None
+        D = self.model.U_ndims
+        n = int(self.num_live_points * self.shell_fraction) // world
+        prop_U = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        prop_X = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        active = torch.zeros(1, dtype=torch.int64, device="cuda")
+        burst = max(4, self.sampler.num_slices // 4)
+        _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+        while True:
+            if host_tc is None:
+                done = bool(reg.done)
+            else:
+                done = termination.determine_termination(host_tc, termination.register_from_c(reg))[0] or bool(reg.done)
+            if done:
+                break
+            _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
+            _lib.check(L.nsb200_engine_split_begin(eng.h, _lib.ptr(prop_U), _lib.ptr(prop_X), stream))
+            while True:
+                for r in range(burst):
+                    logL = self.model.call_likelihood(prop_X)
+                    last = r == burst - 1
+                    if last:
+                        active.zero_()
+                    _lib.check(L.nsb200_engine_split_accept(eng.h, _lib.ptr(logL), _lib.ptr(prop_U), _lib.ptr(prop_X),
+                                                            _lib.ptr(active) if last else ctypes.c_void_p(0), stream))
+                if world > 1:  # every rank leaves the rounds together (the all-gather below must stay matched)
+                    import torch.distributed as dist
+                    dist.all_reduce(active, op=dist.ReduceOp.MAX)
+                if int(active.item()) == 0:
+                    break
+            _lib.check(L.nsb200_engine_split_finish(eng.h, stream))
+            if world > 1:
+                import torch.distributed as dist
+                rows = gather.shape[0] // world
+                dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+            _lib.check(L.nsb200_engine_step_end(eng.h, stream))
+            _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+        _lib.check(L.nsb200_engine_finalize(eng.h, stream))
 
     def _effective_host_cond(self, term_cond):
         """max_samples lowered by one iteration's space (sharded_static.py:464-470), applied to every leaf."""

@@ -123,16 +123,59 @@ class UniDimSliceSampler(AbstractSampler):
         p = _lib.NsSliceParams(self.num_slices, k, int(self.midpoint_shrink), 0, N, int(num_samples),
                                int(chain_begin), int(chain_end))
         d = self.model.desc()
-        _lib.check(_lib.lib().nsb200_slice_batch(
-            ctypes.byref(d), ctypes.byref(p), _lib.key_arg(key), _lib.ptr(contour), _lib.ptr(live_U),
-            _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)), _lib.ptr(out_U), _lib.ptr(out_logL),
-            _lib.ptr(out_nev), _lib.ptr(ph_U) if k else ctypes.c_void_p(0),
-            _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), _lib.stream_arg()))
+        if getattr(self.model, "is_external", False):
+            self._split_batch(d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL)
+        else:
+            self._fused_batch(d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL)
         cons = contour.expand(n)
         sample = Sample(U_sample=out_U, log_L_constraint=cons, log_L=out_logL, num_likelihood_evaluations=out_nev)
         phantom = Sample(U_sample=ph_U, log_L_constraint=contour.expand(n * k), log_L=ph_logL,
                          num_likelihood_evaluations=torch.zeros(n * k, dtype=torch.int64, device="cuda"))
         return sample, phantom
+
+    def _split_batch(self, d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL):
+        """The slice step split around the model's batched device likelihood (include/nsb200.h nsb200_split_*)."""
+        L = _lib.lib()
+        n, D = out_U.shape
+        k = self.num_phantom_save
+        N = live_U.shape[0]
+        if n == 0:
+            return
+        nbytes = L.nsb200_split_workspace_bytes(D, n, k)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        prop_U = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        prop_X = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        active = torch.zeros(1, dtype=torch.int64, device="cuda")
+        st = _lib.stream_arg()
+        _lib.check(L.nsb200_split_begin(ctypes.byref(d), ctypes.byref(p), _lib.key_arg(key), _lib.ptr(contour),
+                                        _lib.ptr(live_U), _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)),
+                                        _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(prop_U), _lib.ptr(prop_X), st))
+        burst = max(4, self.num_slices // 4)  # likelihood rounds between reads of the active-chain counter
+        while True:
+            for r in range(burst):
+                logL = self.model.call_likelihood(prop_X)
+                last = r == burst - 1
+                if last:
+                    active.zero_()
+                _lib.check(L.nsb200_split_accept(ctypes.byref(d), ctypes.byref(p), _lib.ptr(contour), _lib.ptr(logL),
+                                                 _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(prop_U),
+                                                 _lib.ptr(prop_X), _lib.ptr(active) if last else ctypes.c_void_p(0),
+                                                 st))
+            if int(active.item()) == 0:
+                break
+        _lib.check(L.nsb200_split_finish(ctypes.byref(d), ctypes.byref(p), _lib.ptr(ws), ctypes.c_int64(nbytes),
+                                         _lib.ptr(out_U), _lib.ptr(out_logL), _lib.ptr(out_nev),
+                                         _lib.ptr(ph_U) if k else ctypes.c_void_p(0),
+                                         _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), st))
+
+    def _fused_batch(self, d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL):
+        k = self.num_phantom_save
+        N = live_U.shape[0]
+        _lib.check(_lib.lib().nsb200_slice_batch(
+            ctypes.byref(d), ctypes.byref(p), _lib.key_arg(key), _lib.ptr(contour), _lib.ptr(live_U),
+            _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)), _lib.ptr(out_U), _lib.ptr(out_logL),
+            _lib.ptr(out_nev), _lib.ptr(ph_U) if k else ctypes.c_void_p(0),
+            _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), _lib.stream_arg()))
 
 
 @dataclasses.dataclass(eq=False)

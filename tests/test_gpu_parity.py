@@ -380,3 +380,150 @@ def test_full_run_statistics_vs_oracle(torch_cuda, oracle, name, D, N, S, midpoi
     g, c, sg = np.array(g), np.array(c), np.array(sg)
     assert abs(g.mean() - true) < 3 * sg.mean() / 2
     assert abs(g.mean() - c.mean()) < 3 * sg.mean() * np.sqrt(2 / 4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# split propose / accept path around a caller-evaluated likelihood
+# ---------------------------------------------------------------------------------------------------
+def _unit_cube_pair(name, D):
+    """(fused model, external model) over a Uniform(0,1)^D prior, where X == U bit for bit, so the external
+    callable can evaluate the fused family itself (same device function) at the proposed points."""
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd, likelihoods as lk
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(low=np.zeros(D), high=np.ones(D)), name="x")
+        return x
+
+    if name == "gauss":
+        cov = np.full((D, D), 0.5 * 0.01) + 0.5 * 0.01 * np.eye(D)
+        like = lk.DenseGaussianLikelihood(np.full(D, 0.5), covariance_matrix=cov)
+    elif name == "rosenbrock":
+        like = lk.RosenbrockLikelihood()
+    else:
+        like = lk.EggBoxLikelihood()
+    fused = j.Model(prior_model, like)
+    external = j.Model(prior_model, lambda x: fused.forward(x.contiguous()))
+    return fused, external
+
+
+@pytest.mark.parametrize("name,D,N,S,k,midpoint", [("gauss", 8, 128, 12, 3, True), ("gauss", 32, 256, 16, 0, True),
+                                                   ("gauss", 40, 64, 6, 2, True), ("rosenbrock", 3, 200, 9, 0, False),
+                                                   ("eggbox", 1, 64, 4, 1, True)])
+def test_split_batch_equals_fused_batch(torch_cuda, name, D, N, S, k, midpoint):
+    """Same key tree, same arithmetic, same likelihood values -> the split path reproduces the fused kernel."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.types import LivePointCollection
+    fused, external = _unit_cube_pair(name, D)
+    U = random.uniform(random.PRNGKey(5), N * D).reshape(N, D)
+    logL = fused.forward(U)
+    order = torch.argsort(logL, stable=True)
+    state = LivePointCollection(None, U[order].contiguous(), None, logL[order].contiguous(), None)
+    m = N // 2
+    contour = float(state.log_L[m - 1].item())
+    out = []
+    for model in (fused, external):
+        sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint, perfect=True)
+        out.append(sampler.get_samples_batch(random.PRNGKey(9), contour, state, m))
+    (fs, fp), (es, ep) = out
+    assert torch.equal(fs.num_likelihood_evaluations, es.num_likelihood_evaluations)
+    assert torch.equal(fs.U_sample, es.U_sample)
+    assert torch.equal(fs.log_L, es.log_L)
+    if k:
+        assert torch.equal(fp.U_sample, ep.U_sample)
+        assert torch.equal(fp.log_L, ep.log_L)
+    # sharded ranges of the split path reproduce the full batch
+    sampler = j.UniDimSliceSampler(model=external, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint, perfect=True)
+    a, _ = sampler.get_samples_batch(random.PRNGKey(9), contour, state, m, 0, m // 2)
+    b, _ = sampler.get_samples_batch(random.PRNGKey(9), contour, state, m, m // 2, m)
+    assert torch.equal(torch.cat([a.U_sample, b.U_sample]), es.U_sample)
+
+
+def _torch_gauss_model(D, mu=15.0, rho=0.99):
+    """The Gaussian benchmark likelihood written by a 'user' in torch (float64, batched, on the device)."""
+    import torch
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+    cov = np.full((D, D), rho) + (1 - rho) * np.eye(D)
+    Lc = np.linalg.cholesky(cov)
+    Linv = torch.from_numpy(np.linalg.solve(Lc, np.eye(D))).cuda()
+    c = float(-np.sum(np.log(np.diag(Lc))) - 0.5 * D * np.log(2 * np.pi))
+    loc = torch.full((D,), mu, dtype=torch.float64, device="cuda")
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Normal(loc=np.zeros(D), scale=np.ones(D)), name="x")
+        return x
+
+    def log_likelihood(x):
+        z = (x - loc) @ Linv.T
+        return c - 0.5 * (z * z).sum(-1)
+
+    return j.Model(prior_model, log_likelihood)
+
+
+def test_split_batch_user_likelihood_vs_oracle(torch_cuda, oracle):
+    """A torch-coded likelihood through the split path against the oracle's chains for the same problem."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.types import LivePointCollection
+    D, N, S, k = 8, 128, 10, 2
+    ext = _torch_gauss_model(D)
+    om = to_oracle(product_models()["gauss"](D), oracle)
+    oU, ologL, _ = oracle.init_batch(om, random.PRNGKey(3), N)
+    order = np.argsort(ologL, kind="stable")
+    live_U, live_logL = oU[order], ologL[order]
+    m = N // 2
+    contour = live_logL[m - 1]
+    exp = oracle.slice_batch(om, random.PRNGKey(11), contour, live_U, live_logL, S, k, True, num_samples=m)
+    sampler = j.UniDimSliceSampler(model=ext, num_slices=S, num_phantom_save=k, midpoint_shrink=True, perfect=True)
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    sample, phantom = sampler.get_samples_batch(random.PRNGKey(11), contour, state, m)
+    np.testing.assert_array_equal(sample.num_likelihood_evaluations.cpu().numpy(), exp["n_evals"])
+    np.testing.assert_allclose(sample.U_sample.cpu().numpy(), exp["U"], rtol=1e-7, atol=1e-9)
+    np.testing.assert_allclose(sample.log_L.cpu().numpy(), exp["log_L"], rtol=1e-7, atol=1e-7)
+    np.testing.assert_allclose(phantom.U_sample.cpu().numpy(), exp["ph_U"], rtol=1e-7, atol=1e-9)
+    # forward / transform of an external model
+    logL = ext.forward(torch.from_numpy(live_U).cuda())
+    np.testing.assert_allclose(logL.cpu().numpy(), live_logL, rtol=1e-9, atol=1e-9)
+
+
+def test_engine_run_external_equals_fused(torch_cuda):
+    """Whole runs: the caller-driven loop (init_external / step_begin / split rounds / step_end) against the
+    fused engine on the same problem -> identical dead-point store, register and key."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    fused, external = _unit_cube_pair("gauss", 8)
+    res = []
+    for model in (fused, external):
+        ns = j.NestedSampler(model=model, num_live_points=64, num_slices=12, k=2, s=None, max_samples=64 * 3 * 8)
+        reason, state = ns(random.PRNGKey(7))
+        n = min(state.num_samples, ns.nested_sampler.max_samples)
+        r = ns.to_results(reason, state)
+        res.append((reason, state, n, r, ns.nested_sampler.last_register))
+    (r0, s0, n0, a, reg0), (r1, s1, n1, b, reg1) = res
+    assert r0 == r1 and n0 == n1 and s0.next_sample_idx == s1.next_sample_idx
+    np.testing.assert_array_equal(s0.key, s1.key)
+    assert torch.equal(s0.sample_collection.log_L[:n0], s1.sample_collection.log_L[:n1])
+    assert torch.equal(s0.sample_collection.U_samples[:n0], s1.sample_collection.U_samples[:n1])
+    assert torch.equal(s0.sample_collection.sender_node_idx[:n0], s1.sample_collection.sender_node_idx[:n1])
+    assert torch.equal(s0.sample_collection.num_likelihood_evaluations[:n0], s1.sample_collection.num_likelihood_evaluations[:n1])
+    assert torch.equal(s0.sample_collection.phantom[:n0], s1.sample_collection.phantom[:n1])
+    assert a.log_Z_mean == b.log_Z_mean and a.total_num_likelihood_evaluations == b.total_num_likelihood_evaluations
+    assert reg0.num_likelihood_evaluations == reg1.num_likelihood_evaluations
+
+
+def test_external_public_api_gaussian_logZ(torch_cuda, oracle):
+    """A user-written torch likelihood end to end through NestedSampler: log Z on the analytic value."""
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    D = 2
+    ns = j.NestedSampler(model=_torch_gauss_model(D), num_live_points=200)
+    reason, state = ns(random.PRNGKey(42))
+    res = ns.to_results(reason, state)
+    true = oracle.gauss_analytic_logZ(D)
+    assert abs(res.log_Z_mean - true) < 3 * res.log_Z_uncert, (res.log_Z_mean, true, res.log_Z_uncert)
+    assert res.total_num_likelihood_evaluations > 0 and res.samples["x"].shape[1] == D

@@ -120,16 +120,26 @@ def test_model_descriptor_packing():
     assert mu.host_arrays()[2] == _consts.PRIOR_UNIFORM
 
 
-def test_model_rejects_unregistered_likelihood():
+def test_model_wraps_unregistered_likelihood_as_external():
+    """A plain callable becomes an ExternalLikelihood (family EXTERNAL): the split propose / accept path."""
     import jaxns_b200 as j
-    from jaxns_b200 import distributions as tfpd
+    from jaxns_b200 import _consts, distributions as tfpd, likelihoods as lk
 
     def prior_model():
         x = yield j.Prior(tfpd.Uniform(low=0.0, high=1.0), name="x")
-        return x
+        y = yield j.Prior(tfpd.Uniform(low=np.zeros(3), high=np.ones(3)), name="y")
+        return y, x
 
+    m = j.Model(prior_model, lambda y, x: -(x ** 2).sum(-1) - (y ** 2).sum(-1))
+    assert m.is_external and isinstance(m.log_likelihood, lk.ExternalLikelihood)
+    fam, D, pk, K, a, b, params = m.host_arrays()
+    assert fam == _consts.FAM_EXTERNAL == 5 and D == 4 and K == 0 and params.size == 0
+    assert m._ret_slices == [(1, 4), (0, 1)]  # variables reach the callable in prior_model's return order
+    with pytest.raises(TypeError):
+        j.Model(prior_model, 3.0)
+    # a registered family still needs its variables in order (it consumes their concatenation)
     with pytest.raises(NotImplementedError):
-        j.Model(prior_model, lambda x: -x ** 2)
+        j.Model(prior_model, lk.EggBoxLikelihood())
 
 
 def test_termination_condition_algebra_and_host_mirror():
