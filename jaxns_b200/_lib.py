@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libnsb200.so")
+# NSB200_LIB: explicit path of the shared library (kernel experiments: A/B builds side by side)
+_SO = os.environ.get("NSB200_LIB") or os.path.join(_HERE, "libnsb200.so")
 _lib = None
 
 c_f64p = ctypes.c_void_p

@@ -225,9 +225,11 @@ __device__ __forceinline__ double ndtri(double p, unsigned mask) {
         pp = tail ? pp : 0.05;  // keep the non-tail lanes on the fast paths of log / sqrt
         const double rr = sqrt(-log(pp));
         const double a = rr - 1.6, b = rr - 5.0;
-        const double v1 = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
-        const double v2 = fast_div_finite(horner8(kPpndE, b), horner8(kPpndF, b));
-        double v = (rr <= 5.0) ? v1 : v2;
+        double v = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
+        if (__any_sync(mask, rr > 5.0)) {  // far tail (p < 1.4e-11): rare, warp-uniform
+            const double v2 = fast_div_finite(horner8(kPpndE, b), horner8(kPpndF, b));
+            v = (rr <= 5.0) ? v : v2;
+        }
         v = (q < 0.0) ? -v : v;
         if (p == 0.0) v = -kInf;
         if (p == 1.0) v = kInf;

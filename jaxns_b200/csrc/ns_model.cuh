@@ -407,6 +407,13 @@ __device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> 
 }
 
 // Runtime family -> compile-time template argument, once per kernel.
+#ifdef NSB_FAST_BUILD
+#define NSB_FAMILY_SWITCH(FAMILY, ...)                                                          \
+    switch (FAMILY) {                                                                           \
+        case NSB200_FAM_GAUSS_DENSE: { constexpr int kFam = NSB200_FAM_GAUSS_DENSE; __VA_ARGS__; } break;       \
+        default: break;                                                                         \
+    }
+#else
 #define NSB_FAMILY_SWITCH(FAMILY, ...)                                                          \
     switch (FAMILY) {                                                                           \
         case NSB200_FAM_GAUSS_DENSE: { constexpr int kFam = NSB200_FAM_GAUSS_DENSE; __VA_ARGS__; } break;       \
@@ -416,5 +423,6 @@ __device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> 
         case NSB200_FAM_SHELLS: { constexpr int kFam = NSB200_FAM_SHELLS; __VA_ARGS__; } break;                 \
         default: break;                                                                         \
     }
+#endif
 
 }  // namespace nsb

@@ -165,7 +165,8 @@ __host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool
     return (size_t) G * DPL * P + (slice ? (size_t) G * (kPre + 2) : 0);
 }
 
-// W > 1 ("warp team"): the CTA is ONE chain run by W warps that execute the same program; in every
+// W > 1 ("warp team", experiment, NOT instantiated: measured slower on B200 -- register spills at 2 warps x
+// 1600 chains -- kept as the starting point of a producer/consumer split): the CTA is ONE chain run by W warps that execute the same program; in every
 // shrink round warp w evaluates the w-th speculative proposal and the W log-likelihoods are exchanged
 // through shared memory around one __syncthreads().  Unlike the in-warp batch (P) this adds real
 // parallelism: a config-2 sized problem leaves most warp slots and issue cycles idle, and the
@@ -404,6 +405,15 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     loglik_group<G, DPL, P, FAM>(sm, g, row, Xp, scratch, logL);
                     NSB_TICK(5)  // likelihood
                     prof[8] += 1;
+                    {
+                        bool tl = false, tl2 = false;
+                        for (int s = 0; s < DPL; ++s) {
+                            tl |= !(-log(4.0 * (x[0][s] * (1.0 - x[0][s]))) < 6.25);
+                            tl2 |= !(fabs(x[0][s] - 0.5) <= 0.425);
+                        }
+                        prof[10] += __any_sync(g.m(), tl) ? 1 : 0;
+                        prof[11] += __any_sync(g.m(), tl2) ? 1 : 0;
+                    }
                 }
 #else
                 forward_group<G, DPL, P, FAM>(sm, g, row, x, scratch, logL);
@@ -492,14 +502,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) 
     } else {
         NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, false>(a, smem));
     }
-}
-
-// One chain per CTA, W warps per chain (see slice_chains_body).  Register budget: 2 warps x 1600
-// chains must all be resident (21.6 warps per SM), hence the occupancy hint.
-template <int DPL, int W>
-__global__ void __launch_bounds__(32 * W, 22 / W) k_slice_chains_team(SliceArgs a) {
-    extern __shared__ double smem[];
-    NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<32, DPL, 1, kFam, true, W>(a, smem));
 }
 
 __global__ void k_alpha_table(int S, double *out) {

@@ -98,6 +98,16 @@ static int set_smem(KernelT kernel, size_t bytes) {
 }
 
 // Compile-time (G, DPL) instantiations: G < 32 only with DPL == 1.
+// -DNSB_FAST_BUILD (kernel experiments): only the config-2 geometry (G = 32, DPL = 1), P = 1, dense Gaussian.
+#ifdef NSB_FAST_BUILD
+#define NSB_DISPATCH_GEOM(GEOM, ...)                                                \
+    if ((GEOM).G == 32 && (GEOM).DPL == 1) {                                        \
+        constexpr int kG = 32, kDPL = 1;                                            \
+        __VA_ARGS__;                                                                \
+    } else {                                                                        \
+        return fail("NSB_FAST_BUILD supports only 17 <= D <= 32");                  \
+    }
+#else
 #define NSB_DISPATCH_GEOM(GEOM, ...)                                                \
     if ((GEOM).G == 32) {                                                           \
         switch ((GEOM).DPL) {                                                       \
@@ -117,6 +127,7 @@ static int set_smem(KernelT kernel, size_t bytes) {
             default: return fail("unsupported group size %d", (GEOM).G);            \
         }                                                                           \
     }
+#endif
 
 // Number of proposals evaluated speculatively per shrink round (ns_slice.cuh).  NSB200_SPEC
 // overrides it for the D <= 32 instantiation (tuning knob; results do not depend on it).
@@ -296,58 +307,27 @@ static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st
     return 0;
 }
 
-// Warps per chain (slice_chains_body W): 2 when the problem is too small to fill the GPU with one warp
-// per chain (the case where chain latency, not throughput, sets the kernel time).  NSB200_TEAM=1/2
-// overrides.
-static int pick_team(const SliceArgs &a, const Geometry &g) {
-    if (!(g.G == 32 && a.pre_dirs)) return 1;
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    const long long n = a.chain_end - a.chain_begin;
-    int W = 1;  // measured slower on B200 so far (register spills at 2 warps x 1600 chains): opt-in only
-    (void) n;
-    if (const char *e = getenv("NSB200_TEAM")) {
-        const int v = atoi(e);
-        if (v == 1 || v == 2) W = v;
-    }
-    return W;
-}
-
-template <int DPL, int W>
-static int launch_team_t(const SliceArgs &a, cudaStream_t st) {
-    const long long n = a.chain_end - a.chain_begin;
-    const size_t smem = 8 * (model_smem_doubles(a.model.family, a.model.D, 32, DPL, a.model.K) +
-                             W * chain_smem_doubles(32, DPL, 1, true) + 2 * W);
-    if (set_smem(k_slice_chains_team<DPL, W>, smem)) return 1;
-    k_slice_chains_team<DPL, W><<<(unsigned) n, 32 * W, smem, st>>>(a);
-    return 0;
-}
-
 static int launch_slice(const SliceArgs &a, cudaStream_t st) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
     if (a.chain_end <= a.chain_begin) return 0;
-    if (pick_team(a, g) == 2) {
-        int rc;
-        switch (g.DPL) {
-            case 1: rc = launch_team_t<1, 2>(a, st); break;
-            case 2: rc = launch_team_t<2, 2>(a, st); break;
-            case 4: rc = launch_team_t<4, 2>(a, st); break;
-            default: rc = launch_team_t<8, 2>(a, st); break;
-        }
-        if (rc) return rc;
-        NSB_LAUNCH_CHECK();
-        return 0;
-    }
     const int P = pick_spec(g);
     if (g.G == 32 && g.DPL == 1) {
         int rc;
+#ifdef NSB_FAST_BUILD
+        rc = launch_slice_t<32, 1, 1>(a, g, st);
+#else
         if (P == 1) rc = launch_slice_t<32, 1, 1>(a, g, st);
         else if (P == 4) rc = launch_slice_t<32, 1, 4>(a, g, st);
         else rc = launch_slice_t<32, 1, 2>(a, g, st);
+#endif
         if (rc) return rc;
     } else {
+#ifdef NSB_FAST_BUILD
+        return fail("NSB_FAST_BUILD supports only 17 <= D <= 32");
+#else
         NSB_DISPATCH_GEOM(g, { if (launch_slice_t<kG, kDPL, 2>(a, g, st)) return 1; });
+#endif
     }
     NSB_LAUNCH_CHECK();
     return 0;

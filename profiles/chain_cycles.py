@@ -26,3 +26,4 @@ tot = v[:8].sum()
 print(f"chain 0 of every iteration: {slices:.0f} slices, {evals:.0f} eval rounds, {tot:.0f} cycles total, {tot/evals:.0f} cycles per eval")
 for n, c in zip(names, v[:8]):
     print(f"  {n:18s} {c/tot:6.3f}  {c/evals:8.1f} cyc/eval  {c/slices:8.1f} cyc/slice")
+print(f"  evaluations with a lane in the Giles tail (w >= 6.25): {v[10]/evals:.4f}; in the AS241 tail (|q| > 0.425): {v[11]/evals:.4f}")

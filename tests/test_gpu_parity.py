@@ -527,3 +527,43 @@ def test_external_public_api_gaussian_logZ(torch_cuda, oracle):
     true = oracle.gauss_analytic_logZ(D)
     assert abs(res.log_Z_mean - true) < 3 * res.log_Z_uncert, (res.log_Z_mean, true, res.log_Z_uncert)
     assert res.total_num_likelihood_evaluations > 0 and res.samples["x"].shape[1] == D
+
+
+def test_prior_quantile_accuracy_vs_scipy(torch_cuda):
+    """The device normal quantile (AS241 central + tails behind warp-uniform votes) against scipy's Cephes ndtri --
+    the algorithm tfp's Normal.quantile (the reference's prior transform) evaluates: <= 2e-15 relative from the
+    far tails to the centre, exact infinities at 0 and 1."""
+    torch = torch_cuda
+    import ctypes
+    from scipy.special import ndtri
+    import jaxns_b200 as j
+    from jaxns_b200 import _lib, distributions as tfpd, likelihoods as lk
+    D = 32
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Normal(loc=np.zeros(D), scale=np.ones(D)), name="x")
+        return x
+
+    model = j.Model(prior_model, lk.DenseGaussianLikelihood(np.zeros(D), covariance_matrix=np.eye(D)))
+    rng = np.random.default_rng(0)
+    n = 4096
+    U = rng.uniform(0, 1, (n, D))
+    U[:512] = 10.0 ** rng.uniform(-300, -1, (512, D))            # left tail down to 1e-300
+    U[512:1024] = 1.0 - 10.0 ** rng.uniform(-16, -1, (512, D))  # right tail up to 1 - 1e-16
+    U[1024:1536] = 0.5 + rng.uniform(-1e-6, 1e-6, (512, D))     # centre
+    U[1536:1600, ::2] = 10.0 ** rng.uniform(-12, -10, (64, D // 2))  # mixes far-tail and central lanes in one group
+    U = np.clip(U, 1e-300, 1 - 2.0 ** -53)
+    Ut = torch.from_numpy(U).cuda()
+    X = torch.empty_like(Ut)
+    d = model.desc()
+    _lib.check(_lib.lib().nsb200_transform_batch(ctypes.byref(d), _lib.ptr(Ut), ctypes.c_int64(n), _lib.ptr(X),
+                                                  _lib.stream_arg()))
+    got, exp = X.cpu().numpy(), ndtri(U)
+    rel = np.abs(got - exp) / np.maximum(np.abs(exp), 1e-300)
+    assert rel.max() <= 2e-15, rel.max()
+    edge = torch.tensor([[0.0, 1.0, 0.5] + [0.25] * (D - 3)], dtype=torch.float64, device="cuda")
+    Xe = torch.empty_like(edge)
+    _lib.check(_lib.lib().nsb200_transform_batch(ctypes.byref(d), _lib.ptr(edge), ctypes.c_int64(1), _lib.ptr(Xe),
+                                                  _lib.stream_arg()))
+    xe = Xe.cpu().numpy()[0]
+    assert xe[0] == -np.inf and xe[1] == np.inf and xe[2] == 0.0
