@@ -90,8 +90,9 @@ __global__ void k_finalize_ctl(DevCtl *ctl, long long count, long long capacity)
 // Rank of every element of the next live set under a stable ascending sort of
 // [new_0 .. new_{m-1}, survivor_m .. survivor_{N-1}]  (sharded_static.py:269-275): new rows come
 // first on ties.  packed rows: [U[D], logL, nevals, ...].
-constexpr int kRankLanes = 8;  // lanes cooperating on one element's count
-
+// LANES = lanes cooperating on one element's count: 32 for small live sets (the kernel sits on the critical path
+// between two slice kernels, more CTAs shorten it), 8 for large ones (every CTA re-reads all m new keys).
+template <int kRankLanes>
 __global__ void __launch_bounds__(256) k_merge_rank(const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
                                                     const double *packed, long long row_doubles, int D,
                                                     long long m, long long N, unsigned *rank_out) {

@@ -39,6 +39,18 @@ __device__ unsigned long long g_prof[16];
 #define NSB_TICK(k)
 #endif
 
+#ifdef NSB_TIMELINE
+// globaltimer stamps of the generator / slice kernel pair of the latest body (debug builds only):
+// [0] first generator CTA start, [1] last generator CTA end, [2] first slice CTA start, [3] last slice CTA end,
+// [4..7] the same accumulated relative to [0] over all bodies, [8] bodies
+__device__ unsigned long long g_tl[16];
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#endif
+
 // Uniforms per slice drawn ahead by the lane-parallel precompute (shrink steps beyond that fall
 // back to walking the run_key chain inline).
 constexpr int kPre = 8;
@@ -497,6 +509,10 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
 template <int G, int DPL, int P>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) {
     extern __shared__ double smem[];
+#ifdef NSB_TIMELINE
+    if (threadIdx.x == 0) atomicMin(&g_tl[2], gtime());
+    struct Stamp { __device__ ~Stamp() { if (threadIdx.x == 0) atomicMax(&g_tl[3], gtime()); } } stamp;
+#endif
     if (a.pre_dirs) {
         NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, true>(a, smem));
     } else {
@@ -525,6 +541,13 @@ struct StreamArgs {
 };
 
 __global__ void __launch_bounds__(1024) k_chain_streams(StreamArgs a) {
+    // Programmatic dependent launch: this CTA is resident, so the slice kernel queued behind the generator may
+    // start now and take the SMs the generator's CTAs did not claim (no-op for a normally launched successor).
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#ifdef NSB_TIMELINE
+    if (threadIdx.x == 0) atomicMin(&g_tl[0], gtime());
+    struct Stamp { __device__ ~Stamp() { if (threadIdx.x == 0) atomicMax(&g_tl[1], gtime()); } } stamp;
+#endif
     Key base_key = a.key;
     if (a.ctl) base_key = a.ctl->stream_key[a.key_slot];
     const int lane = threadIdx.x & 31;

@@ -296,18 +296,31 @@ static int slice_threads(const Geometry &g) {
     return tpb < g.G ? g.G : tpb;
 }
 
+// pdl: programmatic dependent launch -- the kernel may start as soon as every CTA of the PREVIOUS kernel in
+// the stream has executed griddepcontrol.launch_dependents (or exited), instead of after its completion.
 template <int G, int DPL, int P>
-static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st) {
+static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st, bool pdl) {
     const long long n = a.chain_end - a.chain_begin;
     const int tpb = slice_threads(g);
     const size_t per_chain = chain_smem_doubles(g.G, g.DPL, P, true);
     const size_t smem = 8 * (model_smem_doubles(a.model.family, a.model.D, g.G, g.DPL, a.model.K) + (tpb / g.G) * per_chain);
     if (set_smem(k_slice_chains<G, DPL, P>, smem)) return 1;
-    k_slice_chains<G, DPL, P><<<grid_for(n, tpb / G), tpb, smem, st>>>(a);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned) grid_for(n, tpb / G));
+    cfg.blockDim = dim3((unsigned) tpb);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    NSB_CUDA(cudaLaunchKernelEx(&cfg, k_slice_chains<G, DPL, P>, a));
     return 0;
 }
 
-static int launch_slice(const SliceArgs &a, cudaStream_t st) {
+static int launch_slice(const SliceArgs &a, cudaStream_t st, bool pdl = false) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
     if (a.chain_end <= a.chain_begin) return 0;
@@ -315,18 +328,18 @@ static int launch_slice(const SliceArgs &a, cudaStream_t st) {
     if (g.G == 32 && g.DPL == 1) {
         int rc;
 #ifdef NSB_FAST_BUILD
-        rc = launch_slice_t<32, 1, 1>(a, g, st);
+        rc = launch_slice_t<32, 1, 1>(a, g, st, pdl);
 #else
-        if (P == 1) rc = launch_slice_t<32, 1, 1>(a, g, st);
-        else if (P == 4) rc = launch_slice_t<32, 1, 4>(a, g, st);
-        else rc = launch_slice_t<32, 1, 2>(a, g, st);
+        if (P == 1) rc = launch_slice_t<32, 1, 1>(a, g, st, pdl);
+        else if (P == 4) rc = launch_slice_t<32, 1, 4>(a, g, st, pdl);
+        else rc = launch_slice_t<32, 1, 2>(a, g, st, pdl);
 #endif
         if (rc) return rc;
     } else {
 #ifdef NSB_FAST_BUILD
         return fail("NSB_FAST_BUILD supports only 17 <= D <= 32");
 #else
-        NSB_DISPATCH_GEOM(g, { if (launch_slice_t<kG, kDPL, 2>(a, g, st)) return 1; });
+        NSB_DISPATCH_GEOM(g, { if (launch_slice_t<kG, kDPL, 2>(a, g, st, pdl)) return 1; });
 #endif
     }
     NSB_LAUNCH_CHECK();
@@ -729,6 +742,15 @@ struct NsEngine {
     double slice_ms = 0.0;
     long long slice_launches = 0, all_launches = 0;
     bool initialised = false;
+    // Where the generator of body b + 2 runs relative to the slice kernel of body b (see enqueue_streams):
+    //   0  side stream, released together with the slice kernel (placement is a race between the two grids)
+    //   1  same stream, slice kernel launched as its programmatic dependent: disjoint SM partitions
+    //   2  same stream, before the slice kernel, whole GPU each (serial)
+    //   3  side stream, released when the slice kernel has finished: overlaps the merge / register kernels
+    int gen_mode = 3;
+    bool pdl = false;  // gen_mode == 1
+    cudaEvent_t ev_slice = nullptr;
+    bool tables_ready = false;  // seed table / evidence-term tables / alpha table depend only on (N, S): built once
     // family EXTERNAL: chain state of the split slice step (ns_split.cuh) for this rank's chains
     bool external = false;
     void *split_ws = nullptr;
@@ -753,6 +775,7 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
     if (e->progress) cudaFreeHost((void *) e->progress);
     for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
     if (e->ev_keys) cudaEventDestroy(e->ev_keys);
+    if (e->ev_slice) cudaEventDestroy(e->ev_slice);
     for (int b = 0; b < 3; ++b)
         if (e->ev_streams[b]) cudaEventDestroy(e->ev_streams[b]);
     if (e->side) cudaStreamDestroy(e->side);
@@ -787,6 +810,9 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     e->row_doubles = (e->D + 2) + e->k * (e->D + 1);
     e->packed_rows = e->N > e->m ? e->N : e->m;  // the init pass packs all N prior draws
     e->external = cfg->model.family == NSB200_FAM_EXTERNAL;
+    if (const char *pe = getenv("NSB200_GEN_MODE")) e->gen_mode = atoi(pe);
+    if (e->gen_mode < 0 || e->gen_mode > 3) e->gen_mode = 3;
+    e->pdl = e->gen_mode == 1;
     const size_t D = e->D;
     int rc = 0;
     for (int b = 0; b < 2 && !rc; ++b) {
@@ -826,6 +852,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         }
         if (!rc && cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate failed");
         if (!rc && cudaEventCreateWithFlags(&e->ev_keys, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+        if (!rc && cudaEventCreateWithFlags(&e->ev_slice, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
         for (int b = 0; b < 3; ++b)
             if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     }
@@ -879,7 +906,16 @@ static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
     return t;
 }
 
-static int enqueue_streams(NsEngine *e, int buf);
+static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t after);
+
+static void launch_merge_rank(NsEngine *e, long long m_new, cudaStream_t st) {
+    if (e->N <= 16384)
+        k_merge_rank<32><<<grid_for(e->N * 32, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles,
+                                                                  e->D, m_new, e->N, e->rank);
+    else
+        k_merge_rank<8><<<grid_for(e->N * 8, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles,
+                                                                e->D, m_new, e->N, e->rank);
+}
 
 static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond, nsb200_stream_t stream,
                               const double *extU, const double *extL, const long long *extN) {
@@ -907,12 +943,18 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
         NSB_CUDA(cudaStreamSynchronize(e->side));
         NSB_CUDA(cudaEventRecord(e->ev_keys, st));
         e->body = 0;
-        if (enqueue_streams(e, 0)) return 1;  // bodies 0 and 1; body b + 2 follows the slice kernel of body b
-        if (enqueue_streams(e, 1)) return 1;
+        if (enqueue_streams(e, 0, st, e->ev_keys)) return 1;  // bodies 0 and 1; body b + 2 is enqueued by body b
+        if (enqueue_streams(e, 1, st, e->ev_keys)) return 1;
     }
-    if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
-    k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
-    k_alpha_table<<<4, 256, 0, st>>>(e->cfg.num_slices, e->alpha_tab);
+    const bool build_tables = !e->tables_ready;
+    if (build_tables) {
+        // The seed table is a serial logaddexp recurrence (it has to round like the reference's sequential
+        // cumulative_logsumexp: 36 us per 100 entries); it only depends on N, so repeated runs reuse it.
+        if (nsb200_seed_table(e->N, e->seed_table, stream)) return 1;
+        k_ev_tables<<<64, 256, 0, st>>>(e->N, e->tabT, e->tabT2, e->tabt);
+        k_alpha_table<<<4, 256, 0, st>>>(e->cfg.num_slices, e->alpha_tab);
+        e->tables_ready = true;
+    }
     // N prior draws (replicated on every rank), packed, ranked (stable argsort) and scattered
     const double *tmpU = e->live[1].U, *tmpL = e->live[1].logL;
     const long long *tmpN = e->live[1].nevals;
@@ -924,8 +966,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
         return 1;
     }
     k_pack_rows<<<592, 256, 0, st>>>(tmpU, tmpL, tmpN, e->N, D, e->packed, e->row_doubles);
-    k_merge_rank<<<grid_for(e->N * kRankLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
-                                                       e->N, e->N, e->rank);
+    launch_merge_rank(e, e->N, st);
     DeadStore nodead = e->dead;
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->N, e->N, 0,
                                           e->rank, nodead);
@@ -936,7 +977,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
                                          e->N, e->tc, 1, e->tabT, e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     NSB_LAUNCH_CHECK();
-    e->all_launches += 9;
+    e->all_launches += build_tables ? 9 : 6;
     e->initialised = true;
     return 0;
 }
@@ -998,10 +1039,12 @@ static void drain_events(NsEngine *e) {
     e->ev_used = 0;
 }
 
-// Enqueues, on the engine's side stream, the generation of the chain streams of the body whose
-// sample_key is ctl->stream_key[buf] (valid once ev_keys has fired) into buffer `buf`.
-static int enqueue_streams(NsEngine *e, int buf) {
-    NSB_CUDA(cudaStreamWaitEvent(e->side, e->ev_keys, 0));
+// Enqueues the generation of the chain streams of the body whose sample_key is ctl->stream_key[buf] into
+// buffer `buf`; `after` = event the side stream waits for first (gen_mode 0 and 3).  See NsEngine::gen_mode.
+static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t after) {
+    const bool own_stream = e->gen_mode == 0 || e->gen_mode == 3;
+    cudaStream_t gs = own_stream ? e->side : st;
+    if (own_stream) NSB_CUDA(cudaStreamWaitEvent(e->side, after, 0));
     const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
     StreamArgs sa;
     sa.key = Key{0, 0};
@@ -1015,24 +1058,40 @@ static int enqueue_streams(NsEngine *e, int buf) {
     sa.us = e->pre_us[buf];
     sa.rkeys = e->pre_rkeys[buf];
     const long long warps = (end - begin) * ((sa.S + 31) / 32);
-    // The generator is throughput-bound, the chains are latency-bound: sharing an SM starves the chains.
-    // So the generator gets its own SMs: a few persistent CTAs of 1024 threads that each claim (almost) all
-    // shared memory of an SM, launched just before the slice kernel, whose CTAs then cannot land there.
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-    int gen_sms = (sms * 43) / 100;  // measured optimum on B200 at config 2 (64 of 148): see DESIGN.md
-    if (const char *pe = getenv("NSB200_GEN_SMS")) gen_sms = atoi(pe) > 0 ? atoi(pe) : gen_sms;
-    if ((long long) gen_sms * 32 > warps) gen_sms = (int) ((warps + 31) / 32);
-    static bool attr_set = false;
-    const size_t gen_smem = 200 * 1024;
-    if (!attr_set) {
-        NSB_CUDA(cudaFuncSetAttribute(k_chain_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gen_smem));
-        attr_set = true;
+    int gen_ctas, tpb;
+    size_t gen_smem = 0;
+    if (e->gen_mode <= 1) {
+        // The generator is throughput-bound, the chains are latency-bound: sharing an SM starves the chains.
+        // Partition modes give the generator its own SMs: persistent CTAs of 1024 threads that each claim ALL
+        // shared memory of an SM, so that no slice CTA can land next to them.
+        gen_ctas = (sms * 43) / 100;
+        tpb = 1024;
+        static size_t optin_smem = 0;
+        if (!optin_smem) {
+            int optin = 0;
+            optin_smem = 227 * 1024;
+            if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0) == cudaSuccess && optin > 0) optin_smem = (size_t) optin;
+            NSB_CUDA(cudaFuncSetAttribute(k_chain_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) optin_smem));
+        }
+        gen_smem = e->gen_mode == 1 ? optin_smem : 200 * 1024;
+    } else {
+        // Whole-GPU modes: one persistent CTA of 32 warps per SM (measured: 16 warps per SM lose more generator
+        // throughput than the room they leave for the merge / register-update kernels gains).
+        gen_ctas = e->gen_mode == 3 ? sms - 8 : sms;  // mode 3: a few SMs stay free for the kernels of step_end
+        tpb = 1024;
     }
-    k_chain_streams<<<gen_sms, 1024, gen_smem, e->side>>>(sa);
+    if (const char *pe = getenv("NSB200_GEN_SMS")) gen_ctas = atoi(pe) > 0 ? atoi(pe) : gen_ctas;
+    if (const char *pe = getenv("NSB200_GEN_TPB")) tpb = (atoi(pe) >= 32 && atoi(pe) <= 1024) ? (atoi(pe) / 32) * 32 : tpb;
+    const long long wpc = tpb / 32;
+    if ((long long) gen_ctas * wpc > warps) gen_ctas = (int) ((warps + wpc - 1) / wpc);
+    k_chain_streams<<<gen_ctas, tpb, gen_smem, gs>>>(sa);
     NSB_LAUNCH_CHECK();
-    NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
-    trace_mark(e, "  generator end (side)", e->side);
+    if (own_stream) {
+        NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
+        trace_mark(e, "  generator end (side)", e->side);
+    }
     e->all_launches += 1;
     return 0;
 }
@@ -1043,7 +1102,8 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     const int D = e->D;
     // streams of THIS body were enqueued two steps ago (or by init) on the side stream
     trace_mark(e, "step_begin enqueue", st);
-    if (e->pre_dirs[0]) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->body % 3], 0));
+    const bool own_stream = e->gen_mode == 0 || e->gen_mode == 3;
+    if (e->pre_dirs[0] && own_stream) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->body % 3], 0));
     trace_mark(e, "after wait streams", st);
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
@@ -1075,18 +1135,30 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.pre_dirs = e->pre_dirs[buf];
     a.pre_us = e->pre_us[buf];
     a.pre_rkeys = e->pre_rkeys[buf];
-    if (e->pre_dirs[0]) {
-        // streams of body + 2: generated on dedicated SMs while this body's chains run on the others
-        NSB_CUDA(cudaEventRecord(e->ev_keys, st));
-        if (enqueue_streams(e, (int) ((e->body + 2) % 3))) return 1;
-    }
     cudaEvent_t e0 = next_event(e), e1 = next_event(e);
-    cudaEventRecord(e0, st);
-    trace_mark(e, "slice start", st);
-    if (launch_slice(a, st)) return 1;
+    const int nbuf = (int) ((e->body + 2) % 3);  // streams of body + 2
+    if (e->pdl) {  // nothing may sit between the generator and its programmatic dependent in the stream
+        cudaEventRecord(e0, st);
+        trace_mark(e, "slice start", st);
+    }
+    if (e->pre_dirs[0] && e->gen_mode == 0) {
+        NSB_CUDA(cudaEventRecord(e->ev_keys, st));
+        if (enqueue_streams(e, nbuf, st, e->ev_keys)) return 1;
+    }
+    if (e->pre_dirs[0] && (e->gen_mode == 1 || e->gen_mode == 2) && enqueue_streams(e, nbuf, st, nullptr)) return 1;
+    if (!e->pdl) {
+        cudaEventRecord(e0, st);
+        trace_mark(e, "slice start", st);
+    }
+    if (launch_slice(a, st, e->pdl && e->pre_dirs[0] != nullptr)) return 1;
     cudaEventRecord(e1, st);
     trace_mark(e, "slice end", st);
     NSB_LAUNCH_CHECK();
+    if (e->pre_dirs[0] && e->gen_mode == 3) {
+        // the generator takes the SMs when the chains are done and shares them with the small kernels of step_end
+        NSB_CUDA(cudaEventRecord(e->ev_slice, st));
+        if (enqueue_streams(e, nbuf, st, e->ev_slice)) return 1;
+    }
     e->body += 1;
     e->slice_launches += 1;
     e->all_launches += 3;
@@ -1097,8 +1169,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
-    k_merge_rank<<<grid_for(e->N * kRankLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D,
-                                                       e->m, e->N, e->rank);
+    launch_merge_rank(e, e->m, st);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
     k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
@@ -1324,6 +1395,19 @@ extern "C" int nsb200_bench_fp64_fma(int64_t iters, double *out_tflops) {
     *out_tflops = best;
     return 0;
 }
+
+#ifdef NSB_TIMELINE
+// reset = 1: arm the stamps for the next generator / slice pair; returns the current stamps first
+extern "C" int nsb200_debug_timeline(unsigned long long *out4, int reset) {
+    cudaDeviceSynchronize();
+    if (out4) cudaMemcpyFromSymbol(out4, nsb::g_tl, 4 * 8);
+    if (reset) {
+        unsigned long long z[4] = {~0ull, 0ull, ~0ull, 0ull};
+        cudaMemcpyToSymbol(nsb::g_tl, z, 4 * 8);
+    }
+    return 0;
+}
+#endif
 
 #ifdef NSB_PROFILE
 extern "C" int nsb200_debug_profile(unsigned long long *out16, int reset) {
