@@ -147,7 +147,7 @@ def try_real_jaxns(num_live, seed):
     return int(res.total_num_likelihood_evaluations), dt, os.cpu_count()
 
 
-def run_reference(args):
+def run_reference(args, emit=print):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -160,7 +160,7 @@ def run_reference(args):
             tot_e += e
             tot_t += t
         value = tot_e / tot_t
-        print(json.dumps({
+        emit(json.dumps({
             "impl": "reference", "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -189,13 +189,13 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port of jaxns 2.6.9 (reference needs jax/tfp: not installable offline)",
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # --------------------------------------------------------------------------------------------------
 # native arm
 # --------------------------------------------------------------------------------------------------
-def run_native(args):
+def run_native(args, emit=print):
     import torch
     import torch.distributed as dist
     import jaxns_b200 as j
@@ -349,7 +349,7 @@ def run_native(args):
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -361,10 +361,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    # The contract is ONE JSON line on stdout: everything else that libraries print there (NCCL's version banner,
+    # the "Running over N devices." notice) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lambda text: lines.append(text)  # noqa: E731
+    try:
+        if args.impl == "reference":
+            run_reference(args, emit)
+        else:
+            run_native(args, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for text in lines:
+        print(text, flush=True)
 
 
 if __name__ == "__main__":

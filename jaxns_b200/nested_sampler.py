@@ -136,7 +136,8 @@ class ShardedStaticNestedSampler:
         if self.devices is None:
             self.devices = list(range(self._world))
         if len(self.devices) > 1 and self._rank == 0:
-            print(f"Running over {len(self.devices)} devices.")
+            import sys
+            print(f"Running over {len(self.devices)} devices.", file=sys.stderr)
         self.num_live_points = round_up_num_live_points(
             init_num_live_points=self.num_live_points,
             shell_frac=self.shell_fraction,
