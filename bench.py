@@ -285,8 +285,11 @@ def run_native(args, emit=print):
         t0 = time.perf_counter()
         m2 = make_model()  # host numpy -> device copies happen inside (Model.desc)
         ns2 = j.NestedSampler(model=m2, num_live_points=num_live)
+        t_build = time.perf_counter()
         reason, state = ns2(random.PRNGKey(max(s, 0)))
+        t_run = time.perf_counter()
         res = ns2.to_results(reason, state)
+        t_res = time.perf_counter()
         nres = res.total_num_samples  # posterior samples + weights into the user's pinned host buffers
         host = {"log_L": pinned["log_L"][:nres], "log_dp": pinned["log_dp"][:nres], "x": pinned["x"][:nres]}
         host["log_L"].copy_(res.log_L_samples, non_blocking=True)
@@ -294,6 +297,9 @@ def run_native(args, emit=print):
         host["x"].copy_(res.samples["x"], non_blocking=True)
         host["logZ"] = res.log_Z_mean
         torch.cuda.synchronize()
+        if os.environ.get("NSB200_BENCH_VERBOSE"):
+            print(f"[e2e rank {rank} rep {s}] build {1e3 * (t_build - t0):.1f} ms | run {1e3 * (t_run - t_build):.1f} | "
+                  f"to_results {1e3 * (t_res - t_run):.1f} | d2h {1e3 * (time.perf_counter() - t_res):.1f}", file=sys.stderr)
         if s >= 0:
             e2e_t += time.perf_counter() - t0
             e2e_evals += res.total_num_likelihood_evaluations

@@ -1170,8 +1170,10 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
     launch_merge_rank(e, e->m, st);
+    trace_mark(e, "merge_rank end", st);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
+    trace_mark(e, "merge_scatter end", st);
     k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
                                          e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     NSB_LAUNCH_CHECK();

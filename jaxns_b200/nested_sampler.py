@@ -9,6 +9,9 @@ are all-gathered over NCCL between the two halves of a step.
 import ctypes
 import dataclasses
 import math
+import os
+import sys
+import time
 import warnings
 from typing import Any, List, Optional, Tuple
 
@@ -172,7 +175,10 @@ class ShardedStaticNestedSampler:
         """_run (sharded_static.py:775-851): init, (no-op) uniform phase, slice phase, final append."""
         _lib.require_cuda()
         L = _lib.lib()
+        t_dbg = time.perf_counter()
         eng = self._make_engine()
+        if os.environ.get("NSB200_LOOP_DEBUG"):
+            print(f"[loop rank {self._rank}] engine create {1e3 * (time.perf_counter() - t_dbg):.1f} ms", file=sys.stderr)
         stream = _lib.stream_arg()
         plain = isinstance(term_cond, TerminationCondition)
         if plain:
@@ -209,10 +215,16 @@ class ShardedStaticNestedSampler:
                 # asynchronous poll would let ranks launch different numbers of collectives).
                 burst = 4
                 _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                dbg = os.environ.get("NSB200_LOOP_DEBUG")
                 while not reg.done:
+                    t0 = time.perf_counter()
                     for _ in range(burst):
                         one_body()
+                    t1 = time.perf_counter()
                     _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                    if dbg and time.perf_counter() - t0 > 0.02:
+                        print(f"[loop rank {self._rank}] slow burst at iteration {reg.iteration}: enqueue "
+                              f"{1e3 * (t1 - t0):.1f} ms, wait {1e3 * (time.perf_counter() - t1):.1f} ms", file=sys.stderr)
             else:
                 _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
                 while True:

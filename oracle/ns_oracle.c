@@ -6,10 +6,12 @@
  * cpu_baseline / --impl reference legs of bench.py).
  *
  * Parity status: the reference (pure Python on JAX + TFP) cannot be imported in the
- * build container (no jax / jaxlib / tfp wheels), so per-chain trajectories and the
- * partitionable key layout are "parity unpinned" against a live jaxns run.  What IS
- * pinned: Threefry-2x32 against the Random123 KATs and the published legacy
- * jax.random.split(PRNGKey(0)) words, ndtri against scipy's Cephes ndtri, erf_inv
+ * build container (no jax / jaxlib / tfp wheels), so per-chain trajectories, the word
+ * order of 64-bit draws and XLA's f64 erf_inv rounding are "parity unpinned" against a
+ * live jaxns run.  What IS pinned: Threefry-2x32 against the Random123 KATs and the
+ * published legacy jax.random.split(PRNGKey(0)) words, the partitionable split/counter
+ * layout + uniform/normal recipe against the key(42) values printed in the JAX
+ * documentation's PRNG tutorial, ndtri against scipy's Cephes ndtri, erf_inv
  * against scipy.special.erfinv, tree counts against the reference's golden vectors
  * (src/jaxns/internals/tests/test_tree_structure.py:19-70) and the log-space
  * identities of src/jaxns/internals/tests/test_log_semiring.py.

@@ -4,9 +4,13 @@ CPU oracle for the jaxns 2.6.9 static nested-sampling hot path (numpy driver ove
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the cpu_baseline /
 ``--impl reference`` legs of bench.py.  Nothing under jaxns_b200/ imports this module.
 
-Parity status: "parity unpinned" for RNG layout and per-chain trajectories (jax/jaxlib/tfp are not
-installable in the build container; see ns_oracle.c header); pinned for Threefry KATs, ndtri (scipy
-Cephes), erf_inv (scipy), tree-count golden vectors and log-space identities.
+Parity status: "parity unpinned" against a LIVE jaxns run (jax/jaxlib/tfp are not installable in the
+build container; see ns_oracle.c header): per-chain trajectories, the word order of 64-bit draws and
+XLA's f64 erf_inv rounding have no external vector.  Pinned: Threefry Random123 KATs; the partitionable
+split / counter layout, 32-bit draws and the uniform -> normal recipe against the values the JAX
+documentation publishes for key(42) (tests/test_oracle_cpu.py::
+test_partitionable_stream_matches_published_jax_tutorial); ndtri (scipy Cephes), erf_inv (scipy),
+tree-count golden vectors of the reference's own tests, log-space identities.
 
 Reference paths are relative to /root/reference/src/jaxns.
 """

@@ -7,6 +7,12 @@ from jaxns_b200 import distributions as tfpd, likelihoods as lk, random
 from jaxns_b200.internals.tree_structure import SampleTreeGraph, count_crossed_edges
 from jaxns_b200.internals.shrinkage_statistics import compute_evidence_stats, logsumexp
 
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+if world > 1:  # under torchrun: chains sharded over the ranks, as bench.py --gpus N does
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
 D = 32
 cov = np.full((D, D), 0.99) + 0.01 * np.eye(D)
 
@@ -23,8 +29,10 @@ def make():
     return j.Model(prior_model, lk.DenseGaussianLikelihood(np.full(D, 15.0), covariance_matrix=cov))
 
 
-for rep in range(3):
-    t0 = T(); m = make(); ns = j.NestedSampler(model=m, num_live_points=3200); t1 = T()
+for rep in range(4):
+    if world > 1:
+        dist.barrier()
+    t0 = T(); m = make(); ns = j.NestedSampler(model=m, num_live_points=3200 * world); t1 = T()
     reason, state = ns(random.PRNGKey(rep)); t2 = T()
     sc = state.sample_collection
     n = min(state.num_samples, sc.log_L.numel())
@@ -35,6 +43,6 @@ for rep in range(3):
     lp = m.log_prob_prior(U); t7 = T()
     res = ns.to_results(reason, state); t8 = T()
     host = [res.log_L_samples.cpu(), res.log_dp_mean.cpu(), res.samples["x"].cpu()]; t9 = T()
-    print(f"rep {rep}: build {1e3*(t1-t0):.1f} ms | run {1e3*(t2-t1):.1f} | tree {1e3*(t3-t2):.1f} | gather {1e3*(t4-t3):.1f} | "
+    print(f"[rank {rank}/{world}] rep {rep}: build {1e3*(t1-t0):.1f} ms | run {1e3*(t2-t1):.1f} | tree {1e3*(t3-t2):.1f} | gather {1e3*(t4-t3):.1f} | "
           f"evidence {1e3*(t5-t4):.1f} | transform {1e3*(t6-t5):.1f} | log_prob_prior {1e3*(t7-t6):.1f} | "
           f"to_results(total) {1e3*(t8-t7):.1f} | d2h {1e3*(t9-t8):.1f} | n={n}")

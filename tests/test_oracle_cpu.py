@@ -29,6 +29,33 @@ def test_threefry_published_jax_words(oracle):
     assert oracle.uniform(oracle.PRNGKey(42), 1)[0] == 0.4267275666499091
 
 
+def test_partitionable_stream_matches_published_jax_tutorial(oracle):
+    """Known answers published in the JAX documentation ("Pseudorandom numbers" tutorial, JAX >= 0.5, where
+    jax_threefry_partitionable -- which jaxns switches on, internals/mixed_precision.py:11-15 -- is the default):
+    random.normal(random.key(42)) = -0.028304616 and the split/draw loop 0.6057640314102173,
+    -0.21089035272598267, -0.3948981761932373.  (Values quoted from the published tutorial output; jax itself is
+    not installable here.)  They pin the partitionable split layout split(key)[i] = TF(key; 0, i), the counter
+    order, the 32-bit draw x0 ^ x1, the mantissa-fill uniform and normal = sqrt(2) * erf_inv(uniform(nextafter(-1,0), 1)).
+    float32 erf_inv is XLA's polynomial (a few ulp from scipy's), hence the 4-ulp tolerance."""
+    def normal_f32(key):
+        x0, x1 = oracle.threefry2x32(int(key[0]), int(key[1]), 0, 0)
+        bits = np.uint32(x0) ^ np.uint32(x1)
+        lo = np.nextafter(np.float32(-1), np.float32(0), dtype=np.float32)
+        f = (np.array((bits >> np.uint32(9)) | np.uint32(0x3F800000), dtype=np.uint32).view(np.float32) - np.float32(1.0))
+        u = np.maximum(lo, f * (np.float32(1.0) - lo) + lo)
+        return float(np.float32(np.sqrt(2.0)) * np.float32(special.erfinv(np.float64(u))))
+
+    key = oracle.PRNGKey(42)
+    assert abs(normal_f32(key) - (-0.028304616)) <= 4 * np.spacing(np.float32(0.028304616))
+    draws = []
+    for _ in range(3):
+        new_key, subkey = oracle.split(key, 2)
+        draws.append(normal_f32(subkey))
+        key = new_key
+    for got, want in zip(draws, [0.6057640314102173, -0.21089035272598267, -0.3948981761932373]):
+        assert abs(got - want) <= 4 * np.spacing(np.float32(abs(want))), (got, want)
+
+
 def test_golden_fixture_rng(oracle):
     g = json.load(open(os.path.join(GOLDEN, "rng_vectors.json")))
     for case in g["cases"]:
