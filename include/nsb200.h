@@ -270,6 +270,12 @@ int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *log_L, const
 int nsb200_logsumexp(const double *x, int64_t n, double *out, void *workspace, int64_t workspace_bytes,
                      nsb200_stream_t stream);
 
+/* sample_evidence (utils.py:433-476): S simulations of the shrinkage over the M dead points, simulation s with
+ * split(key, S)[s] and per-point keys split(key_s, M)[i]; log T_i = log(uniform(key_i, ())) / n_i.
+ * num_live_points float64 [M], log_L [M] (sorted), out [S] = samples of log Z.  All DEVICE pointers. */
+int nsb200_sample_evidence(const uint32_t key[2], const double *num_live_points, const double *log_L, int64_t M,
+                           int64_t S, double *out, nsb200_stream_t stream);
+
 /* ---- B2/B3: engine-owned state (ShardedStaticNestedSampler._run, sharded_static.py:775-851) -- */
 int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out);
 void nsb200_engine_destroy(NsEngine *e);

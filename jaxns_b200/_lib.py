@@ -88,7 +88,7 @@ EXPORTS = (
     "nsb200_engine_slice_profile", "nsb200_bench_fp64_fma", "nsb200_engine_progress",
     "nsb200_split_workspace_bytes", "nsb200_split_begin", "nsb200_split_accept", "nsb200_split_finish",
     "nsb200_init_propose", "nsb200_transform_batch", "nsb200_engine_init_external", "nsb200_engine_split_begin",
-    "nsb200_engine_split_accept", "nsb200_engine_split_finish",
+    "nsb200_engine_split_accept", "nsb200_engine_split_finish", "nsb200_sample_evidence",
 )
 
 

@@ -239,6 +239,60 @@ __device__ __forceinline__ double ndtri(double p, unsigned mask) {
     return x;
 }
 
+// P quantiles at once: the P central rationals are straight-line code (their dependent chains interleave), and
+// ONE warp vote decides whether the near-tail piece runs -- for the whole batch, again as straight-line code --
+// instead of P votes that serialise the proposals.  (Late in a run every lane of a chain sits in the central
+// region, so the tail must stay skippable.)  Same operations per element as ndtri(): bit-identical results.
+template <int P>
+__device__ __forceinline__ void ndtri_batch(const double (&p)[P], unsigned mask, double (&x)[P]) {
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+    double q[P];
+    bool tail[P], any_tail = false;
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        q[i] = p[i] - 0.5;
+        tail[i] = !(fabs(q[i]) <= 0.425);
+        any_tail |= tail[i];
+    }
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const double r = fma(-q[i], q[i], 0.180625);
+        x[i] = fast_div_finite(q[i] * horner8(kPpndA, r), horner8(kPpndB, r));
+    }
+    if (__any_sync(mask, any_tail)) {
+        double rr[P], v[P];
+        bool far = false;
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            double pp = (q[i] < 0.0) ? p[i] : 1.0 - p[i];
+            pp = tail[i] ? pp : 0.05;  // keep the non-tail lanes on the fast paths of log / sqrt
+            rr[i] = sqrt(-log(pp));
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const double a = rr[i] - 1.6;
+            v[i] = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
+            far |= rr[i] > 5.0;
+        }
+        if (__any_sync(mask, far)) {  // far tail (p < 1.4e-11): rare, warp-uniform
+#pragma unroll
+            for (int i = 0; i < P; ++i) {
+                const double b = rr[i] - 5.0;
+                const double v2 = fast_div_finite(horner8(kPpndE, b), horner8(kPpndF, b));
+                v[i] = (rr[i] <= 5.0) ? v[i] : v2;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            double w = (q[i] < 0.0) ? -v[i] : v[i];
+            if (p[i] == 0.0) w = -kInf;
+            if (p[i] == 1.0) w = kInf;
+            if (!(p[i] >= 0.0 && p[i] <= 1.0)) w = __longlong_as_double(0x7FF8000000000000ll);
+            x[i] = tail[i] ? w : x[i];
+        }
+    }
+}
+
 // log1p(e) for e in [0, 1] with one log and one division (Kahan): libdevice's log1p costs ~300
 // instructions, this ~70, and it is accurate to an ulp or two on that range.
 __device__ __forceinline__ double log1p_unit(double e) {

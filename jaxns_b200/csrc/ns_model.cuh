@@ -55,6 +55,18 @@ __device__ __forceinline__ double group_sum(const Grp<G> &g, double v) {
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(g.m(), v, o);
     return v;
 }
+// P independent sums, butterfly steps interleaved (the shuffle latencies of the P chains overlap)
+template <int G, int P>
+__device__ __forceinline__ void group_sum_batch(const Grp<G> &g, double (&v)[P]) {
+#pragma unroll
+    for (int o = G >> 1; o > 0; o >>= 1) {
+        double y[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) y[p] = __shfl_xor_sync(g.m(), v[p], o);
+#pragma unroll
+        for (int p = 0; p < P; ++p) v[p] += y[p];
+    }
+}
 template <int G>
 __device__ __forceinline__ double group_prod(const Grp<G> &g, double v) {
 #pragma unroll
@@ -199,6 +211,13 @@ __device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp<G>
         if (sm.prior_kind == NSB200_PRIOR_UNIFORM) {
 #pragma unroll
             for (int p = 0; p < P; ++p) X[p][s] = u[p][s] * b + a;
+        } else if (P > 1 && G >= 16) {
+            double up[P], zp[P];
+#pragma unroll
+            for (int p = 0; p < P; ++p) up[p] = u[p][s];
+            ndtri_batch<P>(up, g.m(), zp);
+#pragma unroll
+            for (int p = 0; p < P; ++p) X[p][s] = zp[p] * b + a;
         } else {
 #pragma unroll
             for (int p = 0; p < P; ++p) X[p][s] = ndtri(u[p][s], g.m()) * b + a;  // padded dims: u = 0.5, b = 0
@@ -300,8 +319,14 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
                     }
                 }
             }
+            if (P > 1) {
+                group_sum_batch<G, P>(g, q);
 #pragma unroll
-            for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * group_sum(g, q[p]);
+                for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * q[p];
+            } else {
+#pragma unroll
+                for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * group_sum(g, q[p]);
+            }
             break;
         }
         case NSB200_FAM_GAUSS_MIX_DIAG: {

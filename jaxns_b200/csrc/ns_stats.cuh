@@ -675,4 +675,44 @@ __global__ void __launch_bounds__(1024) k_logsumexp(const double *x, long long n
     }
 }
 
+// =================================================================================================
+// sample_evidence (/root/reference/src/jaxns/utils.py:433-476): S stochastic simulations of the shrinkage.
+// One CTA per simulation s: key_s = split(key, S)[s]; element i draws log T_i = log(uniform(split(key_s, M)[i], ()))
+// / n_i; log X = cumsum(log T) (block add-scan of per-thread chunk sums), dZ_i = (X_{i-1} - X_i) L_i with the
+// LogSpace subtraction of internals/log_semiring.py:28-48, log Z = logsumexp_i dZ_i (block logaddexp reduction).
+// The draws are recomputed in the second pass (2 Threefry blocks + one log each) instead of being stored:
+// the job is integer-ALU bound, S * M * 16 bytes of scratch would make it HBM bound.
+// =================================================================================================
+__device__ __forceinline__ double sample_evidence_log_T(Key ks, long long i, const double *nlive) {
+    const Key ki = split_child(ks, (uint64_t) i);
+    return log(uniform01(ki, 0)) / nlive[i];
+}
+
+__global__ void __launch_bounds__(1024) k_sample_evidence(Key key, const double *nlive, const double *logL, long long M,
+                                                          double *out) {
+    __shared__ double sh[1][34];
+    const Key ks = split_child(key, (uint64_t) blockIdx.x);
+    const long long per = (M + blockDim.x - 1) / blockDim.x;
+    const long long b = min(M, (long long) threadIdx.x * per), e = min(M, b + per);
+    double sT = 0.0;
+    for (long long i = b; i < e; ++i) sT += sample_evidence_log_T(ks, i, nlive);
+    double in1[1] = {sT}, ex1[1];
+    block_scan_excl_k<OpAdd, 1>(in1, sh, ex1);
+    __syncthreads();
+    double lX = ex1[0];  // log X before this thread's chunk (init log X = 0)
+    double acc = OpLae::id();
+    for (long long i = b; i < e; ++i) {
+        const double nx = lX + sample_evidence_log_T(ks, i, nlive);
+        const double delta = -fabs(nx - lX);
+        // X - next_X = signed_logaddexp(log X, +, log next_X, -): NaN delta (inf - inf) -> sum of the logs
+        const double diff = (delta != delta) ? lX + nx : fmax(lX, nx) + log1p(-exp(delta));
+        acc = logaddexp(acc, diff + logL[i]);
+        lX = nx;
+    }
+    double in2[1] = {acc}, ex2[1];
+    block_scan_excl_k<OpLae, 1>(in2, sh, ex2);
+    __syncthreads();
+    if (threadIdx.x == 0) out[blockIdx.x] = sh[0][32];  // CTA aggregate of the scan = logsumexp over all elements
+}
+
 }  // namespace nsb

@@ -138,7 +138,9 @@ static int pick_spec(const Geometry &g) {
             const int v = atoi(e);
             if (v == 1 || v == 2 || v == 4) return v;
         }
-        return 1;
+        // measured on config 2 (profiles/r1/spec_sweep_r1.txt): P = 2 with the batched quantile is 1.4 % faster than
+        // P = 1 end to end (rounds per slice 4.8 -> 2.6, instructions +5 %), P = 4 is 17 % slower
+        return 2;
     }
     return 2;
 }
@@ -327,7 +329,7 @@ static int launch_slice(const SliceArgs &a, cudaStream_t st, bool pdl = false) {
     const int P = pick_spec(g);
     if (g.G == 32 && g.DPL == 1) {
         int rc;
-#ifdef NSB_FAST_BUILD
+#ifdef NSB_FAST_BUILD_P1
         rc = launch_slice_t<32, 1, 1>(a, g, st, pdl);
 #else
         if (P == 1) rc = launch_slice_t<32, 1, 1>(a, g, st, pdl);
@@ -659,6 +661,17 @@ extern "C" int nsb200_logsumexp(const double *x, int64_t n, double *out, void *w
     return 0;
 }
 
+extern "C" int nsb200_sample_evidence(const uint32_t key[2], const double *num_live_points, const double *log_L,
+                                     int64_t M, int64_t S, double *out, nsb200_stream_t stream) {
+    if (!key || !out) return fail("NULL argument");
+    if (M < 0 || S < 0) return fail("negative size");
+    if (M > 0 && (!num_live_points || !log_L)) return fail("input pointer is NULL");
+    if (S == 0) return 0;
+    k_sample_evidence<<<(unsigned) S, 1024, 0, (cudaStream_t) stream>>>(Key{key[0], key[1]}, num_live_points, log_L, M, out);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // engine
 // -------------------------------------------------------------------------------------------------
@@ -811,7 +824,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     e->packed_rows = e->N > e->m ? e->N : e->m;  // the init pass packs all N prior draws
     e->external = cfg->model.family == NSB200_FAM_EXTERNAL;
     if (const char *pe = getenv("NSB200_GEN_MODE")) e->gen_mode = atoi(pe);
-    if (e->gen_mode < 0 || e->gen_mode > 3) e->gen_mode = 3;
+    if (e->gen_mode < 0 || e->gen_mode > 4) e->gen_mode = 3;
     e->pdl = e->gen_mode == 1;
     const size_t D = e->D;
     int rc = 0;
@@ -1042,7 +1055,7 @@ static void drain_events(NsEngine *e) {
 // Enqueues the generation of the chain streams of the body whose sample_key is ctl->stream_key[buf] into
 // buffer `buf`; `after` = event the side stream waits for first (gen_mode 0 and 3).  See NsEngine::gen_mode.
 static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t after) {
-    const bool own_stream = e->gen_mode == 0 || e->gen_mode == 3;
+    const bool own_stream = e->gen_mode == 0 || e->gen_mode >= 3;
     cudaStream_t gs = own_stream ? e->side : st;
     if (own_stream) NSB_CUDA(cudaStreamWaitEvent(e->side, after, 0));
     const long long begin = e->rows_per_rank * e->cfg.rank, end = begin + e->rows_per_rank;
@@ -1079,8 +1092,15 @@ static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t af
     } else {
         // Whole-GPU modes: one persistent CTA of 32 warps per SM (measured: 16 warps per SM lose more generator
         // throughput than the room they leave for the merge / register-update kernels gains).
-        gen_ctas = e->gen_mode == 3 ? sms - 8 : sms;  // mode 3: a few SMs stay free for the kernels of step_end
+        // mode 3: the merge / register-update kernels of step_end run next to the generator; the register update
+        // is a cluster of 8 CTAs that needs whole free SMs.  While the generator is short (config 2: ~150 us, about
+        // the length of step_end) leaving 28 SMs measured 3 % faster per run than leaving 8: it runs longer but off
+        // the critical path.  A long generator (config 5: D = 100, S = 500) is exposed anyway and wants every SM
+        // (profiles/r1/gen_sweep_r1.txt, config_sweep_r1.txt).
+        const bool short_gen = (double) (end - begin) * sa.S * sa.D < 32e6;
+        gen_ctas = e->gen_mode == 3 ? (short_gen && sms > 56 ? sms - 28 : sms - 8) : sms;
         tpb = 1024;
+        if (e->gen_mode == 4) tpb = 128;  // back-fill: one small CTA per SM in the registers the chains leave free
     }
     if (const char *pe = getenv("NSB200_GEN_SMS")) gen_ctas = atoi(pe) > 0 ? atoi(pe) : gen_ctas;
     if (const char *pe = getenv("NSB200_GEN_TPB")) tpb = (atoi(pe) >= 32 && atoi(pe) <= 1024) ? (atoi(pe) / 32) * 32 : tpb;
@@ -1102,7 +1122,7 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     const int D = e->D;
     // streams of THIS body were enqueued two steps ago (or by init) on the side stream
     trace_mark(e, "step_begin enqueue", st);
-    const bool own_stream = e->gen_mode == 0 || e->gen_mode == 3;
+    const bool own_stream = e->gen_mode == 0 || e->gen_mode >= 3;
     if (e->pre_dirs[0] && own_stream) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->body % 3], 0));
     trace_mark(e, "after wait streams", st);
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
@@ -1146,11 +1166,15 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
         if (enqueue_streams(e, nbuf, st, e->ev_keys)) return 1;
     }
     if (e->pre_dirs[0] && (e->gen_mode == 1 || e->gen_mode == 2) && enqueue_streams(e, nbuf, st, nullptr)) return 1;
+    if (e->pre_dirs[0] && e->gen_mode == 4) NSB_CUDA(cudaEventRecord(e->ev_keys, st));
     if (!e->pdl) {
         cudaEventRecord(e0, st);
         trace_mark(e, "slice start", st);
     }
     if (launch_slice(a, st, e->pdl && e->pre_dirs[0] != nullptr)) return 1;
+    // mode 4: the generator is enqueued AFTER the chains (their CTAs are placed first) but only waits for this
+    // body's keys, so its small CTAs run next to the chains for the whole slice kernel
+    if (e->pre_dirs[0] && e->gen_mode == 4 && enqueue_streams(e, nbuf, st, e->ev_keys)) return 1;
     cudaEventRecord(e1, st);
     trace_mark(e, "slice end", st);
     NSB_LAUNCH_CHECK();

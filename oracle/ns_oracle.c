@@ -629,6 +629,37 @@ void o_evidence_scan(double st[8], const double *logL, const double *nlive, int6
     }
 }
 
+/* sample_evidence (utils.py:433-476): S stochastic simulations of the shrinkage.  Simulation s uses
+ * key_s = split(key, S)[s] (:475) and per-sample keys split(key_s, M)[i] (:470); the scan body (:450-465)
+ * draws log T = log(uniform(key_i, ())) / n_i, next_X = X * T, dZ = (X - next_X) * L, next_Z = Z + dZ, with
+ * LogSpace arithmetic (internals/log_semiring.py:28-48,132-178): X - next_X = signed_logaddexp(+,-). */
+static inline double log_sub_(double la, double lb) { /* log(exp(la) - exp(lb)), la >= lb */
+    const double amax = la > lb ? la : lb;
+    const double delta = -fabs(lb - la);
+    if (delta != delta) return la + lb;
+    return amax + log1p(-exp(delta));
+}
+
+void o_sample_evidence(const uint32_t key[2], const double *nlive, const double *logL, int64_t M, int64_t S,
+                       double *out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t s = 0; s < S; ++s) {
+        uint32_t ks[2];
+        split_child(key, (uint64_t) s, ks);
+        double log_Z = -INFINITY, log_X = 0.0;
+        for (int64_t i = 0; i < M; ++i) {
+            uint32_t ki[2];
+            split_child(ks, (uint64_t) i, ki);
+            const double log_T = log(uniform01(ki, 0)) / nlive[i];
+            const double next_X = log_X + log_T;
+            const double dZ = log_sub_(log_X, next_X) + logL[i];
+            log_Z = logaddexp_(log_Z, dZ);
+            log_X = next_X;
+        }
+        out[s] = log_Z;
+    }
+}
+
 int o_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

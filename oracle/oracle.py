@@ -361,6 +361,17 @@ def evidence_scan(state, log_L, num_live, per_sample: bool = False):
     return (st, per) if per_sample else st
 
 
+def sample_evidence(key, num_live, log_L, S: int = 100) -> np.ndarray:
+    """utils.py:433-476 (serial scan per simulation, exactly as the reference's cumulative_op_static)."""
+    nl = np.ascontiguousarray(num_live, dtype=np.float64)
+    ll = np.ascontiguousarray(log_L, dtype=np.float64)
+    out = np.empty(S, dtype=np.float64)
+    k = _key(key)
+    lib().o_sample_evidence(_p(k, _u32p), _p(nl, _f64p), _p(ll, _f64p), ctypes.c_int64(ll.size), ctypes.c_int64(S),
+                            _p(out, _f64p))
+    return out
+
+
 def linear_to_log_stats(log_f_mean, log_f2_mean):
     """internals/stats.py:55-74."""
     mu = 2.0 * log_f_mean - 0.5 * log_f2_mean

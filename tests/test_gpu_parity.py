@@ -150,6 +150,47 @@ def test_slice_batch_parity(torch_cuda, oracle, name, D, N, S, k, midpoint):
                        sample.num_likelihood_evaluations)
 
 
+@pytest.mark.parametrize("prior", ["normal", "uniform"])
+def test_slice_batch_independent_of_speculation_width(torch_cuda, oracle, prior, monkeypatch):
+    """The number of proposals evaluated speculatively per shrink round (NSB200_SPEC, a tuning knob of the D <= 32
+    instantiation; the batched quantile ndtri_batch serves P > 1) must not change a single bit of the result:
+    the first accepted proposal wins and n_evals counts up to it, as in the sequential loop
+    (samplers/uni_slice_sampler.py:160-186)."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd, likelihoods as lk, random
+    from jaxns_b200.types import LivePointCollection
+    D, N, S, k = 32, 320, 24, 2
+    if prior == "normal":
+        model = product_models()["gauss"](D)
+    else:
+        cov = np.full((D, D), 0.9) + 0.1 * np.eye(D)
+
+        def prior_model():
+            x = yield j.Prior(tfpd.Uniform(low=-3.0 * np.ones(D), high=5.0 * np.ones(D)), name="x")
+            return x
+        model = j.Model(prior_model, lk.DenseGaussianLikelihood(np.full(D, 1.0), covariance_matrix=cov))
+    om = to_oracle(model, oracle)
+    oU, ologL, _ = oracle.init_batch(om, random.PRNGKey(5), N)
+    order = np.argsort(ologL, kind="stable")
+    live_U, live_logL = oU[order], ologL[order]
+    m = N // 2
+    contour = live_logL[m - 1]
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=True, perfect=True)
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    outs = []
+    for spec in ("1", "2", "4"):
+        monkeypatch.setenv("NSB200_SPEC", spec)
+        sample, phantom = sampler.get_samples_batch(random.PRNGKey(13), contour, state, m)
+        outs.append((sample.U_sample.clone(), sample.log_L.clone(), sample.num_likelihood_evaluations.clone(),
+                     phantom.U_sample.clone(), phantom.log_L.clone()))
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert torch.equal(a, b)
+    exp = oracle.slice_batch(om, random.PRNGKey(13), contour, live_U, live_logL, S, k, True, num_samples=m)
+    np.testing.assert_array_equal(outs[0][2].cpu().numpy(), exp["n_evals"])
+
+
 def test_slice_plateau_and_no_seed(torch_cuda, oracle):
     """Edge cases of the reference: contour at the maximum (no satisfying seed -> index 0)."""
     torch = torch_cuda
@@ -567,3 +608,68 @@ def test_prior_quantile_accuracy_vs_scipy(torch_cuda):
                                                   _lib.stream_arg()))
     xe = Xe.cpu().numpy()[0]
     assert xe[0] == -np.inf and xe[1] == np.inf and xe[2] == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+# post-processing: sample_evidence, resample, summary, save / load
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,S", [(1, 3), (37, 5), (5000, 16), (200000, 4)])
+def test_sample_evidence_vs_oracle(torch_cuda, oracle, M, S):
+    """utils.py:433-476 through nsb200_sample_evidence: same key tree, same draws; the parallel scan re-associates
+    the serial recurrence (rtol 1e-10, like the evidence statistics)."""
+    torch = torch_cuda
+    from jaxns_b200 import random, utils
+    rng = np.random.default_rng(M)
+    log_L = np.sort(-0.5 * rng.chisquare(5, size=M)) * 40.0
+    n = np.maximum(1, rng.integers(1, 400, size=M)).astype(np.int32)
+    if M > 30:
+        n[M - 30:] = np.arange(30, 0, -1)
+    key = random.PRNGKey(3)
+    got = utils.sample_evidence(key, torch.from_numpy(n).cuda(), torch.from_numpy(log_L).cuda(), S=S)
+    exp = oracle.sample_evidence(key, n, log_L, S=S)
+    np.testing.assert_allclose(got.cpu().numpy(), exp, rtol=1e-10)
+
+
+def test_resample_and_summary_and_wire_format(torch_cuda, oracle, tmp_path, capsys):
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random, utils
+    model = product_models()["gauss"](4)
+    ns = j.NestedSampler(model=model, num_live_points=200, max_samples=40000)
+    reason, state = ns(random.PRNGKey(0))
+    res = ns.to_results(reason, state)
+    # resample_indicies (internals/random.py:34-75): searchsorted of log r in the cumulative logsumexp
+    key = random.PRNGKey(9)
+    idx = utils.resample_indicies(key, res.log_dp_mean, S=500, replace=True).cpu().numpy()
+    lw = res.log_dp_mean.cpu().numpy()
+    cum = np.logaddexp.accumulate(lw)
+    log_r = cum[-1] + np.log(1.0 - oracle.uniform(key, 500))
+    exp = np.searchsorted(cum, log_r, side="left")
+    assert np.mean(idx == exp) > 0.995 and np.max(np.abs(idx - exp)) <= 1  # ties at rounding level only
+    # without replacement: a permutation prefix (Gumbel top-k)
+    idx2 = utils.resample_indicies(key, res.log_dp_mean, S=50, replace=False).cpu().numpy()
+    assert len(set(idx2.tolist())) == 50
+    # ESS default, tree-mapped samples
+    rs = utils.resample(key, res.samples, res.log_dp_mean)
+    assert rs["x"].shape[0] == int(np.exp(2 * np.logaddexp.reduce(lw) - np.logaddexp.reduce(2 * lw)))
+    post_mean = rs["x"].mean(0).cpu().numpy()
+    fam, D, pk, K, a, b, params = model.host_arrays()
+    assert np.all(np.isfinite(post_mean))
+    m_static = utils.marginalise_static(key, res.samples, res.log_dp_mean, 200, lambda x: x)
+    m_dyn = utils.marginalise_dynamic(key, res.samples, res.log_dp_mean, 50, lambda x: x)
+    assert torch.allclose(m_static, rs["x"].mean(0), atol=0.5) and torch.allclose(m_dyn, m_static, atol=0.8)
+    mp = utils.maximum_a_posteriori_point(res)
+    assert torch.equal(mp["x"], res.samples["x"][int(torch.argmax(res.log_posterior_density))])
+    assert torch.equal(utils.evaluate_map_estimate(res, lambda x: 2 * x), 2 * mp["x"])
+    text = utils.summary(res)
+    assert "Small remaining evidence" in text and "x[#]: mean +- std.dev." in text and f"samples: {res.total_num_samples}" in text
+    # save -> load round trip of real results
+    f = str(tmp_path / "res.json")
+    utils.save_results(res, f)
+    back = utils.load_results(f)
+    assert back.total_num_samples == res.total_num_samples and back.termination_reason == res.termination_reason
+    assert torch.equal(back.log_L_samples, res.log_L_samples) and torch.equal(back.samples["x"], res.samples["x"])
+    assert back.log_Z_mean == res.log_Z_mean and back.num_live_points_per_sample.dtype == torch.int32
+    # sample_evidence of the run agrees with the analytic evidence statistics
+    lz = utils.sample_evidence(random.PRNGKey(1), res.num_live_points_per_sample, res.log_L_samples, S=64)
+    assert abs(float(lz.mean()) - res.log_Z_mean) < 4 * res.log_Z_uncert

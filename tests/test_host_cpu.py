@@ -174,3 +174,77 @@ def test_oracle_is_not_imported_by_product():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in text.lower() or f == "__init__.py" and False, f"{f} mentions the oracle"
+
+
+def _fake_results(n=7, D=3):
+    import torch
+    from jaxns_b200.types import NestedSamplerResults
+    g = torch.Generator().manual_seed(0)
+    r = lambda *shape: torch.rand(*shape, generator=g, dtype=torch.float64)  # noqa: E731
+    return NestedSamplerResults(
+        log_Z_mean=-3.25, log_Z_uncert=0.125, ESS=41.5, H_mean=-2.5, samples={"x": r(n, D)}, parametrised_samples={},
+        U_samples=r(n, D), log_L_samples=r(n), log_dp_mean=r(n), log_X_mean=r(n), log_posterior_density=r(n),
+        num_live_points_per_sample=torch.arange(n, dtype=torch.int32),
+        num_likelihood_evaluations_per_sample=torch.arange(n, dtype=torch.int64), total_num_samples=n,
+        total_phantom_samples=0, total_num_likelihood_evaluations=123, log_efficiency=-2.0, termination_reason=4)
+
+
+def test_results_wire_format_is_the_references(tmp_path):
+    """save_results / load_results (utils.py:588-641): the JSON schema of internals/namedtuple_utils.py:34-103 --
+    '__namedtuple__' nodes naming the reference's class path, arrays as base64 of the raw bytes with dtype and
+    shape, scalars as 0-d arrays -- so a file written here loads in jaxns and vice versa."""
+    import base64
+    import json
+    import torch
+    from jaxns_b200 import utils
+    res = _fake_results()
+    f = str(tmp_path / "results.json")
+    utils.save_results(res, f)
+    doc = json.load(open(f))
+    assert doc["type"] == "__namedtuple__"
+    assert doc["__class__"] == "jaxns.nested_samplers.common.types.NestedSamplerResults"
+    assert list(doc["__data__"].keys()) == list(res._fields)
+    node = doc["__data__"]["log_L_samples"]
+    assert node["type"] == "__jax_ndarray__" and node["__dtype__"] == "float64" and node["__shape__"] == [7]
+    raw = np.frombuffer(base64.b64decode(node["__data__"]), dtype="float64")
+    np.testing.assert_array_equal(raw, res.log_L_samples.numpy())
+    assert doc["__data__"]["log_Z_mean"]["__shape__"] == [] and doc["__data__"]["log_Z_mean"]["__dtype__"] == "float64"
+    assert doc["__data__"]["termination_reason"]["__dtype__"] == "int64"
+    assert doc["__data__"]["num_live_points_per_sample"]["__dtype__"] == "int32"
+    assert doc["__data__"]["samples"]["x"]["__shape__"] == [7, 3]
+    back = utils.load_results(f, device="cpu")
+    assert type(back).__name__ == "NestedSamplerResults"
+    for name in res._fields:
+        a, b = getattr(res, name), getattr(back, name)
+        if isinstance(a, torch.Tensor):
+            assert a.dtype == b.dtype and torch.equal(a, b)
+        elif isinstance(a, dict):
+            assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+        else:
+            assert a == b
+    with pytest.warns(UserWarning, match="json"):
+        utils.save_results(res, str(tmp_path / "results.txt"))
+    with pytest.raises(ValueError):
+        utils.save_pytree({"a": 1}, f)
+
+
+def test_load_results_written_by_the_reference_serialiser(tmp_path):
+    """A document laid out exactly as jaxns' serialise_namedtuple writes it (namedtuple_utils.py:34-48, :90-96)."""
+    import base64
+    import json
+    from jaxns_b200 import utils
+
+    def arr(a, kind="__jax_ndarray__"):
+        a = np.asarray(a)
+        return {"type": kind, "__dtype__": str(a.dtype), "__data__": base64.b64encode(a.tobytes()).decode(), "__shape__": a.shape}
+
+    doc = {"type": "__namedtuple__", "__class__": "jaxns.nested_samplers.common.types.TerminationCondition",
+           "__data__": {"ess": arr(np.float64(100.0)), "evidence_uncert": None, "live_evidence_frac": None,
+                        "dlogZ": arr(np.float64(1e-3)), "max_samples": arr(np.int64(5000)),
+                        "max_num_likelihood_evaluations": None, "log_L_contour": None, "efficiency_threshold": None,
+                        "rtol": None, "atol": None, "peak_XL_frac": arr(np.arange(3.0), "__ndarray__")}}
+    f = str(tmp_path / "tc.json")
+    json.dump(doc, open(f, "w"), indent=2)
+    tc = utils.load_pytree(f, device="cpu")
+    assert type(tc).__name__ == "TerminationCondition" and tc.ess == 100.0 and tc.max_samples == 5000
+    assert tc.evidence_uncert is None and isinstance(tc.peak_XL_frac, np.ndarray)

@@ -211,3 +211,20 @@ def test_oracle_phantom_and_cap_overflow(oracle):
     assert reason & 1 and st["num_samples"] == 260
     r = ns.to_results(reason, st)
     assert r["total_num_samples"] == 240
+
+
+def test_sample_evidence_matches_deterministic_evidence(oracle):
+    """utils.py:433-476: the simulated log Z samples scatter around the deterministic estimate with about its
+    uncertainty (shrinkage statistics of the same dead-point set)."""
+    rng = np.random.default_rng(0)
+    M, N = 4000, 100
+    log_L = np.sort(-0.5 * rng.chisquare(4, size=M))
+    # static run with N live points: n = N for the dead points, N..1 for the final live set
+    n = np.concatenate([np.full(M - N, N), np.arange(N, 0, -1)]).astype(np.float64)
+    samples = oracle.sample_evidence(oracle.PRNGKey(7), n, log_L, S=200)
+    st = oracle.evidence_scan(oracle.init_evidence_calc(), log_L, n)
+    mean, var = oracle.linear_to_log_stats(st[3], st[5])
+    assert abs(samples.mean() - mean) < 4 * np.sqrt(var / 200) + 0.05
+    assert 0.5 * np.sqrt(var) < samples.std() < 2.0 * np.sqrt(var)
+    # simulations are independent of S (simulation s only depends on split(key, S)[s] = TF(key; 0, s))
+    np.testing.assert_array_equal(oracle.sample_evidence(oracle.PRNGKey(7), n, log_L, S=3), samples[:3])
