@@ -270,6 +270,20 @@ int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *log_L, const
 int nsb200_logsumexp(const double *x, int64_t n, double *out, void *workspace, int64_t workspace_bytes,
                      nsb200_stream_t stream);
 
+/* ---- multi-GPU: fused all-gather over NVLink peer memory --------------------------------------
+ * Replaces the all-gather of the new samples after the sharded get_samples
+ * (nested_samplers/sharded/sharded_static.py:104-129, out_specs=PartitionSpec()): once every rank's engine is
+ * connected, the slice kernel stores each packed row straight into the gather buffer of every rank and
+ * engine_step_end starts with an arrival barrier on device flags -- the host issues no collective.
+ * export: the CUDA IPC handle of this engine's arena + byte offsets of {gather buffer 0, gather buffer 1, flags};
+ * connect: handles [world][64] and offsets [world][3] of all ranks in rank order (exchange them with any host
+ * transport).  enabled(e, -1) queries nothing and is a no-op, 0/1 switch the mode (the host all-gather of
+ * nsb200_engine_gather_buffer stays available).  error: 1 if a peer did not arrive within ~2 s. */
+int nsb200_engine_p2p_export(NsEngine *e, uint8_t handle[64], int64_t offsets[3]);
+int nsb200_engine_p2p_connect(NsEngine *e, const uint8_t *handles, const int64_t *offsets);
+int nsb200_engine_p2p_enabled(NsEngine *e, int32_t enable);
+int nsb200_engine_p2p_error(NsEngine *e, int32_t *out);
+
 /* sample_evidence (utils.py:433-476): S simulations of the shrinkage over the M dead points, simulation s with
  * split(key, S)[s] and per-point keys split(key_s, M)[i]; log T_i = log(uniform(key_i, ())) / n_i.
  * num_live_points float64 [M], log_L [M] (sorted), out [S] = samples of log Z.  All DEVICE pointers. */

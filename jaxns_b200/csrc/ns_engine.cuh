@@ -139,6 +139,107 @@ __global__ void __launch_bounds__(256) k_merge_rank(const DevCtl *ctl, const Liv
     rank_out[e] = cnt;
 }
 
+// ---- rank merge for large shells: sorted tiles of the new keys + binary searches ---------------------------
+// k_merge_rank compares every element with every new key: N * m compares (3.3e8 for the live set of an 8-GPU
+// weak-scaling run: 175 us; 5e9 for config 5).  For m >= 2048 the new (key, index) pairs are sorted in tiles of
+// 1024 (one CTA per tile, bitonic network in shared memory on the composite (key, index) order = the stable
+// order); then, with T = ceil(m / 1024) tiles,
+//   rank(new e)      = sum_t #{(k, i) in tile t : (k, i) < (key_e, e)} + #{survivors with key <  key_e}
+//   rank(survivor p) = (p - m) + sum_t #{k in tile t : k <= key_p}
+// are T ten-step binary searches per element, spread over 16 lanes: O(N T log 1024) instead of O(N m).
+// (A single-CTA sort of all m keys was measured first: 280 us at m = 12800 -- one SM's issue rate.)
+constexpr int kMergeTile = 1024;
+
+__global__ void __launch_bounds__(kMergeTile) k_merge_sort_tiles(const DevCtl *ctl, const double *packed,
+                                                                 long long row_doubles, int D, long long m,
+                                                                 uint64_t *sorted_keys, unsigned *sorted_idx) {
+    if (!ctl->active) return;
+    __shared__ uint64_t sk[kMergeTile];
+    __shared__ unsigned si[kMergeTile];
+    const long long base = (long long) blockIdx.x * kMergeTile;
+    {
+        const long long r = base + threadIdx.x;
+        sk[threadIdx.x] = (r < m) ? sort_key_f64(packed[r * row_doubles + D]) : 0xFFFFFFFFFFFFFFFFull;
+        si[threadIdx.x] = (unsigned) r;  // pads carry indices >= m: they sort after NaN keys (same u64) of real rows
+    }
+    __syncthreads();
+    for (int k = 2; k <= kMergeTile; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (threadIdx.x < (kMergeTile >> 1)) {
+                const int t = threadIdx.x;
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // t with a zero bit inserted at log2(j)
+                const int l = i | j;
+                const uint64_t ka = sk[i], kb = sk[l];
+                const unsigned ia = si[i], ib = si[l];
+                const bool a_after_b = (ka > kb) || (ka == kb && ia > ib);
+                const bool ascending = (i & k) == 0;
+                if (a_after_b == ascending) {
+                    sk[i] = kb;
+                    sk[l] = ka;
+                    si[i] = ib;
+                    si[l] = ia;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    sorted_keys[base + threadIdx.x] = sk[threadIdx.x];
+    sorted_idx[base + threadIdx.x] = si[threadIdx.x];
+}
+
+constexpr int kMergeLanes = 16;  // lanes sharing the tiles of one element
+
+__global__ void __launch_bounds__(256) k_merge_rank_tiles(const DevCtl *ctl, const LiveSet live0, const LiveSet live1,
+                                                          const double *packed, long long row_doubles, int D,
+                                                          long long m, long long N, const uint64_t *sorted_keys,
+                                                          const unsigned *sorted_idx, unsigned *rank_out) {
+    if (!ctl->active) return;
+    const LiveSet &live = ctl->cur ? live1 : live0;
+    const long long gt = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const long long e = gt / kMergeLanes;
+    const int sub = (int) (gt % kMergeLanes);
+    const bool valid = e < N;
+    const bool is_new = e < m;
+    uint64_t key = 0;
+    if (valid) key = sort_key_f64(is_new ? packed[e * row_doubles + D] : live.logL[e]);
+    const int T = (int) ((m + kMergeTile - 1) / kMergeTile);
+    unsigned cnt = 0;
+    if (valid) {
+        for (int t = sub; t < T; t += kMergeLanes) {
+            const uint64_t *tk = sorted_keys + (long long) t * kMergeTile;
+            const unsigned *ti = sorted_idx + (long long) t * kMergeTile;
+            int lo = 0, hi = (int) min((long long) kMergeTile, m - (long long) t * kMergeTile);
+            if (is_new) {  // entries strictly before (key, e) in the stable order
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const uint64_t km = tk[mid];
+                    if (km < key || (km == key && ti[mid] < (unsigned) e)) lo = mid + 1; else hi = mid;
+                }
+            } else {  // new keys <= key (new rows come first on ties)
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (tk[mid] <= key) lo = mid + 1; else hi = mid;
+                }
+            }
+            cnt += (unsigned) lo;
+        }
+    }
+#pragma unroll
+    for (int o = kMergeLanes >> 1; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (!valid || sub != 0) return;
+    if (is_new) {
+        long long lo = m, hi = N;  // survivors strictly below
+        while (lo < hi) {
+            const long long mid = lo + ((hi - lo) >> 1);
+            if (sort_key_f64(live.logL[mid]) < key) lo = mid + 1; else hi = mid;
+        }
+        cnt += (unsigned) (lo - m);
+    } else {
+        cnt += (unsigned) (e - m);
+    }
+    rank_out[e] = cnt;
+}
+
 // Scatter rows into the other live buffer at their rank; phantom rows go to the dead store
 // (add_phantom_samples_to_state, sharded_static.py:181-207).
 __global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const LiveSet live1, const double *packed,
@@ -187,6 +288,36 @@ __global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const Li
             }
         }
     }
+}
+
+// Arrival barrier of the fused all-gather.  The slice kernel of every rank has stored its rows into every rank's
+// gather buffer (NVLink peer stores); lane r of this one-warp kernel publishes this rank's arrival (epoch = body
+// counter, monotone over the engine's life) in rank r's flag array and waits for rank r's arrival in its own.
+// The system-scope fence before the flag store orders the chains' peer stores (previous kernel in the stream)
+// before it; the fence after the wait orders the merge kernels' reads after it.  A rank that does not arrive
+// within ~30 s sets *err instead of hanging the GPU.  `force`: the run-entry barrier of engine_init (no rank may
+// store rows of a new run into a peer that is still finishing the previous one).
+struct PeerFlags {
+    unsigned long long *p[8];
+};
+
+__global__ void k_peer_barrier(const DevCtl *ctl, unsigned long long epoch, volatile unsigned long long *mine,
+                               PeerFlags peers, int world, int me, int *err, int force) {
+    if (!force && !ctl->active) return;
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    __threadfence_system();
+    *((volatile unsigned long long *) (peers.p[r] + me)) = epoch;
+    __threadfence_system();
+    long long spins = 0;
+    while (mine[r] < epoch) {
+        __nanosleep(200);
+        if (++spins > 150000000ll) {  // ~30 s
+            atomicExch(err, 1);
+            break;
+        }
+    }
+    __threadfence_system();
 }
 
 // linear_to_log_stats (stats.py:55-74)

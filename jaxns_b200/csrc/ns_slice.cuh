@@ -83,7 +83,17 @@ struct SliceArgs {
     const double *pre_us;
     const uint2 *pre_rkeys;
     const double *alpha_tab;  // optional [S]: alpha_schedule(j, S) (saves an int->double division per slice)
+    // fused all-gather (multi-GPU engines connected over CUDA IPC): every packed row is also stored straight
+    // into the gather buffer of each rank (own buffer included) through NVLink peer mappings, so no collective
+    // kernel runs between the chains and the merge -- only an arrival barrier (k_peer_barrier)
+    int n_peers;
+    double *peers[8];  // this rank's block inside rank r's gather buffer
 };
+
+__device__ __forceinline__ void packed_store(const SliceArgs &a, long long off, double v) {
+    if (a.packed) a.packed[off] = v;
+    for (int r = 0; r < a.n_peers; ++r) a.peers[r][off] = v;
+}
 
 // jnp.linspace(0.5, 1., S)[j]
 __device__ __forceinline__ double alpha_schedule(int j, int S) {
@@ -469,14 +479,12 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     const int jj = s * G + g.lane;
                     if (jj < D) {
                         if (a.ph_U) a.ph_U[slot * D + jj] = U0[s];
-                        if (a.packed)
-                            a.packed[out_row * a.packed_row_doubles + (D + 2) + (long long) (j - (S - 1 - kph)) * (D + 1) + jj] = U0[s];
+                        packed_store(a, out_row * a.packed_row_doubles + (D + 2) + (long long) (j - (S - 1 - kph)) * (D + 1) + jj, U0[s]);
                     }
                 }
                 if (g.lane == 0) {
                     if (a.ph_logL) a.ph_logL[slot] = logL0;
-                    if (a.packed)
-                        a.packed[out_row * a.packed_row_doubles + (D + 2) + (long long) (j - (S - 1 - kph)) * (D + 1) + D] = logL0;
+                    packed_store(a, out_row * a.packed_row_doubles + (D + 2) + (long long) (j - (S - 1 - kph)) * (D + 1) + D, logL0);
                 }
             }
         }
@@ -493,16 +501,14 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         const int j = s * G + g.lane;
         if (j < D) {
             if (a.out_U) a.out_U[out_row * D + j] = U0[s];
-            if (a.packed) a.packed[out_row * a.packed_row_doubles + j] = U0[s];
+            packed_store(a, out_row * a.packed_row_doubles + j, U0[s]);
         }
     }
     if (g.lane == 0) {
         if (a.out_logL) a.out_logL[out_row] = logL0;
         if (a.out_nevals) a.out_nevals[out_row] = nev;
-        if (a.packed) {
-            a.packed[out_row * a.packed_row_doubles + D] = logL0;
-            a.packed[out_row * a.packed_row_doubles + D + 1] = __longlong_as_double(nev);
-        }
+        packed_store(a, out_row * a.packed_row_doubles + D, logL0);
+        packed_store(a, out_row * a.packed_row_doubles + D + 1, __longlong_as_double(nev));
     }
 }
 

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "ns_engine.cuh"
@@ -736,6 +737,19 @@ struct NsEngine {
     double *seed_table = nullptr;
     double *packed = nullptr;
     unsigned *rank = nullptr;
+    // fused all-gather over CUDA IPC peer mappings (world_size > 1, after nsb200_engine_p2p_connect)
+    bool p2p = false;
+    double *packed_home = nullptr;               // the engine's own gather / init-packing buffer (`packed` outside p2p bodies)
+    double *packed_buf[2] = {nullptr, nullptr};  // p2p gather buffers by body parity (peers store into these)
+    unsigned long long *p2p_flags = nullptr;     // [8] arrival epochs written by the peers
+    int *p2p_err = nullptr;
+    size_t off_packed[2] = {0, 0}, off_flags = 0;  // byte offsets inside the arena (exported to the peers)
+    void *peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    double *peer_packed[2][8] = {};
+    unsigned long long *peer_flags[8] = {};
+    unsigned long long p2p_epoch = 0;
+    uint64_t *sorted_new = nullptr;  // new keys sorted in tiles of 1024 (large shells: k_merge_sort_tiles)
+    unsigned *new_pos = nullptr;     // row index of each sorted entry
     // chain streams of this rank's chains (k_chain_streams), triple buffered: the streams of body i+2
     // are generated on `side` in the gap between the slice kernels of bodies i and i+1
     double *pre_dirs[3] = {nullptr, nullptr, nullptr};
@@ -750,6 +764,8 @@ struct NsEngine {
     NsTermCond tc;
     std::vector<void *> allocs;
     // profiling
+    std::vector<std::pair<void **, size_t>> arena_slots;  // pointer location, byte offset in the arena
+    size_t arena_bytes = 0;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     double slice_ms = 0.0;
@@ -770,18 +786,31 @@ struct NsEngine {
     size_t split_ws_bytes = 0;
 };
 
+// Engine buffers are carved out of ONE device allocation: dev_alloc only records (where the pointer lives, offset),
+// arena_commit makes the single cudaMalloc and fills the pointers in.  (30 separate cudaMalloc calls cost ~5 ms per
+// NestedSampler, 5 % of a config-2 run through the public API.)
 template <typename T>
 static int dev_alloc(NsEngine *e, T **p, size_t count) {
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t) 255;
+    e->arena_slots.push_back({(void **) p, e->arena_bytes});
+    e->arena_bytes += bytes;
+    *p = nullptr;
+    return 0;
+}
+
+static int arena_commit(NsEngine *e) {
     void *q = nullptr;
-    cudaError_t err = cudaMalloc(&q, (count ? count : 1) * sizeof(T));
-    if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(err));
+    cudaError_t err = cudaMalloc(&q, e->arena_bytes);
+    if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", e->arena_bytes, cudaGetErrorString(err));
     e->allocs.push_back(q);
-    *p = (T *) q;
+    for (const auto &sl : e->arena_slots) *sl.first = (char *) q + sl.second;
     return 0;
 }
 
 extern "C" void nsb200_engine_destroy(NsEngine *e) {
     if (!e) return;
+    for (int r = 0; r < 8; ++r)
+        if (e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     for (void *p : e->allocs) cudaFree(p);
     if (e->reg_host) cudaFreeHost(e->reg_host);
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
@@ -845,7 +874,18 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->reg, 1);
     if (!rc) rc |= dev_alloc(e, &e->seed_table, e->N);
     if (!rc) rc |= dev_alloc(e, &e->packed, (size_t) e->packed_rows * e->row_doubles);
+    if (cfg->world_size > 1 && cfg->world_size <= 8) {
+        for (int b = 0; b < 2; ++b) {
+            e->off_packed[b] = e->arena_bytes;
+            if (!rc) rc |= dev_alloc(e, &e->packed_buf[b], (size_t) e->m * e->row_doubles);
+        }
+        e->off_flags = e->arena_bytes;
+        if (!rc) rc |= dev_alloc(e, &e->p2p_flags, 8);
+        if (!rc) rc |= dev_alloc(e, &e->p2p_err, 1);
+    }
     if (!rc) rc |= dev_alloc(e, &e->rank, e->N);
+    if (!rc) rc |= dev_alloc(e, &e->sorted_new, e->N + kMergeTile);  // whole tiles (pads included)
+    if (!rc) rc |= dev_alloc(e, &e->new_pos, e->N + kMergeTile);
     if (!rc) rc |= dev_alloc(e, &e->epi, 1);
     if (!rc) rc |= dev_alloc(e, &e->alpha_tab, cfg->num_slices);
     if (!rc) rc |= dev_alloc(e, &e->tabT, e->N + 2);
@@ -853,9 +893,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= dev_alloc(e, &e->tabt, e->N + 2);
     if (e->external) {
         e->split_ws_bytes = split_workspace_bytes(e->D, e->rows_per_rank, (int) e->k);
-        char *ws = nullptr;
-        if (!rc) rc |= dev_alloc(e, &ws, e->split_ws_bytes);
-        e->split_ws = ws;
+        if (!rc) rc |= dev_alloc(e, (char **) &e->split_ws, e->split_ws_bytes);
     } else if (g.G >= 8) {  // data-independent chain streams are generated off the chains' critical path
         const size_t rows = (size_t) e->rows_per_rank * cfg->num_slices;
         for (int b = 0; b < 3; ++b) {
@@ -868,6 +906,13 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         if (!rc && cudaEventCreateWithFlags(&e->ev_slice, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
         for (int b = 0; b < 3; ++b)
             if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+    }
+    if (!rc) rc |= arena_commit(e);
+    if (!rc) e->packed_home = e->packed;
+    if (!rc && e->p2p_flags) {
+        if (cudaMemset(e->p2p_flags, 0, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(e->p2p_err, 0, sizeof(int)) != cudaSuccess)
+            rc = fail("cudaMemset failed");
     }
     if (!rc && cudaMallocHost((void **) &e->reg_host, sizeof(NsRegister)) != cudaSuccess) rc = fail("cudaMallocHost failed");
     if (!rc && cudaMallocHost((void **) &e->ctl_host, sizeof(DevCtl)) != cudaSuccess) rc = fail("cudaMallocHost failed");
@@ -886,6 +931,69 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         return 1;
     }
     *out = e;
+    return 0;
+}
+
+// ---- fused all-gather: CUDA IPC wiring (host side exchanges the handles, e.g. with all_gather_object) ---------
+extern "C" int nsb200_engine_p2p_export(NsEngine *e, uint8_t handle[64], int64_t offsets[3]) {
+    if (!e || !handle || !offsets) return fail("NULL argument");
+    if (!e->p2p_flags) return fail("p2p needs 2 <= world_size <= 8");
+    if (e->external) return fail("family EXTERNAL uses the host all-gather");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    NSB_CUDA(cudaIpcGetMemHandle(&h, e->allocs[0]));
+    memcpy(handle, &h, 64);
+    offsets[0] = (int64_t) e->off_packed[0];
+    offsets[1] = (int64_t) e->off_packed[1];
+    offsets[2] = (int64_t) e->off_flags;
+    return 0;
+}
+
+extern "C" int nsb200_engine_p2p_connect(NsEngine *e, const uint8_t *handles, const int64_t *offsets) {
+    if (!e || !handles || !offsets) return fail("NULL argument");
+    if (!e->p2p_flags) return fail("p2p needs 2 <= world_size <= 8");
+    const int world = e->cfg.world_size, me = e->cfg.rank;
+    for (int r = 0; r < world; ++r) {
+        char *base;
+        if (r == me) {
+            base = (char *) e->allocs[0];
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t) r * 64, 64);
+            void *q = nullptr;
+            cudaError_t err = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+            if (err != cudaSuccess) {
+                cudaGetLastError();
+                return fail("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(err));
+            }
+            e->peer_base[r] = q;
+            base = (char *) q;
+        }
+        e->peer_packed[0][r] = (double *) (base + offsets[r * 3 + 0]);
+        e->peer_packed[1][r] = (double *) (base + offsets[r * 3 + 1]);
+        e->peer_flags[r] = (unsigned long long *) (base + offsets[r * 3 + 2]);
+    }
+    e->p2p = true;
+    return 0;
+}
+
+extern "C" int nsb200_engine_p2p_enabled(NsEngine *e, int32_t enable) {
+    if (!e) return fail("NULL engine");
+    if (enable >= 0) {
+        if (enable && !e->peer_flags[e->cfg.rank]) return fail("p2p is not connected");
+        e->p2p = enable != 0;
+    }
+    return 0;
+}
+
+extern "C" int nsb200_engine_p2p_error(NsEngine *e, int32_t *out) {
+    if (!e || !out) return fail("NULL argument");
+    *out = 0;
+    if (e->p2p_err) {
+        int v = 0;
+        NSB_CUDA(cudaMemcpy(&v, e->p2p_err, sizeof(int), cudaMemcpyDeviceToHost));
+        *out = v;
+    }
     return 0;
 }
 
@@ -922,6 +1030,17 @@ static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
 static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t after);
 
 static void launch_merge_rank(NsEngine *e, long long m_new, cudaStream_t st) {
+    const char *brute = getenv("NSB200_MERGE_BRUTE");  // A/B and parity knob: results do not depend on it
+    if (!(brute && atoi(brute)) && m_new >= 2048) {
+        const unsigned tiles = (unsigned) ((m_new + kMergeTile - 1) / kMergeTile);
+        k_merge_sort_tiles<<<tiles, kMergeTile, 0, st>>>(e->ctl, e->packed, e->row_doubles, e->D, m_new, e->sorted_new,
+                                                         e->new_pos);
+        k_merge_rank_tiles<<<grid_for(e->N * kMergeLanes, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed,
+                                                                               e->row_doubles, e->D, m_new, e->N,
+                                                                               e->sorted_new, e->new_pos, e->rank);
+        e->all_launches += 1;
+        return;
+    }
     if (e->N <= 16384)
         k_merge_rank<32><<<grid_for(e->N * 32, 256), 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles,
                                                                   e->D, m_new, e->N, e->rank);
@@ -942,6 +1061,13 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     e->slice_launches = 0;
     e->all_launches = 0;
     e->ev_used = 0;
+    e->packed = e->packed_home;
+    if (e->p2p) {  // run-entry barrier: peers may only store rows of this run once every rank has left the previous one
+        PeerFlags pf;
+        for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
+        e->p2p_epoch += 1;
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 1);
+    }
     // create_init_state (initialisation.py:38-47): empty dead store, key split
     NSB_CUDA(cudaMemsetAsync(e->dead.sender, 0, (size_t) e->cap * 8, st));
     NSB_CUDA(cudaMemsetAsync(e->dead.U, 0, (size_t) e->cap * D * 8, st));
@@ -1147,6 +1273,15 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.midpoint = e->cfg.midpoint_shrink;
     a.packed = e->packed + begin * e->row_doubles;
     a.packed_row_doubles = e->row_doubles;
+    if (e->p2p) {
+        // gather buffers alternate with the body parity: a peer one body ahead writes the other buffer
+        e->p2p_epoch += 1;
+        const int par = (int) (e->p2p_epoch & 1);
+        e->packed = e->packed_buf[par];
+        a.packed = nullptr;
+        a.n_peers = e->cfg.world_size;
+        for (int r = 0; r < a.n_peers; ++r) a.peers[r] = e->peer_packed[par][r] + begin * e->row_doubles;
+    }
     a.ctl = e->ctl;
     a.live0 = e->live[0];
     a.live1 = e->live[1];
@@ -1193,6 +1328,13 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
     const int D = e->D;
+    if (e->p2p) {
+        PeerFlags pf;
+        for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 0);
+        e->all_launches += 1;
+        trace_mark(e, "peer barrier end", st);
+    }
     launch_merge_rank(e, e->m, st);
     trace_mark(e, "merge_rank end", st);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,

@@ -196,16 +196,20 @@ class ShardedStaticNestedSampler:
             _lib.check(L.nsb200_engine_run(eng.h, _lib.key_arg(key), ctypes.byref(tc), ctypes.c_int64(-1),
                                            ctypes.byref(reg), stream))
         else:
+            p2p = world > 1 and self._connect_peers(eng, world)
             _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
-            gather = self._gather_tensor(eng) if world > 1 else None
+            gather = self._gather_tensor(eng) if (world > 1 and not p2p) else None
             host_tc = self._effective_host_cond(term_cond) if not plain else None
 
             def one_body():
                 _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
-                if world > 1:
+                if gather is not None:
+                    # host-issued collective (NSB200_P2P=0, or no peer access): NCCL all-gather of the packed rows
                     import torch.distributed as dist
                     rows = gather.shape[0] // world
                     dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+                # p2p: the slice kernel already stored the rows into every rank's buffer; step_end starts with the
+                # device-side arrival barrier
                 _lib.check(L.nsb200_engine_step_end(eng.h, stream))
 
             if plain:
@@ -234,6 +238,11 @@ class ShardedStaticNestedSampler:
                     one_body()
                     _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
             _lib.check(L.nsb200_engine_finalize(eng.h, stream))
+            if p2p:
+                err = ctypes.c_int32()
+                _lib.check(L.nsb200_engine_p2p_error(eng.h, ctypes.byref(err)))
+                if err.value:
+                    raise RuntimeError("nsb200: a peer GPU did not reach the all-gather barrier (fused NVLink exchange)")
         register = termination.register_from_c(reg)
         if plain:
             termination_reason = int(reg.termination_reason)
@@ -248,6 +257,36 @@ class ShardedStaticNestedSampler:
         self.last_profile = dict(slice_ms=ms.value, slice_launches=nsl.value, all_launches=nall.value,
                                  iterations=int(reg.iteration))
         return termination_reason, register, state
+
+    def _connect_peers(self, eng, world) -> bool:
+        """Wire the engines of all ranks together for the fused all-gather (include/nsb200.h, nsb200_engine_p2p_*):
+        CUDA IPC handles of the engine arenas are exchanged once per engine through the process group; every rank
+        must succeed, otherwise all of them keep the host-issued NCCL all-gather."""
+        if getattr(self, "_p2p_state", None) is not None:
+            return self._p2p_state
+        import torch.distributed as dist
+        L = _lib.lib()
+        ok = os.environ.get("NSB200_P2P", "0") == "1" and world <= 8 and dist.get_backend() == "nccl"
+        handle = (ctypes.c_uint8 * 64)()
+        offs = (ctypes.c_int64 * 3)()
+        if ok and L.nsb200_engine_p2p_export(eng.h, handle, offs) != 0:
+            ok = False
+        mine = (bytes(handle), [int(x) for x in offs], bool(ok))
+        everyone = [None] * world
+        dist.all_gather_object(everyone, mine)
+        ok = all(o[2] for o in everyone)
+        if ok:
+            hbuf = (ctypes.c_uint8 * (64 * world)).from_buffer_copy(b"".join(o[0] for o in everyone))
+            obuf = (ctypes.c_int64 * (3 * world))(*[x for o in everyone for x in o[1]])
+            ok = L.nsb200_engine_p2p_connect(eng.h, hbuf, obuf) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+        _lib.check(L.nsb200_engine_p2p_enabled(eng.h, ctypes.c_int32(1 if ok else 0))) if ok else None
+        if not ok:
+            L.nsb200_engine_p2p_enabled(eng.h, ctypes.c_int32(0))
+        self._p2p_state = ok
+        return ok
 
     def _initial_points_external(self, key):
         """create_init_state's prior draws (common/initialisation.py:47-60, common/uniform_sample.py:12-60) with the

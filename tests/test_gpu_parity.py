@@ -367,6 +367,29 @@ def test_engine_run_matches_oracle(torch_cuda, oracle, name, D, N, S, k, midpoin
     assert register.num_likelihood_evaluations == oreg["num_likelihood_evaluations"]
 
 
+@pytest.mark.parametrize("N", [4096, 6000])
+def test_sorted_merge_rank_equals_brute_force(torch_cuda, N, monkeypatch):
+    """Large shells (2048 <= m <= 16384) rank the merged live set by sorting the new keys in one CTA + binary
+    searches instead of N * m compares; the stable order (sharded_static.py:269-275: new rows first on ties) and
+    therefore the whole run must be bit-identical to the brute-force kernel (NSB200_MERGE_BRUTE=1).  The egg-box
+    family makes exact log L ties likely (plateaus at the prior corners are common in U space)."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    model = product_models()["eggbox"](2)
+    outs = []
+    for brute in ("1", "0"):
+        monkeypatch.setenv("NSB200_MERGE_BRUTE", brute)
+        ns = j.NestedSampler(model=model, num_live_points=N, max_samples=N * 6, s=2)
+        reason, state = ns(random.PRNGKey(4), j.TerminationCondition(max_samples=float(N * 5)))
+        sc = state.sample_collection
+        outs.append((int(reason), int(state.num_samples), sc.log_L.clone(), sc.U_samples.clone(),
+                     sc.sender_node_idx.clone(), sc.num_likelihood_evaluations.clone()))
+    assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][1] >= N * 4
+    for a, b in zip(outs[0][2:], outs[1][2:]):
+        assert torch.equal(a, b)
+
+
 def test_public_api_gaussian_logZ(torch_cuda, oracle):
     """End to end through NestedSampler with default settings: 2-D Gaussian (BASELINE config 1),
     |logZ - analytic| < 3 sigma for every one of 10 seeds is too strict for a 3-sigma test, so the
