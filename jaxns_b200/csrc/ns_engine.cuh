@@ -292,7 +292,7 @@ __global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const Li
 
 // Arrival barrier of the fused all-gather.  The slice kernel of every rank has stored its rows into every rank's
 // gather buffer (NVLink peer stores); lane r of this one-warp kernel publishes this rank's arrival (epoch = body
-// counter, monotone over the engine's life) in rank r's flag array and waits for rank r's arrival in its own.
+// counter kept on the device, monotone over the engine's life) in rank r's flag array and waits for rank r's arrival in its own.
 // The system-scope fence before the flag store orders the chains' peer stores (previous kernel in the stream)
 // before it; the fence after the wait orders the merge kernels' reads after it.  A rank that does not arrive
 // within ~30 s sets *err instead of hanging the GPU.  `force`: the run-entry barrier of engine_init (no rank may
@@ -301,9 +301,18 @@ struct PeerFlags {
     unsigned long long *p[8];
 };
 
-__global__ void k_peer_barrier(const DevCtl *ctl, unsigned long long epoch, volatile unsigned long long *mine,
+__global__ void k_peer_barrier(const DevCtl *ctl, unsigned long long *epoch_dev, volatile unsigned long long *mine,
                                PeerFlags peers, int world, int me, int *err, int force) {
     if (!force && !ctl->active) return;
+    // The epoch counts the barriers this engine has passed.  It lives on the device and only advances for ACTIVE
+    // bodies (and run entries), which every rank executes identically -- the host may enqueue different numbers of
+    // no-op bodies per rank after the loop has ended without desynchronising the ranks.
+    unsigned long long epoch = 0;
+    if (threadIdx.x == 0) {
+        epoch = *epoch_dev + 1;
+        *epoch_dev = epoch;
+    }
+    epoch = __shfl_sync(0xFFFFFFFFu, epoch, 0);
     const int r = threadIdx.x;
     if (r >= world) return;
     __threadfence_system();

@@ -747,7 +747,7 @@ struct NsEngine {
     void *peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *peer_packed[2][8] = {};
     unsigned long long *peer_flags[8] = {};
-    unsigned long long p2p_epoch = 0;
+    unsigned long long *p2p_epoch_dev = nullptr;  // barriers passed (device counter, advanced by active bodies only)
     uint64_t *sorted_new = nullptr;  // new keys sorted in tiles of 1024 (large shells: k_merge_sort_tiles)
     unsigned *new_pos = nullptr;     // row index of each sorted entry
     // chain streams of this rank's chains (k_chain_streams), triple buffered: the streams of body i+2
@@ -881,6 +881,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         }
         e->off_flags = e->arena_bytes;
         if (!rc) rc |= dev_alloc(e, &e->p2p_flags, 8);
+        if (!rc) rc |= dev_alloc(e, &e->p2p_epoch_dev, 1);
         if (!rc) rc |= dev_alloc(e, &e->p2p_err, 1);
     }
     if (!rc) rc |= dev_alloc(e, &e->rank, e->N);
@@ -911,6 +912,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) e->packed_home = e->packed;
     if (!rc && e->p2p_flags) {
         if (cudaMemset(e->p2p_flags, 0, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMemset(e->p2p_epoch_dev, 0, sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(e->p2p_err, 0, sizeof(int)) != cudaSuccess)
             rc = fail("cudaMemset failed");
     }
@@ -1062,11 +1064,11 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     e->all_launches = 0;
     e->ev_used = 0;
     e->packed = e->packed_home;
+    e->body = 0;
     if (e->p2p) {  // run-entry barrier: peers may only store rows of this run once every rank has left the previous one
         PeerFlags pf;
         for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
-        e->p2p_epoch += 1;
-        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 1);
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 1);
     }
     // create_init_state (initialisation.py:38-47): empty dead store, key split
     NSB_CUDA(cudaMemsetAsync(e->dead.sender, 0, (size_t) e->cap * 8, st));
@@ -1081,7 +1083,6 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
         // the side stream may still be writing streams from a previous run into these buffers
         NSB_CUDA(cudaStreamSynchronize(e->side));
         NSB_CUDA(cudaEventRecord(e->ev_keys, st));
-        e->body = 0;
         if (enqueue_streams(e, 0, st, e->ev_keys)) return 1;  // bodies 0 and 1; body b + 2 is enqueued by body b
         if (enqueue_streams(e, 1, st, e->ev_keys)) return 1;
     }
@@ -1274,9 +1275,9 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     a.packed = e->packed + begin * e->row_doubles;
     a.packed_row_doubles = e->row_doubles;
     if (e->p2p) {
-        // gather buffers alternate with the body parity: a peer one body ahead writes the other buffer
-        e->p2p_epoch += 1;
-        const int par = (int) (e->p2p_epoch & 1);
+        // gather buffers alternate with the body parity (bodies are numbered from 0 in every run, identically on
+        // every rank): a peer one body ahead writes the other buffer
+        const int par = (int) (e->body & 1);
         e->packed = e->packed_buf[par];
         a.packed = nullptr;
         a.n_peers = e->cfg.world_size;
@@ -1331,7 +1332,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     if (e->p2p) {
         PeerFlags pf;
         for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
-        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 0);
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 0);
         e->all_launches += 1;
         trace_mark(e, "peer barrier end", st);
     }
@@ -1351,7 +1352,9 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
 
 extern "C" int nsb200_engine_step(NsEngine *e, nsb200_stream_t stream) {
     if (!e) return fail("NULL engine");
-    if (e->cfg.world_size != 1) return fail("engine_step requires world_size == 1; use step_begin / all-gather / step_end");
+    if (e->cfg.world_size != 1 && !e->p2p)
+        return fail("engine_step requires world_size == 1 or connected peers (nsb200_engine_p2p_connect); otherwise use "
+                    "step_begin / all-gather / step_end");
     if (e->external) return fail("family EXTERNAL: drive the body with step_begin / engine_split_* / step_end");
     if (nsb200_engine_step_begin(e, stream)) return 1;
     return nsb200_engine_step_end(e, stream);
@@ -1452,7 +1455,7 @@ extern "C" int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream) {
 extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,
                                  int64_t max_iterations, NsRegister *out_register, nsb200_stream_t stream) {
     if (!e) return fail("NULL engine");
-    if (e->cfg.world_size != 1) return fail("engine_run requires world_size == 1");
+    if (e->cfg.world_size != 1 && !e->p2p) return fail("engine_run requires world_size == 1 or connected peers");
     if (e->external) return fail("family EXTERNAL: the caller drives the loop (engine_init_external / step_begin / engine_split_* / step_end)");
     if (nsb200_engine_init(e, key, term_cond, stream)) return 1;
     // Steps are no-ops on the device once the register says done, so the host runs ahead: it keeps

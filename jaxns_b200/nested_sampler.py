@@ -164,10 +164,11 @@ class ShardedStaticNestedSampler:
         if self._engine is None:
             s = self.sampler
             desc = self.model.desc()
+            eng_world = len(self.devices) if self._world > 1 else 1
             cfg = _lib.NsEngineConfig(desc, int(self.num_live_points), int(self.max_samples),
                                       int(self.num_live_points * self.shell_fraction), s.num_slices,
-                                      s.num_phantom_save, int(s.midpoint_shrink), 0, self._rank,
-                                      len(self.devices) if self._world > 1 else 1)
+                                      s.num_phantom_save, int(s.midpoint_shrink), 0,
+                                      self._rank if eng_world > 1 else 0, eng_world)
             self._engine = _Engine(cfg, keepalive=(self.model, desc))
         return self._engine
 
@@ -189,14 +190,17 @@ class ShardedStaticNestedSampler:
             tc = _lib.NsTermCond()  # device stops only on plateau / no seed points; host decides the rest
         reg = _lib.NsRegister()
         world = len(self.devices) if self._world > 1 else 1
-        if getattr(self.model, "is_external", False):
+        external = getattr(self.model, "is_external", False)
+        # fused NVLink all-gather: with connected peers a body needs no host-issued collective, so
+        # the whole loop runs inside the library exactly as on one GPU
+        p2p = world > 1 and not external and self._connect_peers(eng, world)
+        if external:
             host_tc = self._effective_host_cond(term_cond) if not plain else None
             self._run_external(eng, key, tc, reg, stream, world, host_tc)
-        elif plain and world == 1:
+        elif plain and (world == 1 or p2p):
             _lib.check(L.nsb200_engine_run(eng.h, _lib.key_arg(key), ctypes.byref(tc), ctypes.c_int64(-1),
                                            ctypes.byref(reg), stream))
         else:
-            p2p = world > 1 and self._connect_peers(eng, world)
             _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
             gather = self._gather_tensor(eng) if (world > 1 and not p2p) else None
             host_tc = self._effective_host_cond(term_cond) if not plain else None
@@ -238,11 +242,11 @@ class ShardedStaticNestedSampler:
                     one_body()
                     _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
             _lib.check(L.nsb200_engine_finalize(eng.h, stream))
-            if p2p:
-                err = ctypes.c_int32()
-                _lib.check(L.nsb200_engine_p2p_error(eng.h, ctypes.byref(err)))
-                if err.value:
-                    raise RuntimeError("nsb200: a peer GPU did not reach the all-gather barrier (fused NVLink exchange)")
+        if p2p:
+            err = ctypes.c_int32()
+            _lib.check(L.nsb200_engine_p2p_error(eng.h, ctypes.byref(err)))
+            if err.value:
+                raise RuntimeError("nsb200: a peer GPU did not reach the all-gather barrier (fused NVLink exchange)")
         register = termination.register_from_c(reg)
         if plain:
             termination_reason = int(reg.termination_reason)
