@@ -18,7 +18,7 @@ struct EpiScratch {
     NsEvidenceCalc mid, fin;
     unsigned long long sum_new, sum_live;
     int not_plateau;
-    int pad;
+    unsigned bar;  // arrival counter of the register update's software grid barrier (zeroed by the prologue)
 };
 
 __device__ __forceinline__ long long clampll(long long v, long long lo, long long hi) {
@@ -36,6 +36,7 @@ __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSe
     epi->sum_new = 0;
     epi->sum_live = 0;
     epi->not_plateau = 0;
+    epi->bar = 0;
     const LiveSet &live = ctl->cur ? live1 : live0;
     Key k = split_child(ctl->key, 0);      // :491  key, ephemeral_key = split(state.key)
     ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
@@ -381,17 +382,16 @@ __device__ inline void determine_termination(const NsTermCond &tc, NsRegister &r
 // One thread-block cluster (kEvCluster CTAs x kEvThreads threads on neighbouring SMs, hardware
 // cluster barrier between the scan phases).  `old` = live set before the merge (its first m rows are
 // the discarded shell), `cur` = merged live set.
-__global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
-k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet live1, const double *packed,
-                long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
-                const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi,
-                volatile long long *progress) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+template <class Sync>
+__device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsRegister *reg, const LiveSet &live0,
+                                                   const LiveSet &live1, const double *packed, long long row_doubles,
+                                                   int D, long long m, long long N, const NsTermCond &tc, int init_only,
+                                                   const double *tabT, const double *tabT2, const double *tabt,
+                                                   long long tab_n, EpiScratch *epi, volatile long long *progress) {
     __shared__ double sh[3][34];
     if (!init_only && !ctl->active) return;
-    const long long gtid = (long long) cluster.block_rank() * blockDim.x + threadIdx.x;
-    const long long nthreads = (long long) blockDim.x * cluster.num_blocks();
+    const long long gtid = (long long) grp.rank() * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long) blockDim.x * grp.nranks();
     if (init_only) {
         // _main_ns_thread entry (:471-473): no_seed_points of the initial live set, then cond.
         if (gtid == 0) {
@@ -426,8 +426,8 @@ k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet
     out.mark = m;
     out.fin = &epi->fin;
     out.per_sample = nullptr;
-    if (m + N <= 8 * nthreads) evidence_scan_block<8>(q, reg->evidence_calc, out, sh, epi->gpart);
-    else evidence_scan_block<0>(q, reg->evidence_calc, out, sh, epi->gpart);
+    if (m + N <= 8 * nthreads) evidence_scan_block<8>(q, reg->evidence_calc, out, sh, epi->gpart, grp);
+    else evidence_scan_block<0>(q, reg->evidence_calc, out, sh, epi->gpart, grp);
     // sums of likelihood evaluations, plateau flag
     long long sum_new = 0, sum_live = 0;
     int not_plateau = 0;
@@ -449,7 +449,7 @@ k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet
         if (not_plateau) atomicOr(&epi->not_plateau, 1);
     }
     __threadfence();
-    cluster.sync();
+    grp.sync();
     if (gtid == 0) {
         NsRegister r = *reg;
         const NsEvidenceCalc s_mid = epi->mid;
@@ -479,6 +479,28 @@ k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet
             __threadfence_system();
         }
     }
+}
+
+// Cluster form (8 CTAs on one GPC, hardware barrier) and grid form (8 CTAs anywhere, software barrier) of the
+// register update; the engine launches the grid form inside the loop (NSB200_EPI_CLUSTER=1 switches back).
+__global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
+k_iter_epilogue(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet live1, const double *packed,
+                long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
+                const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi,
+                volatile long long *progress) {
+    ClusterSync grp;
+    iter_epilogue_body(grp, ctl, reg, live0, live1, packed, row_doubles, D, m, N, tc, init_only, tabT, tabT2, tabt, tab_n,
+                       epi, progress);
+}
+
+__global__ void __launch_bounds__(kEvThreads)
+k_iter_epilogue_grid(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const LiveSet live1, const double *packed,
+                     long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
+                     const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi,
+                     volatile long long *progress) {
+    GridSync grp{&epi->bar, 0u};
+    iter_epilogue_body(grp, ctl, reg, live0, live1, packed, row_doubles, D, m, N, tc, init_only, tabT, tabT2, tabt, tab_n,
+                       epi, progress);
 }
 
 }  // namespace nsb

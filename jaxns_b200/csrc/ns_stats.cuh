@@ -113,14 +113,41 @@ __device__ __forceinline__ void block_scan_excl_k(const double (&v)[K], double (
 }
 
 // Exclusive scan across all threads of a thread-block CLUSTER (1..16 CTAs on neighbouring SMs):
+// How the CTAs of a multi-CTA scan meet.  ClusterSync: a thread-block cluster and its hardware barrier (the CTAs
+// must be placed on free SMs of ONE GPC).  GridSync: a plain grid of a few CTAs and a counter in global memory
+// (zeroed before the launch) -- the CTAs can land on any free SM, which matters for the per-iteration register
+// update: it runs next to the chain-stream generator, and a cluster waits until the generator has drained a GPC.
+// The grid form spins, so it needs its CTAs to become resident eventually (they do: nothing else waits on them).
+struct ClusterSync {
+    __device__ __forceinline__ unsigned rank() const { return cooperative_groups::this_cluster().block_rank(); }
+    __device__ __forceinline__ unsigned nranks() const { return cooperative_groups::this_cluster().num_blocks(); }
+    __device__ __forceinline__ void sync() { cooperative_groups::this_cluster().sync(); }
+};
+struct GridSync {
+    unsigned *counter;
+    unsigned target;
+    __device__ __forceinline__ unsigned rank() const { return blockIdx.x; }
+    __device__ __forceinline__ unsigned nranks() const { return gridDim.x; }
+    __device__ __forceinline__ void sync() {
+        __syncthreads();
+        target += gridDim.x;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(counter, 1u);
+            while (*(volatile unsigned *) counter < target) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+    }
+};
+
 // CTA-level scan, CTA aggregates exchanged through `gpart` ([ranks][K] doubles of global memory)
-// around one hardware cluster barrier, prefix of the lower-ranked CTAs folded in by warp 0.
-template <class Op, int K>
+// around one barrier of the CTA group, prefix of the lower-ranked CTAs folded in by warp 0.
+template <class Op, int K, class Sync>
 __device__ __forceinline__ void cluster_scan_excl_k(const double (&v)[K], double (*sh)[34], double *gpart,
-                                                    double (&out)[K]) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = cluster.block_rank(), nranks = cluster.num_blocks();
+                                                    double (&out)[K], Sync &grp) {
+    const unsigned rank = grp.rank(), nranks = grp.nranks();
     double exc[K];
     block_scan_excl_k<Op, K>(v, sh, exc);
     if (nranks == 1) {
@@ -132,12 +159,12 @@ __device__ __forceinline__ void cluster_scan_excl_k(const double (&v)[K], double
 #pragma unroll
         for (int k = 0; k < K; ++k) gpart[rank * K + k] = sh[k][32];
     }
-    cluster.sync();
+    grp.sync();
     const int lane = threadIdx.x & 31;
     if (threadIdx.x < 32) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
-            double inc = ((unsigned) lane < nranks) ? gpart[lane * K + k] : Op::id();
+            double inc = ((unsigned) lane < nranks) ? ((volatile double *) gpart)[lane * K + k] : Op::id();
 #pragma unroll
             for (int o = 1; o < 16; o <<= 1) {
                 double y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
@@ -490,15 +517,13 @@ struct EvOut {
 // the per-iteration register update (m + N elements over 1024 threads) runs this way.
 // `gpart` = 3 * 16 * 3 doubles of global scratch for the cluster-level scans (nullptr is fine for a
 // single CTA).
-template <int CACHE>
+template <int CACHE, class Sync>
 __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc &init, const EvOut &out, double (*sh)[34],
-                                           double *gpart) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
+                                           double *gpart, Sync &grp) {
     const double kLog2 = 0.6931471805599453;
     const long long M = q.len_a + q.len_b;
-    const long long nthreads = (long long) blockDim.x * cluster.num_blocks();
-    const long long gtid = (long long) cluster.block_rank() * blockDim.x + threadIdx.x;
+    const long long nthreads = (long long) blockDim.x * grp.nranks();
+    const long long gtid = (long long) grp.rank() * blockDim.x + threadIdx.x;
     const long long per = (M + nthreads - 1) / nthreads;
     const long long b = min(M, gtid * per), e = min(M, b + per);
     double prev0 = init.log_L;
@@ -547,7 +572,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
     double sT = 0.0, sT2 = 0.0;
     NSB_EV_LOOP({ (void) i; (void) logL; sT += t.T; sT2 += t.T2; })
     double in2[2] = {sT, sT2}, ex2[2];
-    cluster_scan_excl_k<OpAdd, 2>(in2, sh, gpart, ex2);
+    cluster_scan_excl_k<OpAdd, 2>(in2, sh, gpart, ex2, grp);
     const double X0 = init.log_X_mean + ex2[0];
     const double X20 = init.log_X2_mean + ex2[1];
     // pass 2: Z, dZ2, W = ZX / X
@@ -565,7 +590,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in3[3] = {sa, sb, sw}, ex3[3];
-    cluster_scan_excl_k<OpLae, 3>(in3, sh, gpart + 48, ex3);
+    cluster_scan_excl_k<OpLae, 3>(in3, sh, gpart + 48, ex3, grp);
     const double Z0 = logaddexp(init.log_Z_mean, ex3[0]);
     const double dZ20 = logaddexp(init.log_dZ2_mean, ex3[1]);
     const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, ex3[2]);
@@ -583,7 +608,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in1[1] = {sc}, ex1[1];
-    cluster_scan_excl_k<OpLae, 1>(in1, sh, gpart + 96, ex1);
+    cluster_scan_excl_k<OpLae, 1>(in1, sh, gpart + 96, ex1, grp);
     const double Z20 = logaddexp(init.log_Z2_mean, ex1[0]);
     // pass 4: outputs (skipped by threads that own neither a requested position nor per-sample rows)
     const bool wanted = out.per_sample || (out.mid && out.mark - 1 >= b && out.mark - 1 < e) || (out.fin && M - 1 >= b && M - 1 < e);
@@ -638,7 +663,8 @@ constexpr int kEvThreads = 512;  // threads per CTA
 __global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
 k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out, double *gpart) {
     __shared__ double sh[3][34];
-    evidence_scan_block<0>(q, init, out, sh, gpart);
+    ClusterSync grp;
+    evidence_scan_block<0>(q, init, out, sh, gpart, grp);
 }
 
 // =================================================================================================

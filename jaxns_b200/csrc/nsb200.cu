@@ -1341,8 +1341,20 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
                                           (int) e->k, e->rank, e->dead);
     trace_mark(e, "merge_scatter end", st);
-    k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m,
-                                         e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
+    // grid form: 8 CTAs on ANY free SMs (a cluster has to wait until the generator has drained one GPC)
+    static int epi_cluster = -1;
+    if (epi_cluster < 0) {
+        const char *ec = getenv("NSB200_EPI_CLUSTER");
+        epi_cluster = (ec && atoi(ec)) ? 1 : 0;
+    }
+    if (epi_cluster)
+        k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D,
+                                                           e->m, e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi,
+                                                           e->progress_dev);
+    else
+        k_iter_epilogue_grid<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles,
+                                                                D, e->m, e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N,
+                                                                e->epi, e->progress_dev);
     NSB_LAUNCH_CHECK();
     trace_mark(e, "epilogue end", st);
     if (e->slice_launches == 64) trace_dump();
