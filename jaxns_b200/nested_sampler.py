@@ -265,12 +265,16 @@ class ShardedStaticNestedSampler:
     def _connect_peers(self, eng, world) -> bool:
         """Wire the engines of all ranks together for the fused all-gather (include/nsb200.h, nsb200_engine_p2p_*):
         CUDA IPC handles of the engine arenas are exchanged once per engine through the process group; every rank
-        must succeed, otherwise all of them keep the host-issued NCCL all-gather."""
+        must succeed, otherwise all of them keep the host-issued NCCL all-gather.  Opt-in (NSB200_P2P=1) in this
+        round: results are identical, but the wiring costs ~15 ms per new engine."""
         if getattr(self, "_p2p_state", None) is not None:
             return self._p2p_state
         import torch.distributed as dist
         L = _lib.lib()
-        ok = os.environ.get("NSB200_P2P", "0") == "1" and world <= 8 and dist.get_backend() == "nccl"
+        if os.environ.get("NSB200_P2P", "0") != "1" or world > 8 or dist.get_backend() != "nccl":
+            self._p2p_state = False  # same decision on every rank (launcher environment), no communication needed
+            return False
+        ok = True
         handle = (ctypes.c_uint8 * 64)()
         offs = (ctypes.c_int64 * 3)()
         if ok and L.nsb200_engine_p2p_export(eng.h, handle, offs) != 0:
@@ -286,9 +290,7 @@ class ShardedStaticNestedSampler:
         flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device="cuda")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN)
         ok = bool(flag.item())
-        _lib.check(L.nsb200_engine_p2p_enabled(eng.h, ctypes.c_int32(1 if ok else 0))) if ok else None
-        if not ok:
-            L.nsb200_engine_p2p_enabled(eng.h, ctypes.c_int32(0))
+        _lib.check(L.nsb200_engine_p2p_enabled(eng.h, ctypes.c_int32(1 if ok else 0)))
         self._p2p_state = ok
         return ok
 
