@@ -315,7 +315,15 @@ def run_native(args, emit=print):
         fam, D_, pk, K, a, b, params = m2.host_arrays()
         h2d = int(a.nbytes + b.nbytes + params.nbytes + 8)
         d2h = int(sum(v.numel() * v.element_size() for v in host.values() if hasattr(v, "numel")) + 8 * 8)
-        del ns2, m2
+        # release this rep's engine (its device arena is freed with it) OUTSIDE the next timed region: `state` holds
+        # zero-copy views of engine memory, so without this the engine would die when `state` is rebound at the end of
+        # the next run -- a cudaFree of the arena between NCCL collectives, seen as 100-600 ms stalls at N > 1
+        del ns2, m2, reason, state, host
+        if rank == 0:
+            del res
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
     te = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
