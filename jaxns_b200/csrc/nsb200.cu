@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cmath>
 #include <string>
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -766,6 +767,7 @@ struct NsEngine {
     // profiling
     std::vector<std::pair<void **, size_t>> arena_slots;  // pointer location, byte offset in the arena
     size_t arena_bytes = 0;
+    int arena_device = -1;
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     double slice_ms = 0.0;
@@ -798,10 +800,33 @@ static int dev_alloc(NsEngine *e, T **p, size_t count) {
     return 0;
 }
 
+// The arena of the most recently destroyed engine is kept (one per process and device) and handed to the next
+// engine of exactly the same size: a sampler rebuilt for every run -- what the public API invites -- then pays no
+// cudaMalloc / cudaFree (each 1-10 ms of driver time for a 100 MB arena, and a device-wide synchronisation).
+struct ArenaCache {
+    void *ptr = nullptr;
+    size_t bytes = 0;
+    int device = -1;
+};
+static ArenaCache g_arena_cache;
+static std::mutex g_arena_mutex;
+
 static int arena_commit(NsEngine *e) {
     void *q = nullptr;
-    cudaError_t err = cudaMalloc(&q, e->arena_bytes);
-    if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", e->arena_bytes, cudaGetErrorString(err));
+    int dev = -1;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_arena_mutex);
+        if (g_arena_cache.ptr && g_arena_cache.bytes == e->arena_bytes && g_arena_cache.device == dev) {
+            q = g_arena_cache.ptr;
+            g_arena_cache = ArenaCache();
+        }
+    }
+    if (!q) {
+        cudaError_t err = cudaMalloc(&q, e->arena_bytes);
+        if (err != cudaSuccess) return fail("cudaMalloc(%zu bytes) failed: %s", e->arena_bytes, cudaGetErrorString(err));
+    }
+    e->arena_device = dev;
     e->allocs.push_back(q);
     for (const auto &sl : e->arena_slots) *sl.first = (char *) q + sl.second;
     return 0;
@@ -811,7 +836,22 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
     if (!e) return;
     for (int r = 0; r < 8; ++r)
         if (e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
-    for (void *p : e->allocs) cudaFree(p);
+    for (void *p : e->allocs) {
+        // kernels of this engine may still be running on the caller's stream: the next owner of the arena is only
+        // safe after they are done (cudaFree would have waited for them as well)
+        cudaDeviceSynchronize();
+        void *evict = p;
+        {
+            std::lock_guard<std::mutex> lock(g_arena_mutex);
+            if (e->arena_bytes && e->arena_device >= 0) {
+                evict = g_arena_cache.ptr;
+                g_arena_cache.ptr = p;
+                g_arena_cache.bytes = e->arena_bytes;
+                g_arena_cache.device = e->arena_device;
+            }
+        }
+        if (evict) cudaFree(evict);
+    }
     if (e->reg_host) cudaFreeHost(e->reg_host);
     if (e->ctl_host) cudaFreeHost(e->ctl_host);
     if (e->progress) cudaFreeHost((void *) e->progress);
