@@ -228,3 +228,104 @@ def test_sample_evidence_matches_deterministic_evidence(oracle):
     assert 0.5 * np.sqrt(var) < samples.std() < 2.0 * np.sqrt(var)
     # simulations are independent of S (simulation s only depends on split(key, S)[s] = TF(key; 0, s))
     np.testing.assert_array_equal(oracle.sample_evidence(oracle.PRNGKey(7), n, log_L, S=3), samples[:3])
+
+
+def test_streaming_max_sum_scan_reproduces_the_serial_evidence_recurrence(oracle):
+    """Groundwork for the round-2 register update: the log-space recurrences of
+    internals/shrinkage_statistics.py:43-94 evaluated with streaming (max, sum) accumulators per chunk and
+    (max, sum) pairs as the scan element -- no log / division on any dependent chain -- must agree with the serial
+    recurrence (the oracle) to the 1e-10 bar, including the per-sample running values early in a run where log L
+    spans thousands of nats (a plain max-shifted linear-space sum would underflow there)."""
+    rng = np.random.default_rng(3)
+    M, N, chunk = 6000, 400, 37
+    log_L = np.sort(np.concatenate([-7000.0 * rng.random(M // 2) ** 3 - 140.0, -140.0 - 30.0 * rng.random(M - M // 2)]))
+    n = np.concatenate([np.full(M - N, float(N)), np.arange(N, 0, -1.0)])
+    ref_final, ref_per = oracle.evidence_scan(oracle.init_evidence_calc(), log_L, n, per_sample=True)
+
+    NEG = -np.inf
+
+    def acc_new():  # (max, sum) with value = max + log(sum); empty = (-inf, 0)
+        return [NEG, 0.0]
+
+    def acc_add(a, x):
+        if x == NEG:
+            return
+        if x <= a[0]:
+            a[1] += np.exp(x - a[0])
+        else:
+            a[1] = a[1] * np.exp(a[0] - x) + 1.0 if a[0] != NEG else 1.0
+            a[0] = x
+
+    def acc_merge(a, b):  # associative combine of two accumulators
+        if b[0] == NEG:
+            return list(a)
+        if a[0] == NEG:
+            return list(b)
+        mx = max(a[0], b[0])
+        return [mx, a[1] * np.exp(a[0] - mx) + b[1] * np.exp(b[0] - mx)]
+
+    def acc_val(a):
+        return a[0] + np.log(a[1]) if a[0] != NEG else NEG
+
+    # n-dependent terms (SURVEY App. B)
+    ln, lnp1, lnp2 = np.log(n), np.log(n + 1.0), np.log(n + 2.0)
+    T = -np.logaddexp(0.0, -ln)
+    T2 = -np.logaddexp(0.0, np.log(2.0) - ln)
+    t, t2, tT = -lnp1, np.log(2.0) - lnp1 - lnp2, T - lnp2
+    mid = np.log(0.5) + np.logaddexp(log_L, np.concatenate([[NEG], log_L[:-1]]))
+    lX_ex = np.concatenate([[0.0], np.cumsum(T)[:-1]])       # exclusive log X, log X2 (pass 1: plain add-scan)
+    lX2_ex = np.concatenate([[0.0], np.cumsum(T2)[:-1]])
+    a_term = lX_ex + t + mid                                   # dZ
+    b_term = lX2_ex + t2 + 2.0 * mid                           # dZ2 / second Z2 term
+    w_term = (lX2_ex + tT + mid) - (lX_ex + T)                 # W = ZX / X increments
+    bounds = list(range(0, M, chunk)) + [M]
+    # pass 2: chunk accumulators, then an exclusive scan of accumulators across chunks
+    def chunk_scan(terms):
+        accs = []
+        for c in range(len(bounds) - 1):
+            a = acc_new()
+            for i in range(bounds[c], bounds[c + 1]):
+                acc_add(a, terms[i])
+            accs.append(a)
+        ex, run = [], acc_new()
+        for a in accs:
+            ex.append(list(run))
+            run = acc_merge(run, a)
+        return ex
+    exZ, exD, exW = chunk_scan(a_term), chunk_scan(b_term), chunk_scan(w_term)
+    # pass 3: Z2 terms need the running W inside the chunk
+    c_terms = np.empty((M, 2))
+    lW_run = np.empty(M)
+    for c in range(len(bounds) - 1):
+        w = list(exW[c])
+        for i in range(bounds[c], bounds[c + 1]):
+            zx_prev = lX_ex[i] + acc_val(w)                    # ZX_{i-1} = X_{i-1} W_{i-1}
+            c_terms[i] = (np.log(2.0) + zx_prev + t[i] + mid[i], b_term[i])
+            acc_add(w, w_term[i])
+            lW_run[i] = acc_val(w)
+    accs = []  # two terms per element go into the same accumulator
+    for c in range(len(bounds) - 1):
+        a = acc_new()
+        for i in range(bounds[c], bounds[c + 1]):
+            acc_add(a, c_terms[i, 0])
+            acc_add(a, c_terms[i, 1])
+        accs.append(a)
+    exC, run = [], acc_new()
+    for a in accs:
+        exC.append(list(run))
+        run = acc_merge(run, a)
+    # pass 4: per-sample outputs from the running accumulators
+    got = np.empty((M, 8))
+    for c in range(len(bounds) - 1):
+        z, d, z2 = list(exZ[c]), list(exD[c]), list(exC[c])
+        for i in range(bounds[c], bounds[c + 1]):
+            acc_add(z, a_term[i])
+            acc_add(d, b_term[i])
+            acc_add(z2, c_terms[i, 0])
+            acc_add(z2, c_terms[i, 1])
+            lX, lX2 = lX_ex[i] + T[i], lX2_ex[i] + T2[i]
+            got[i] = (log_L[i], lX, lX2, acc_val(z), lX + lW_run[i], acc_val(z2), a_term[i], acc_val(d))
+    fin = np.isfinite(ref_per)
+    assert np.array_equal(fin, np.isfinite(got))
+    np.testing.assert_allclose(got[fin], ref_per[fin], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(got[-1], ref_final, rtol=1e-10)
