@@ -355,3 +355,27 @@ def test_oracle_run_passes_the_references_own_result_check(oracle, seed):
     np.testing.assert_allclose(mean, true, atol=3.0 * r["log_Z_uncert"])
     np.testing.assert_allclose(r["log_Z_mean"], mean, atol=3.0 * r["log_Z_uncert"])
     np.testing.assert_allclose(r["log_Z_uncert"], std, atol=np.sqrt(r["log_Z_uncert"] ** 2 + std ** 2))
+
+
+def test_golden_fixture_whole_run(oracle):
+    """tests/golden/run_vectors.json (make_run_vectors.py): a tiny whole run -- dead-point store bookkeeping, phantom
+    rows, sender indices, evaluation counts and tree counts exactly; floats to 1e-9 (libm)."""
+    g = json.load(open(os.path.join(GOLDEN, "run_vectors.json")))
+    ns = oracle.OracleNestedSampler(oracle.gauss_model(g["D"]), g["N"], g["S"], g["k"], True, max_samples=g["N"] * 40)
+    reason, st = ns.run(np.array(g["key"], dtype=np.uint32), max_iterations=g["max_iterations"])
+    r = ns.to_results(reason, st)
+    n = g["num_samples"]
+    assert int(st["num_samples"]) == n and int(st["next_sample_idx"]) == g["next_sample_idx"]
+    assert int(reason) == g["termination_reason"]
+    np.testing.assert_array_equal(st["sender"][:n], g["sender"])
+    np.testing.assert_array_equal(st["phantom"][:n].astype(int), g["phantom"])
+    np.testing.assert_array_equal(st["n_evals"][:n], g["n_evals"])
+    np.testing.assert_allclose(st["log_L"][:n], g["log_L"], rtol=1e-9)
+    np.testing.assert_allclose(st["U"][0], g["U_row0"], rtol=1e-9)
+    np.testing.assert_allclose(st["U"][n - 1], g["U_last"], rtol=1e-9)
+    np.testing.assert_array_equal(r["samples_indices"], g["samples_indices"])
+    np.testing.assert_array_equal(r["num_live_points_per_sample"], g["num_live_points_per_sample"])
+    for name in ("log_Z_mean", "log_Z_uncert", "ESS", "H_mean"):
+        np.testing.assert_allclose(r[name], g[name], rtol=1e-9)
+    assert r["total_num_likelihood_evaluations"] == g["total_num_likelihood_evaluations"]
+    assert r["total_phantom_samples"] == g["total_phantom_samples"]
