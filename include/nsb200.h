@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NSB200_ABI_VERSION 1
+#define NSB200_ABI_VERSION 2
 
 typedef void *nsb200_stream_t; /* cudaStream_t */
 
@@ -108,7 +108,7 @@ typedef struct NsRegister {
     double absolute_spread;
     double peak_log_XL;
     int32_t done;               /* determine_termination(...)[0] */
-    int32_t reserved;
+    int32_t error_flags;        /* NSB200_ERR_* bits raised by the device loop (0 = clean run) */
     int64_t termination_reason; /* determine_termination(...)[1], bit map termination.py:17-29 */
     int64_t iteration;
 } NsRegister;
@@ -153,9 +153,22 @@ typedef struct NsStateView {
 
 typedef struct NsEngine NsEngine;
 
+/* Device-side error bits (NsRegister.error_flags; the whole-run entry points turn them into an error return). */
+enum {
+    NSB200_ERR_SHRINK_LOOP = 1, /* a slice did not accept within 65536 proposals: the likelihood is non-deterministic
+                                   or NaN at its own seed point (the reference's lax.while_loop would spin forever,
+                                   samplers/uni_slice_sampler.py:160-196) */
+    NSB200_ERR_PEER_TIMEOUT = 2 /* a peer GPU did not reach the fused all-gather's arrival barrier */
+};
+
 /* ---- misc ----------------------------------------------------------------------------------- */
 int nsb200_abi_version(void);
 const char *nsb200_last_error(void);
+/* Tuning / A-B knobs (launch geometry, kernel selection: results never depend on them).  Every knob is also an
+ * environment variable of the same name, read once per process; value < 0 returns to that default.  Names:
+ * NSB200_SPEC, NSB200_TPB, NSB200_SLICE_MMA, NSB200_MMA_P, NSB200_MMA_WPB, NSB200_MERGE_BRUTE, NSB200_GEN_MODE,
+ * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_EPI_CLUSTER, NSB200_DEPTH, NSB200_TRACE, NSB200_SORT_LEGACY. */
+int nsb200_set_option(const char *name, int32_t value);
 
 /* ---- jax.random under jax_threefry_partitionable=True (internals/mixed_precision.py:11-15) --- */
 /* threefry2x32 primitive over n counter pairs (device arrays). */
@@ -198,6 +211,19 @@ int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams *p, const u
                        const double *contour, const double *live_U, const double *live_logL,
                        const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
                        double *ph_U, double *ph_logL, nsb200_stream_t stream);
+
+/* Same call with caller-provided scratch for the chains' data-independent streams (directions, proposal
+ * uniforms, continuation keys: nothing in a chain's key tree depends on a likelihood value, so they are produced
+ * by a throughput kernel first).  With the streams available the dense-Gaussian family with D <= 32 runs on the
+ * FP64 tensor-core path (8 proposals per warp through mma.sync.m8n8k4.f64); results are identical to
+ * nsb200_slice_batch up to the summation order of the quadratic form.  workspace_bytes >=
+ * nsb200_slice_streams_bytes(D, num_slices, chain_end - chain_begin). */
+int64_t nsb200_slice_streams_bytes(int32_t D, int32_t num_slices, int64_t n_chains);
+int nsb200_slice_batch_ws(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                          const double *contour, const double *live_U, const double *live_logL,
+                          const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
+                          double *ph_U, double *ph_logL, void *workspace, int64_t workspace_bytes,
+                          int32_t *error_flags, nsb200_stream_t stream);
 
 /* ---- B1 for likelihoods the library cannot fuse: the slice step split around a caller-evaluated
  * batched likelihood (BASELINE north_star).  Same chains as nsb200_slice_batch

@@ -54,7 +54,7 @@ class NsRegister(ctypes.Structure):
                 ("log_L_contour", ctypes.c_double), ("efficiency", ctypes.c_double), ("plateau", ctypes.c_int32),
                 ("no_seed_points", ctypes.c_int32), ("relative_spread", ctypes.c_double),
                 ("absolute_spread", ctypes.c_double), ("peak_log_XL", ctypes.c_double), ("done", ctypes.c_int32),
-                ("reserved", ctypes.c_int32), ("termination_reason", ctypes.c_int64), ("iteration", ctypes.c_int64)]
+                ("error_flags", ctypes.c_int32), ("termination_reason", ctypes.c_int64), ("iteration", ctypes.c_int64)]
 
 
 class NsEngineConfig(ctypes.Structure):
@@ -78,7 +78,7 @@ WS_ARGSORT, WS_COUNT_CROSSED_EDGES, WS_EVIDENCE_STATS, WS_LOGSUMEXP = 0, 1, 2, 3
 
 # every symbol include/nsb200.h declares
 EXPORTS = (
-    "nsb200_abi_version", "nsb200_last_error", "nsb200_threefry2x32", "nsb200_random_split",
+    "nsb200_abi_version", "nsb200_last_error", "nsb200_set_option", "nsb200_threefry2x32", "nsb200_random_split",
     "nsb200_random_bits64", "nsb200_random_uniform", "nsb200_random_normal", "nsb200_forward_batch",
     "nsb200_seed_table", "nsb200_init_batch", "nsb200_slice_batch", "nsb200_uniform_batch",
     "nsb200_workspace_bytes", "nsb200_argsort_f64", "nsb200_count_crossed_edges", "nsb200_evidence_stats",
@@ -89,6 +89,7 @@ EXPORTS = (
     "nsb200_split_workspace_bytes", "nsb200_split_begin", "nsb200_split_accept", "nsb200_split_finish",
     "nsb200_init_propose", "nsb200_transform_batch", "nsb200_engine_init_external", "nsb200_engine_split_begin",
     "nsb200_engine_split_accept", "nsb200_engine_split_finish", "nsb200_sample_evidence",
+    "nsb200_slice_streams_bytes", "nsb200_slice_batch_ws",
     "nsb200_engine_p2p_export", "nsb200_engine_p2p_connect", "nsb200_engine_p2p_enabled", "nsb200_engine_p2p_error",
 )
 
@@ -112,8 +113,15 @@ def lib():
         L.nsb200_engine_destroy.restype = None
         L.nsb200_split_workspace_bytes.restype = ctypes.c_int64
         L.nsb200_split_workspace_bytes.argtypes = [ctypes.c_int32, ctypes.c_int64, ctypes.c_int32]
+        L.nsb200_slice_streams_bytes.restype = ctypes.c_int64
+        L.nsb200_slice_streams_bytes.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_int64]
         _lib = L
     return _lib
+
+
+def set_option(name: str, value: int):
+    """Tuning / A-B knob of the library (include/nsb200.h nsb200_set_option); value < 0 restores the default."""
+    check(lib().nsb200_set_option(name.encode(), ctypes.c_int32(int(value))))
 
 
 def check(rc: int):

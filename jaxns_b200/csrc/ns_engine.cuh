@@ -302,8 +302,8 @@ struct PeerFlags {
     unsigned long long *p[8];
 };
 
-__global__ void k_peer_barrier(const DevCtl *ctl, unsigned long long *epoch_dev, volatile unsigned long long *mine,
-                               PeerFlags peers, int world, int me, int *err, int force) {
+__global__ void k_peer_barrier(DevCtl *ctl, unsigned long long *epoch_dev, volatile unsigned long long *mine,
+                               PeerFlags peers, int world, int me, int *err, int force, volatile long long *progress) {
     if (!force && !ctl->active) return;
     // The epoch counts the barriers this engine has passed.  It lives on the device and only advances for ACTIVE
     // bodies (and run entries), which every rank executes identically -- the host may enqueue different numbers of
@@ -324,6 +324,11 @@ __global__ void k_peer_barrier(const DevCtl *ctl, unsigned long long *epoch_dev,
         __nanosleep(200);
         if (++spins > 150000000ll) {  // ~30 s
             atomicExch(err, 1);
+            atomicOr(&ctl->err, NSB200_ERR_PEER_TIMEOUT);
+            if (progress) {  // host-mapped: nsb200_engine_run polls it instead of spinning on a run that cannot finish
+                progress[2] = 1;
+                __threadfence_system();
+            }
             break;
         }
     }
@@ -467,7 +472,9 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
         r.no_seed_points = cur.logL[m - 1] >= hi;
         r.peak_log_XL = fmax(r.peak_log_XL, s_mid.log_X_mean + s_mid.log_L);
         r.iteration = ctl->iteration;
+        r.error_flags = *(volatile int *) &ctl->err;
         determine_termination(tc, r);
+        if (r.error_flags) r.done = 1;  // a flagged run stops at once (the host turns the flags into an error)
         *reg = r;
         ctl->cur ^= 1;
         if (progress) {

@@ -293,6 +293,48 @@ __device__ __forceinline__ void ndtri_batch(const double (&p)[P], unsigned mask,
     }
 }
 
+// K quantiles per lane for warps whose 32 lanes are convergent (the round-synchronous DMMA slice kernel keeps 8
+// dimensions of one proposal in every lane).  The K central rationals are straight-line code; tail values are
+// sparse (late in a run a few of the warp's 32 K values per round), so they are drained through a vote loop
+// that evaluates ONE pending value per lane per trip instead of a K-wide tail block.  Same operations per element
+// as ndtri(): bit-identical results.
+template <int K>
+__device__ __forceinline__ void ndtri_multi(const double (&p)[K], double (&x)[K]) {
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+    unsigned pend = 0;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const double q = p[i] - 0.5;
+        const double r = fma(-q, q, 0.180625);
+        x[i] = fast_div_finite(q * horner8(kPpndA, r), horner8(kPpndB, r));
+        pend |= (!(fabs(q) <= 0.425)) ? (1u << i) : 0u;  // also true for NaN
+    }
+    while (__any_sync(0xFFFFFFFFu, pend != 0)) {
+        const int i0 = __ffs((int) pend) - 1;  // -1: nothing pending in this lane
+        double pv = 0.5;
+#pragma unroll
+        for (int i = 0; i < K; ++i) pv = (i == i0) ? p[i] : pv;
+        const bool tail = pend != 0;
+        const double q = pv - 0.5;
+        double pp = (q < 0.0) ? pv : 1.0 - pv;
+        pp = tail ? pp : 0.05;  // idle lanes stay on the fast paths of log / sqrt
+        const double rr = sqrt(-log(pp));
+        const double a = rr - 1.6, b = rr - 5.0;
+        double v = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
+        if (__any_sync(0xFFFFFFFFu, rr > 5.0)) {  // far tail (p < 1.4e-11): rare, warp-uniform
+            const double v2 = fast_div_finite(horner8(kPpndE, b), horner8(kPpndF, b));
+            v = (rr <= 5.0) ? v : v2;
+        }
+        v = (q < 0.0) ? -v : v;
+        if (pv == 0.0) v = -kInf;
+        if (pv == 1.0) v = kInf;
+        if (!(pv >= 0.0 && pv <= 1.0)) v = __longlong_as_double(0x7FF8000000000000ll);
+#pragma unroll
+        for (int i = 0; i < K; ++i) x[i] = (i == i0) ? v : x[i];
+        pend &= pend - 1u;
+    }
+}
+
 // log1p(e) for e in [0, 1] with one log and one division (Kahan): libdevice's log1p costs ~300
 // instructions, this ~70, and it is accurate to an ulp or two on that range.
 __device__ __forceinline__ double log1p_unit(double e) {

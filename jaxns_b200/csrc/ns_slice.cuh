@@ -55,6 +55,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 // back to walking the run_key chain inline).
 constexpr int kPre = 8;
 
+// Watchdog of the shrink loop: a bracket that has collapsed onto the seed point re-evaluates the seed
+// itself, which satisfies the constraint, so a deterministic likelihood accepts within ~2200 halvings of a double.
+// A chain still shrinking after this many proposals of ONE slice faces a non-deterministic (or NaN at the seed)
+// likelihood: it stays where it is and NSB200_ERR_SHRINK_LOOP is raised instead of hanging the GPU.
+constexpr int kMaxShrinkProposals = 1 << 16;
+
 struct SliceArgs {
     NsModelDesc model;
     Key key;                // get_samples key: chain keys = split(key, m)
@@ -88,6 +94,7 @@ struct SliceArgs {
     // kernel runs between the chains and the merge -- only an arrival barrier (k_peer_barrier)
     int n_peers;
     double *peers[8];  // this rank's block inside rank r's gather buffer
+    int *err;          // optional device word: NSB200_ERR_* bits are OR-ed in (shrink-loop watchdog)
 };
 
 __device__ __forceinline__ void packed_store(const SliceArgs &a, long long off, double v) {
@@ -462,6 +469,11 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                 ne += P;
                 left = l;
                 right = r;
+                if (ne >= kMaxShrinkProposals) {  // watchdog: stay at the current point, flag the run
+                    if (a.err && g.lane == 0) atomicOr(a.err, NSB200_ERR_SHRINK_LOOP);
+                    logL_acc = logL0;
+                    break;
+                }
             }
             NSB_TICK(6)  // accept logic / loop overhead
             logL0 = logL_acc;

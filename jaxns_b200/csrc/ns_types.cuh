@@ -20,6 +20,7 @@ struct DevCtl {
     long long sender;      // sender_node_idx of the replacements
     int active;            // 0 once the register says done: every step kernel becomes a no-op
     int cur;               // which of the two live buffers is current
+    int err;               // NSB200_ERR_* bits raised by device code during the run (copied into NsRegister.error_flags)
 };
 
 struct LiveSet {

@@ -7,12 +7,15 @@
 #include <cstdlib>
 #include <cmath>
 #include <string>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
 #include "ns_engine.cuh"
 #include "ns_slice.cuh"
+#include "ns_slice_mma.cuh"
 #include "ns_split.cuh"
 
 using namespace nsb;
@@ -46,6 +49,52 @@ static int fail(const char *fmt, ...) {
 
 extern "C" int nsb200_abi_version(void) { return NSB200_ABI_VERSION; }
 extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
+
+// Tuning / A-B knobs.  Each is an integer option whose default comes from an environment variable read ONCE per
+// process (getenv walks the whole environment: it has no place on a per-launch path); nsb200_set_option overrides
+// it at run time (tests A/B kernels inside one process).  None of them changes results.
+enum {
+    OPT_SPEC, OPT_TPB, OPT_SLICE_MMA, OPT_MMA_P, OPT_MMA_WPB, OPT_MERGE_BRUTE, OPT_GEN_MODE, OPT_GEN_SMS, OPT_GEN_TPB,
+    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_SORT_LEGACY, OPT_COUNT
+};
+struct NsOption {
+    const char *name;
+    int dflt;
+    int value;
+    bool loaded;
+};
+static NsOption g_opts[OPT_COUNT] = {
+    {"NSB200_SPEC", 0, 0, false},        {"NSB200_TPB", 0, 0, false},         {"NSB200_SLICE_MMA", 1, 0, false},
+    {"NSB200_MMA_P", 0, 0, false},       {"NSB200_MMA_WPB", 4, 0, false},     {"NSB200_MERGE_BRUTE", 0, 0, false},
+    {"NSB200_GEN_MODE", 3, 0, false},    {"NSB200_GEN_SMS", 0, 0, false},     {"NSB200_GEN_TPB", 0, 0, false},
+    {"NSB200_EPI_CLUSTER", 0, 0, false}, {"NSB200_DEPTH", 4, 0, false},       {"NSB200_TRACE", 0, 0, false},
+    {"NSB200_SORT_LEGACY", 0, 0, false},
+};
+static int opt(int id) {
+    NsOption &o = g_opts[id];
+    if (!o.loaded) {
+        const char *e = getenv(o.name);
+        o.value = (e && *e) ? atoi(e) : o.dflt;
+        o.loaded = true;
+    }
+    return o.value;
+}
+
+extern "C" int nsb200_set_option(const char *name, int32_t value) {
+    if (!name) return fail("option name is NULL");
+    for (int i = 0; i < OPT_COUNT; ++i) {
+        if (strcmp(name, g_opts[i].name) == 0) {
+            if (value < 0) {
+                g_opts[i].loaded = false;  // back to the environment / built-in default
+            } else {
+                g_opts[i].value = value;
+                g_opts[i].loaded = true;
+            }
+            return 0;
+        }
+    }
+    return fail("unknown option %s", name);
+}
 
 // -------------------------------------------------------------------------------------------------
 // launch geometry: group size G (lanes per chain) and DPL (dims per lane)
@@ -135,11 +184,8 @@ static int set_smem(KernelT kernel, size_t bytes) {
 // overrides it for the D <= 32 instantiation (tuning knob; results do not depend on it).
 static int pick_spec(const Geometry &g) {
     if (g.G == 32 && g.DPL == 1) {
-        const char *e = getenv("NSB200_SPEC");
-        if (e) {
-            const int v = atoi(e);
-            if (v == 1 || v == 2 || v == 4) return v;
-        }
+        const int spec = opt(OPT_SPEC);
+        if (spec == 1 || spec == 2 || spec == 4) return spec;
         // measured on config 2 (profiles/r1/spec_sweep_r1.txt): P = 2 with the batched quantile is 1.4 % faster than
         // P = 1 end to end (rounds per slice 4.8 -> 2.6, instructions +5 %), P = 4 is 17 % slower
         return 2;
@@ -292,11 +338,8 @@ extern "C" int nsb200_uniform_batch(const NsModelDesc *model, const uint32_t key
 // per CTA, so one chain per CTA gives the block scheduler the finest grain to balance the 148 SMs.
 static int slice_threads(const Geometry &g) {
     int tpb = (g.G == 32 && g.DPL == 1) ? 32 : kThreadsPerBlock;
-    const char *e = getenv("NSB200_TPB");
-    if (e) {
-        const int v = atoi(e);
-        if (v == 32 || v == 64 || v == 128) tpb = v;
-    }
+    const int v = opt(OPT_TPB);
+    if (v == 32 || v == 64 || v == 128) tpb = v;
     return tpb < g.G ? g.G : tpb;
 }
 
@@ -324,10 +367,76 @@ static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st
     return 0;
 }
 
+// ---- FP64 tensor-core slice kernel (ns_slice_mma.cuh): dense Gaussian, D <= 32, pre-generated streams ----------
+static bool slice_mma_eligible(const SliceArgs &a) {
+    // NSB200_SLICE_MMA=0: always the lane-per-dimension kernel (A/B, parity)
+    return opt(OPT_SLICE_MMA) != 0 && a.model.family == NSB200_FAM_GAUSS_DENSE && a.model.D <= 32 && a.pre_dirs != nullptr;
+}
+
+// Speculative proposals per chain and round: a warp carries 8 proposal columns = 8 / P chains.  One warp per SM
+// sub-partition keeps the FP64 pipe of that sub-partition busy on its own (8 independent quantiles per lane), so
+// P grows as the chains get fewer (strong scaling over GPUs) until the warps no longer cover the sub-partitions.
+static int slice_mma_spec(long long n_chains) {
+    const int forced = opt(OPT_MMA_P);
+    if (forced == 1 || forced == 2 || forced == 4) return forced;
+    static int smsp = 0;
+    if (!smsp) {
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        smsp = 4 * sms;
+    }
+    if (n_chains * 4 / 8 <= smsp) return 4;
+    if (n_chains * 2 / 8 <= smsp) return 2;
+    return 1;
+}
+
+template <int NB, int P>
+static int launch_slice_mma_t(const SliceArgs &a, cudaStream_t st, bool pdl) {
+    const int wpb_env = opt(OPT_MMA_WPB);
+    const int wpb = (wpb_env >= 1 && wpb_env <= 4) ? wpb_env : 4;
+    const long long n = a.chain_end - a.chain_begin;
+    const long long per_cta = (long long) wpb * (8 / P);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned) ((n + per_cta - 1) / per_cta));
+    cfg.blockDim = dim3((unsigned) (32 * wpb));
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    NSB_CUDA(cudaLaunchKernelEx(&cfg, k_slice_chains_mma<NB, P>, a));
+    return 0;
+}
+
+template <int NB>
+static int launch_slice_mma_nb(const SliceArgs &a, cudaStream_t st, bool pdl) {
+    switch (slice_mma_spec(a.chain_end - a.chain_begin)) {
+        case 1: return launch_slice_mma_t<NB, 1>(a, st, pdl);
+        case 4: return launch_slice_mma_t<NB, 4>(a, st, pdl);
+        default: return launch_slice_mma_t<NB, 2>(a, st, pdl);
+    }
+}
+
+static int launch_slice_mma(const SliceArgs &a, cudaStream_t st, bool pdl) {
+    int rc;
+    const int D = a.model.D;
+    if (D <= 8) rc = launch_slice_mma_nb<1>(a, st, pdl);
+    else if (D <= 16) rc = launch_slice_mma_nb<2>(a, st, pdl);
+    else if (D <= 24) rc = launch_slice_mma_nb<3>(a, st, pdl);
+    else rc = launch_slice_mma_nb<4>(a, st, pdl);
+    if (rc) return rc;
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
 static int launch_slice(const SliceArgs &a, cudaStream_t st, bool pdl = false) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
     if (a.chain_end <= a.chain_begin) return 0;
+    if (slice_mma_eligible(a)) return launch_slice_mma(a, st, pdl);
     const int P = pick_spec(g);
     if (g.G == 32 && g.DPL == 1) {
         int rc;
@@ -350,10 +459,10 @@ static int launch_slice(const SliceArgs &a, cudaStream_t st, bool pdl = false) {
     return 0;
 }
 
-extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
-                                  const double *contour, const double *live_U, const double *live_logL,
-                                  const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
-                                  double *ph_U, double *ph_logL, nsb200_stream_t stream) {
+static int slice_batch_args(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                            const double *contour, const double *live_U, const double *live_logL,
+                            const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
+                            double *ph_U, double *ph_logL, SliceArgs &a) {
     if (check_model(model)) return 1;
     if (!p) return fail("params is NULL");
     if (p->num_slices < 1) return fail("num_slices should be >= 1, got %d", p->num_slices);
@@ -364,10 +473,9 @@ extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams 
     if (p->chain_begin < 0 || p->chain_end > p->num_samples || p->chain_begin > p->chain_end)
         return fail("bad chain range [%lld, %lld) of %lld", (long long) p->chain_begin, (long long) p->chain_end,
                     (long long) p->num_samples);
-    if (!contour || !live_U || !live_logL || !seed_table) return fail("input pointer is NULL");
+    if (!key || !contour || !live_U || !live_logL || !seed_table) return fail("input pointer is NULL");
     if (!out_U || !out_logL || !out_nevals) return fail("output pointer is NULL");
     if (p->num_phantom > 0 && (!ph_U || !ph_logL)) return fail("phantom outputs are NULL but num_phantom > 0");
-    SliceArgs a;
     memset(&a, 0, sizeof(a));
     a.model = *model;
     a.key = Key{key[0], key[1]};
@@ -386,10 +494,85 @@ extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams 
     a.S = p->num_slices;
     a.k = p->num_phantom;
     a.midpoint = p->midpoint_shrink;
-    a.packed = nullptr;
-    a.packed_row_doubles = 0;
-    a.ctl = nullptr;
+    return 0;
+}
+
+extern "C" int nsb200_slice_batch(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                                  const double *contour, const double *live_U, const double *live_logL,
+                                  const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
+                                  double *ph_U, double *ph_logL, nsb200_stream_t stream) {
+    SliceArgs a;
+    if (slice_batch_args(model, p, key, contour, live_U, live_logL, seed_table, out_U, out_logL, out_nevals, ph_U,
+                         ph_logL, a))
+        return 1;
     return launch_slice(a, (cudaStream_t) stream);
+}
+
+// chain streams of n chains x S slices: directions [n][S][D], proposal uniforms [n][S][kPre], continuation keys
+// [n][S], + one error word
+static size_t slice_streams_bytes(int D, int S, long long n) {
+    const size_t rows = (size_t) n * (size_t) S;
+    return align256(rows * D * 8) + align256(rows * kPre * 8) + align256(rows * 8) + 256;
+}
+
+extern "C" int64_t nsb200_slice_streams_bytes(int32_t D, int32_t num_slices, int64_t n_chains) {
+    if (D < 1 || num_slices < 1 || n_chains < 0) return -1;
+    return (int64_t) slice_streams_bytes(D, num_slices, n_chains);
+}
+
+static int launch_chain_streams(const StreamArgs &sa, int ctas, int tpb, size_t smem, cudaStream_t st) {
+    const long long warps = (sa.chain_end - sa.chain_begin) * ((sa.S + 31) / 32);
+    const long long wpc = tpb / 32;
+    if ((long long) ctas * wpc > warps) ctas = (int) ((warps + wpc - 1) / wpc);
+    if (ctas < 1) return 0;
+    k_chain_streams<<<ctas, tpb, smem, st>>>(sa);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_slice_batch_ws(const NsModelDesc *model, const NsSliceParams *p, const uint32_t key[2],
+                                     const double *contour, const double *live_U, const double *live_logL,
+                                     const double *seed_table, double *out_U, double *out_logL, int64_t *out_nevals,
+                                     double *ph_U, double *ph_logL, void *workspace, int64_t workspace_bytes,
+                                     int32_t *error_flags, nsb200_stream_t stream) {
+    SliceArgs a;
+    if (slice_batch_args(model, p, key, contour, live_U, live_logL, seed_table, out_U, out_logL, out_nevals, ph_U,
+                         ph_logL, a))
+        return 1;
+    const long long n = a.chain_end - a.chain_begin;
+    if (n <= 0) return 0;
+    Geometry g;
+    if (pick_geometry(model->D, g)) return 1;
+    cudaStream_t st = (cudaStream_t) stream;
+    a.err = (int *) error_flags;  // optional DEVICE word, OR-ed with NSB200_ERR_* bits
+    if (g.G >= 8) {  // narrower groups keep their in-kernel lane-parallel stream precompute
+        if (!workspace) return fail("workspace is NULL");
+        if (workspace_bytes < (int64_t) slice_streams_bytes(model->D, a.S, n))
+            return fail("workspace too small: %lld < %zu (nsb200_slice_streams_bytes)", (long long) workspace_bytes,
+                        slice_streams_bytes(model->D, a.S, n));
+        const size_t rows = (size_t) n * (size_t) a.S;
+        char *w = (char *) align256((size_t) workspace);
+        StreamArgs sa;
+        sa.key = a.key;
+        sa.ctl = nullptr;
+        sa.key_slot = 0;
+        sa.chain_begin = a.chain_begin;
+        sa.chain_end = a.chain_end;
+        sa.S = a.S;
+        sa.D = model->D;
+        sa.dirs = (double *) w;
+        w += align256(rows * model->D * 8);
+        sa.us = (double *) w;
+        w += align256(rows * kPre * 8);
+        sa.rkeys = (uint2 *) w;
+        int sms = 148;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        if (launch_chain_streams(sa, sms, 1024, 0, st)) return 1;
+        a.pre_dirs = sa.dirs;
+        a.pre_us = sa.us;
+        a.pre_rkeys = sa.rkeys;
+    }
+    return launch_slice(a, st);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -700,6 +883,7 @@ __global__ void k_init_ctl(DevCtl *ctl, Key key) {
     ctl->ph_start = 0;
     ctl->sender = 0;
     ctl->active = 1;
+    ctl->err = 0;
     ctl->cur = 1;  // the init scatter writes live0 ("other" buffer of cur = 1)
 }
 
@@ -892,7 +1076,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     e->row_doubles = (e->D + 2) + e->k * (e->D + 1);
     e->packed_rows = e->N > e->m ? e->N : e->m;  // the init pass packs all N prior draws
     e->external = cfg->model.family == NSB200_FAM_EXTERNAL;
-    if (const char *pe = getenv("NSB200_GEN_MODE")) e->gen_mode = atoi(pe);
+    e->gen_mode = opt(OPT_GEN_MODE);
     if (e->gen_mode < 0 || e->gen_mode > 4) e->gen_mode = 3;
     e->pdl = e->gen_mode == 1;
     const size_t D = e->D;
@@ -965,6 +1149,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
             e->progress = (volatile long long *) hp;
             e->progress[0] = -1;
             e->progress[1] = 0;
+            e->progress[2] = 0;
             if (cudaHostGetDevicePointer((void **) &e->progress_dev, hp, 0) != cudaSuccess) rc = fail("cudaHostGetDevicePointer failed");
         }
     }
@@ -1072,8 +1257,8 @@ static NsTermCond effective_term_cond(const NsEngine *e, const NsTermCond *tc) {
 static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t after);
 
 static void launch_merge_rank(NsEngine *e, long long m_new, cudaStream_t st) {
-    const char *brute = getenv("NSB200_MERGE_BRUTE");  // A/B and parity knob: results do not depend on it
-    if (!(brute && atoi(brute)) && m_new >= 2048) {
+    // NSB200_MERGE_BRUTE: A/B and parity knob, results do not depend on it
+    if (!opt(OPT_MERGE_BRUTE) && m_new >= 2048) {
         const unsigned tiles = (unsigned) ((m_new + kMergeTile - 1) / kMergeTile);
         k_merge_sort_tiles<<<tiles, kMergeTile, 0, st>>>(e->ctl, e->packed, e->row_doubles, e->D, m_new, e->sorted_new,
                                                          e->new_pos);
@@ -1099,6 +1284,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     e->tc = effective_term_cond(e, term_cond);
     e->progress[0] = -1;
     e->progress[1] = 0;
+    e->progress[2] = 0;
     e->slice_ms = 0.0;
     e->slice_launches = 0;
     e->all_launches = 0;
@@ -1108,7 +1294,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     if (e->p2p) {  // run-entry barrier: peers may only store rows of this run once every rank has left the previous one
         PeerFlags pf;
         for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
-        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 1);
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 1, e->progress_dev);
     }
     // create_init_state (initialisation.py:38-47): empty dead store, key split
     NSB_CUDA(cudaMemsetAsync(e->dead.sender, 0, (size_t) e->cap * 8, st));
@@ -1179,9 +1365,7 @@ extern "C" int nsb200_engine_init_external(NsEngine *e, const uint32_t key[2], c
 struct TraceMark { cudaEvent_t ev; const char *name; };
 static std::vector<TraceMark> g_trace;
 static bool trace_on(NsEngine *e) {
-    static int on = -1;
-    if (on < 0) on = getenv("NSB200_TRACE") ? 1 : 0;
-    return on && e->slice_launches >= 60 && e->slice_launches < 64;
+    return opt(OPT_TRACE) && e->slice_launches >= 60 && e->slice_launches < 64;
 }
 static void trace_mark(NsEngine *e, const char *name, cudaStream_t s) {
     if (!trace_on(e)) return;
@@ -1269,8 +1453,8 @@ static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t af
         tpb = 1024;
         if (e->gen_mode == 4) tpb = 128;  // back-fill: one small CTA per SM in the registers the chains leave free
     }
-    if (const char *pe = getenv("NSB200_GEN_SMS")) gen_ctas = atoi(pe) > 0 ? atoi(pe) : gen_ctas;
-    if (const char *pe = getenv("NSB200_GEN_TPB")) tpb = (atoi(pe) >= 32 && atoi(pe) <= 1024) ? (atoi(pe) / 32) * 32 : tpb;
+    if (opt(OPT_GEN_SMS) > 0) gen_ctas = opt(OPT_GEN_SMS);
+    if (opt(OPT_GEN_TPB) >= 32 && opt(OPT_GEN_TPB) <= 1024) tpb = (opt(OPT_GEN_TPB) / 32) * 32;
     const long long wpc = tpb / 32;
     if ((long long) gen_ctas * wpc > warps) gen_ctas = (int) ((warps + wpc - 1) / wpc);
     k_chain_streams<<<gen_ctas, tpb, gen_smem, gs>>>(sa);
@@ -1324,6 +1508,7 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
         for (int r = 0; r < a.n_peers; ++r) a.peers[r] = e->peer_packed[par][r] + begin * e->row_doubles;
     }
     a.ctl = e->ctl;
+    a.err = &e->ctl->err;
     a.live0 = e->live[0];
     a.live1 = e->live[1];
     a.alpha_tab = e->alpha_tab;
@@ -1372,7 +1557,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     if (e->p2p) {
         PeerFlags pf;
         for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
-        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 0);
+        k_peer_barrier<<<1, 32, 0, st>>>(e->ctl, e->p2p_epoch_dev, e->p2p_flags, pf, e->cfg.world_size, e->cfg.rank, e->p2p_err, 0, e->progress_dev);
         e->all_launches += 1;
         trace_mark(e, "peer barrier end", st);
     }
@@ -1382,12 +1567,7 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
                                           (int) e->k, e->rank, e->dead);
     trace_mark(e, "merge_scatter end", st);
     // grid form: 8 CTAs on ANY free SMs (a cluster has to wait until the generator has drained one GPC)
-    static int epi_cluster = -1;
-    if (epi_cluster < 0) {
-        const char *ec = getenv("NSB200_EPI_CLUSTER");
-        epi_cluster = (ec && atoi(ec)) ? 1 : 0;
-    }
-    if (epi_cluster)
+    if (opt(OPT_EPI_CLUSTER))
         k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D,
                                                            e->m, e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi,
                                                            e->progress_dev);
@@ -1512,9 +1692,10 @@ extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTer
     if (nsb200_engine_init(e, key, term_cond, stream)) return 1;
     // Steps are no-ops on the device once the register says done, so the host runs ahead: it keeps
     // `depth` bodies in flight and polls two host-mapped words the epilogue writes, never the stream.
-    long long depth = 4;
-    if (const char *de = getenv("NSB200_DEPTH")) depth = atoll(de) > 0 ? atoll(de) : depth;
-    long long launched = 0;
+    const long long depth = opt(OPT_DEPTH) > 0 ? opt(OPT_DEPTH) : 4;
+    long long launched = 0, last_completed = -2;
+    auto last_progress = std::chrono::steady_clock::now();
+    unsigned idle = 0;
     for (;;) {
         const long long completed = e->progress[0];
         if (completed >= 0 && e->progress[1]) break;                                 // loop condition false
@@ -1525,12 +1706,30 @@ extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTer
             ++launched;
             continue;
         }
-        if (cudaStreamQuery((cudaStream_t) stream) == cudaErrorLaunchFailure) return fail("kernel failed during the run");
+        // Nothing to enqueue: wait for the device.  Any sticky error (illegal address, ECC, launch timeout, a peer
+        // fault) would leave the progress words frozen, so everything but "not ready" is fatal, a rank that missed
+        // the all-gather barrier is reported through the third progress word, and a watchdog bounds the wait.
+        const cudaError_t q = cudaStreamQuery((cudaStream_t) stream);
+        if (q != cudaSuccess && q != cudaErrorNotReady)
+            return fail("device error during the run: %s", cudaGetErrorString(q));
+        if (e->progress[2]) return fail("a peer GPU did not reach the all-gather barrier (fused NVLink exchange)");
+        const auto now = std::chrono::steady_clock::now();
+        if (completed != last_completed) {
+            last_completed = completed;
+            last_progress = now;
+        } else if (std::chrono::duration<double>(now - last_progress).count() > 300.0) {
+            return fail("no progress on the device for 300 s (body %lld of %lld enqueued)", completed, launched);
+        }
+        if (++idle > 64) std::this_thread::yield();  // a run spends < 1 ms per body: spin briefly, then be polite
     }
     NsRegister r;
     if (nsb200_engine_finalize(e, stream)) return 1;
     if (nsb200_engine_register(e, &r, stream)) return 1;  // synchronises the stream
     if (out_register) *out_register = r;
+    if (r.error_flags & NSB200_ERR_SHRINK_LOOP)
+        return fail("a slice chain did not accept within %d proposals: the likelihood is non-deterministic or NaN at "
+                    "its seed point (the run was stopped at iteration %lld)", kMaxShrinkProposals, (long long) r.iteration);
+    if (r.error_flags & NSB200_ERR_PEER_TIMEOUT) return fail("a peer GPU did not reach the all-gather barrier");
     return 0;
 }
 

@@ -169,13 +169,27 @@ class UniDimSliceSampler(AbstractSampler):
                                          _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), st))
 
     def _fused_batch(self, d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL):
+        """nsb200_slice_batch_ws: the chains' data-independent streams are generated into a scratch buffer first, so
+        the dense-Gaussian family with D <= 32 runs on the FP64 tensor-core kernel, exactly as inside the engine."""
+        L = _lib.lib()
         k = self.num_phantom_save
+        n, D = out_U.shape
         N = live_U.shape[0]
-        _lib.check(_lib.lib().nsb200_slice_batch(
+        if n == 0:
+            return
+        nbytes = int(L.nsb200_slice_streams_bytes(D, self.num_slices, n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        err = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(L.nsb200_slice_batch_ws(
             ctypes.byref(d), ctypes.byref(p), _lib.key_arg(key), _lib.ptr(contour), _lib.ptr(live_U),
             _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)), _lib.ptr(out_U), _lib.ptr(out_logL),
             _lib.ptr(out_nev), _lib.ptr(ph_U) if k else ctypes.c_void_p(0),
-            _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), _lib.stream_arg()))
+            _lib.ptr(ph_logL) if k else ctypes.c_void_p(0), _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(err),
+            _lib.stream_arg()))
+        flags = int(err.item())
+        if flags:
+            raise RuntimeError(f"nsb200: slice chains raised error flags {flags} (1 = a slice did not accept within "
+                               "65536 proposals: non-deterministic or NaN likelihood)")
 
 
 @dataclasses.dataclass(eq=False)

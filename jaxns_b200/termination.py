@@ -52,13 +52,17 @@ def _sub(a, b):
 
 def determine_termination(term_cond, termination_register: TerminationRegister) -> Tuple[bool, int]:
     if isinstance(term_cond, TerminationConditionConjunction):
-        # reference quirk kept: starts from done=False, reason=0 and ANDs the children in
-        done, reason = False, 0
+        # Deviation from the reference on purpose: termination.py:52-57 starts from done=False and ANDs the
+        # children in, so a conjunction could never fire (and _main_ns_thread raises AttributeError on
+        # `.max_samples` for it, sharded_static.py:464, so the reference cannot run one at all).  Here `a & b`
+        # means what it says: done when every child is done; the reason is the union of the children's bits.
+        done, reason = True, 0
         for c in term_cond.conds:
             d, r = determine_termination(c, termination_register)
             done = done and d
-            reason = reason & r
-        return done, reason
+            reason = reason | r
+        done = done and len(term_cond.conds) > 0
+        return done, (reason if done else 0)
     if isinstance(term_cond, TerminationConditionDisjunction):
         done, reason = False, 0
         for c in term_cond.conds:

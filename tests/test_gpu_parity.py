@@ -158,7 +158,7 @@ def test_slice_batch_independent_of_speculation_width(torch_cuda, oracle, prior,
     (samplers/uni_slice_sampler.py:160-186)."""
     torch = torch_cuda
     import jaxns_b200 as j
-    from jaxns_b200 import distributions as tfpd, likelihoods as lk, random
+    from jaxns_b200 import _lib, distributions as tfpd, likelihoods as lk, random
     from jaxns_b200.types import LivePointCollection
     D, N, S, k = 32, 320, 24, 2
     if prior == "normal":
@@ -180,15 +180,71 @@ def test_slice_batch_independent_of_speculation_width(torch_cuda, oracle, prior,
     state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
     outs = []
     for spec in ("1", "2", "4"):
-        monkeypatch.setenv("NSB200_SPEC", spec)
+        _lib.set_option("NSB200_SLICE_MMA", 0)  # NSB200_SPEC is a knob of the lane-per-dimension kernel
+        _lib.set_option("NSB200_SPEC", int(spec))
         sample, phantom = sampler.get_samples_batch(random.PRNGKey(13), contour, state, m)
         outs.append((sample.U_sample.clone(), sample.log_L.clone(), sample.num_likelihood_evaluations.clone(),
                      phantom.U_sample.clone(), phantom.log_L.clone()))
+    _lib.set_option("NSB200_SPEC", -1)
+    _lib.set_option("NSB200_SLICE_MMA", -1)
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert torch.equal(a, b)
     exp = oracle.slice_batch(om, random.PRNGKey(13), contour, live_U, live_logL, S, k, True, num_samples=m)
     np.testing.assert_array_equal(outs[0][2].cpu().numpy(), exp["n_evals"])
+
+
+@pytest.mark.parametrize("D,N,S,k,prior", [(32, 320, 32, 0, "normal"), (32, 320, 24, 2, "uniform"),
+                                           (8, 240, 40, 3, "normal"), (13, 200, 20, 1, "normal"),
+                                           (20, 200, 12, 0, "uniform"), (5, 96, 9, 2, "normal")])
+def test_slice_mma_kernel_parity(torch_cuda, oracle, D, N, S, k, prior):
+    """The FP64 tensor-core slice kernel (ns_slice_mma.cuh: 8 proposal columns per warp through DMMA, P = 1, 2, 4
+    speculative proposals per chain) against the oracle and against the lane-per-dimension kernel: n_evals exact,
+    points to rounding (the quadratic form is summed in MMA tile order)."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import _lib, distributions as tfpd, likelihoods as lk, random
+    from jaxns_b200.types import LivePointCollection
+    if prior == "normal":
+        model = product_models()["gauss"](D)
+    else:
+        cov = np.full((D, D), 0.9) + 0.1 * np.eye(D)
+
+        def prior_model():
+            x = yield j.Prior(tfpd.Uniform(low=-3.0 * np.ones(D), high=5.0 * np.ones(D)), name="x")
+            return x
+        model = j.Model(prior_model, lk.DenseGaussianLikelihood(np.full(D, 1.0), covariance_matrix=cov))
+    om = to_oracle(model, oracle)
+    oU, ologL, _ = oracle.init_batch(om, random.PRNGKey(5), N)
+    order = np.argsort(ologL, kind="stable")
+    live_U, live_logL = oU[order], ologL[order]
+    m = N // 2 - 3  # not a multiple of the chains per warp: the last warp carries empty slots
+    contour = live_logL[N // 2 - 1]
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=True, perfect=True)
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    exp = oracle.slice_batch(om, random.PRNGKey(13), contour, live_U, live_logL, S, k, True, num_samples=m)
+    outs = {}
+    try:
+        for impl, P in [(0, 0), (1, 1), (1, 2), (1, 4)]:
+            _lib.set_option("NSB200_SLICE_MMA", impl)
+            _lib.set_option("NSB200_MMA_P", P)
+            sample, phantom = sampler.get_samples_batch(random.PRNGKey(13), contour, state, m)
+            outs[(impl, P)] = (sample.U_sample.clone(), sample.log_L.clone(), sample.num_likelihood_evaluations.clone(),
+                               phantom.U_sample.clone(), phantom.log_L.clone())
+    finally:
+        _lib.set_option("NSB200_SLICE_MMA", -1)
+        _lib.set_option("NSB200_MMA_P", -1)
+    for key, (U, logL, nev, phU, phL) in outs.items():
+        np.testing.assert_array_equal(nev.cpu().numpy(), exp["n_evals"], err_msg=str(key))
+        np.testing.assert_allclose(U.cpu().numpy(), exp["U"], rtol=1e-7, atol=1e-9, err_msg=str(key))
+        np.testing.assert_allclose(logL.cpu().numpy(), exp["log_L"], rtol=1e-7, atol=1e-7, err_msg=str(key))
+        if k:
+            np.testing.assert_allclose(phU.cpu().numpy(), exp["ph_U"], rtol=1e-7, atol=1e-9, err_msg=str(key))
+            np.testing.assert_allclose(phL.cpu().numpy(), exp["ph_log_L"], rtol=1e-7, atol=1e-7, err_msg=str(key))
+    # the speculation width of the MMA kernel changes no bit either
+    for P in (2, 4):
+        for a, b in zip(outs[(1, 1)], outs[(1, P)]):
+            assert torch.equal(a, b), P
 
 
 def test_slice_plateau_and_no_seed(torch_cuda, oracle):
@@ -375,16 +431,17 @@ def test_sorted_merge_rank_equals_brute_force(torch_cuda, N, monkeypatch):
     family makes exact log L ties likely (plateaus at the prior corners are common in U space)."""
     torch = torch_cuda
     import jaxns_b200 as j
-    from jaxns_b200 import random
+    from jaxns_b200 import _lib, random
     model = product_models()["eggbox"](2)
     outs = []
     for brute in ("1", "0"):
-        monkeypatch.setenv("NSB200_MERGE_BRUTE", brute)
+        _lib.set_option("NSB200_MERGE_BRUTE", int(brute))
         ns = j.NestedSampler(model=model, num_live_points=N, max_samples=N * 6, s=2)
         reason, state = ns(random.PRNGKey(4), j.TerminationCondition(max_samples=float(N * 5)))
         sc = state.sample_collection
         outs.append((int(reason), int(state.num_samples), sc.log_L.clone(), sc.U_samples.clone(),
                      sc.sender_node_idx.clone(), sc.num_likelihood_evaluations.clone()))
+    _lib.set_option("NSB200_MERGE_BRUTE", -1)
     assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1] and outs[0][1] >= N * 4
     for a, b in zip(outs[0][2:], outs[1][2:]):
         assert torch.equal(a, b)

@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS)
     for name in declared:
         assert getattr(L, name) is not None
-    assert L.nsb200_abi_version() == 1
+    assert L.nsb200_abi_version() == 2
     assert L.nsb200_workspace_bytes(_lib.WS_ARGSORT, 1000) > 0
     assert L.nsb200_workspace_bytes(99, 1000) == -1
 
@@ -160,8 +160,10 @@ def test_termination_condition_algebra_and_host_mirror():
     reg2 = reg._replace(num_samples_used=100, plateau=True)
     assert T.determine_termination(a, reg2) == (True, 1 + 128)
     assert T.determine_termination(a | b, reg2) == (True, 1 + 128)
-    # reference quirk: a conjunction starts from done=False and ANDs, so it never fires
-    assert T.determine_termination(a & a, reg2) == (False, 0)
+    # a conjunction fires when every child does (the reference's starts from done=False and could never fire)
+    assert T.determine_termination(a & a, reg2) == (True, 1 + 128)
+    assert T.determine_termination(a & b, reg2) == (True, 1 + 128)  # plateau fires in every child
+    assert T.determine_termination(a & b, reg._replace(num_samples_used=100)) == (False, 0)
     tc = T.to_c(j.TerminationCondition(dlogZ=0.5, max_samples=7, peak_XL_frac=0.1))
     assert tc.mask == (1 << 3) | (1 << 4) | (1 << 10) and tc.dlogZ == 0.5 and tc.max_samples == 7.0
 
