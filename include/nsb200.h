@@ -158,7 +158,9 @@ enum {
     NSB200_ERR_SHRINK_LOOP = 1, /* a slice did not accept within 65536 proposals: the likelihood is non-deterministic
                                    or NaN at its own seed point (the reference's lax.while_loop would spin forever,
                                    samplers/uni_slice_sampler.py:160-196) */
-    NSB200_ERR_PEER_TIMEOUT = 2 /* a peer GPU did not reach the fused all-gather's arrival barrier */
+    NSB200_ERR_PEER_TIMEOUT = 2, /* a peer GPU did not reach the fused all-gather's arrival barrier */
+    NSB200_ERR_CONTOUR_MISMATCH = 4 /* the ranks' likelihood contours (L_min), exchanged with the arrival flags of the
+                                       fused all-gather, disagree: their replicated live sets have diverged */
 };
 
 /* ---- misc ----------------------------------------------------------------------------------- */
@@ -167,7 +169,7 @@ const char *nsb200_last_error(void);
 /* Tuning / A-B knobs (launch geometry, kernel selection: results never depend on them).  Every knob is also an
  * environment variable of the same name, read once per process; value < 0 returns to that default.  Names:
  * NSB200_SPEC, NSB200_TPB, NSB200_SLICE_MMA, NSB200_MMA_P, NSB200_MMA_WPB, NSB200_MERGE_BRUTE, NSB200_GEN_MODE,
- * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_EPI_CLUSTER, NSB200_DEPTH, NSB200_TRACE, NSB200_SORT_LEGACY. */
+ * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_EPI_CLUSTER, NSB200_DEPTH, NSB200_TRACE. */
 int nsb200_set_option(const char *name, int32_t value);
 
 /* ---- jax.random under jax_threefry_partitionable=True (internals/mixed_precision.py:11-15) --- */
@@ -242,7 +244,9 @@ int nsb200_split_begin(const NsModelDesc *model, const NsSliceParams *p, const u
                        const double *contour, const double *live_U, const double *live_logL,
                        const double *seed_table, void *workspace, int64_t workspace_bytes, double *prop_U,
                        double *prop_X, nsb200_stream_t stream);
-/* n_active: DEVICE counter (uint64) incremented by every chain that still needs evaluations, or NULL. */
+/* n_active: DEVICE counter (uint64) incremented by every chain that still needs evaluations, or NULL.  Bit 62 is set
+ * when a chain was stopped by the shrink-loop watchdog (NSB200_ERR_SHRINK_LOOP: 65536 proposals of one slice
+ * rejected -- a non-deterministic likelihood, or NaN at the chain's own seed point). */
 int nsb200_split_accept(const NsModelDesc *model, const NsSliceParams *p, const double *contour,
                         const double *prop_logL, void *workspace, int64_t workspace_bytes, double *prop_U,
                         double *prop_X, uint64_t *n_active, nsb200_stream_t stream);

@@ -316,6 +316,13 @@ __global__ void k_peer_barrier(DevCtl *ctl, unsigned long long *epoch_dev, volat
     epoch = __shfl_sync(0xFFFFFFFFu, epoch, 0);
     const int r = threadIdx.x;
     if (r >= world) return;
+    // L_min agreement (north star: "L_min is agreed each iteration ... over NVLink"): the live log L is replicated, so
+    // every rank derives the same contour without a collective; the barrier carries each rank's contour
+    // along with its arrival flag and every rank checks all of them against its own -- an all-gather + compare of
+    // L_min fused into the exchange that has to happen anyway.  A mismatch (a rank whose replicated state diverged)
+    // raises NSB200_ERR_CONTOUR_MISMATCH instead of silently merging different runs.
+    const unsigned long long my_contour = (unsigned long long) __double_as_longlong(ctl->contour);
+    if (!force) *((volatile unsigned long long *) (peers.p[r] + 8 + me)) = my_contour;
     __threadfence_system();
     *((volatile unsigned long long *) (peers.p[r] + me)) = epoch;
     __threadfence_system();
@@ -333,6 +340,7 @@ __global__ void k_peer_barrier(DevCtl *ctl, unsigned long long *epoch_dev, volat
         }
     }
     __threadfence_system();
+    if (!force && mine[r] == epoch && mine[8 + r] != my_contour) atomicOr(&ctl->err, NSB200_ERR_CONTOUR_MISMATCH);
 }
 
 // linear_to_log_stats (stats.py:55-74)

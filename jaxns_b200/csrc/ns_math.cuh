@@ -153,6 +153,10 @@ __device__ __forceinline__ double normal_from_bits(uint64_t bits) {
     return 1.4142135623730951 * erfinv_xla(u);
 }
 
+// The IEEE division of fast_div's fallback as a real call: inlined, the compiler evaluates the ~25-instruction
+// division sequence unconditionally and selects afterwards; out of line it costs one never-taken branch.
+__device__ __noinline__ double slow_div(double a, double b) { return a / b; }
+
 // a / b for the chains' critical path: MUFU reciprocal seed + two Newton steps + one residual
 // correction (8 instructions, ~75 cycles) instead of the IEEE division sequence (20 instructions with
 // its slow-path check, ~125 cycles).  Result within 1 ulp of a / b; non-finite intermediates (b = 0,
@@ -164,7 +168,7 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     r = fma(fma(-b, r, 1.0), r, r);
     double q = a * r;
     q = fma(fma(-b, q, a), r, q);
-    return (q - q == 0.0) ? q : a / b;  // q - q != 0 for NaN / inf
+    return (q - q == 0.0) ? q : slow_div(a, b);  // q - q != 0 for NaN / inf
 }
 
 // Same without the fallback, for denominators known to be finite, normal and non-zero (the AS241
@@ -298,18 +302,54 @@ __device__ __forceinline__ void ndtri_batch(const double (&p)[P], unsigned mask,
 // sparse (late in a run a few of the warp's 32 K values per round), so they are drained through a vote loop
 // that evaluates ONE pending value per lane per trip instead of a K-wide tail block.  Same operations per element
 // as ndtri(): bit-identical results.
+#ifdef NSB_PROFILE
+__device__ unsigned long long g_tail_trips;
+#endif
 template <int K>
 __device__ __forceinline__ void ndtri_multi(const double (&p)[K], double (&x)[K]) {
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
     unsigned pend = 0;
+    {
+        // coefficient-major order: the 2 K Horner chains and the K divisions advance together, so a lone warp on
+        // its SM sub-partition issues an independent FP64 instruction every slot instead of waiting 8 cycles for
+        // its own last result (value-major source order was scheduled as K back-to-back dependent chains)
+        double q[K], r[K], na[K], nb[K], rc[K];
 #pragma unroll
-    for (int i = 0; i < K; ++i) {
-        const double q = p[i] - 0.5;
-        const double r = fma(-q, q, 0.180625);
-        x[i] = fast_div_finite(q * horner8(kPpndA, r), horner8(kPpndB, r));
-        pend |= (!(fabs(q) <= 0.425)) ? (1u << i) : 0u;  // also true for NaN
+        for (int i = 0; i < K; ++i) {
+            q[i] = p[i] - 0.5;
+            r[i] = fma(-q[i], q[i], 0.180625);
+            na[i] = kPpndA[7];
+            nb[i] = kPpndB[7];
+            pend |= (!(fabs(q[i]) <= 0.425)) ? (1u << i) : 0u;  // also true for NaN
+        }
+#pragma unroll
+        for (int c = 6; c >= 0; --c) {
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                na[i] = fma(na[i], r[i], kPpndA[c]);
+                nb[i] = fma(nb[i], r[i], kPpndB[c]);
+            }
+        }
+        // fast_div_finite(q * A(r), B(r)), the K quotients interleaved
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            na[i] = q[i] * na[i];
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc[i]) : "d"(nb[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < K; ++i) rc[i] = fma(fma(-nb[i], rc[i], 1.0), rc[i], rc[i]);
+#pragma unroll
+        for (int i = 0; i < K; ++i) rc[i] = fma(fma(-nb[i], rc[i], 1.0), rc[i], rc[i]);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const double qq = na[i] * rc[i];
+            x[i] = fma(fma(-nb[i], qq, na[i]), rc[i], qq);
+        }
     }
     while (__any_sync(0xFFFFFFFFu, pend != 0)) {
+#ifdef NSB_PROFILE
+        if (threadIdx.x == 0 && blockIdx.x == 0) g_tail_trips += 1;
+#endif
         const int i0 = __ffs((int) pend) - 1;  // -1: nothing pending in this lane
         double pv = 0.5;
 #pragma unroll

@@ -104,12 +104,14 @@ __host__ __device__ inline bool dense_in_smem(int D, int DP) { return (size_t) D
 __host__ __device__ constexpr bool dense_in_regs(int G, int DPL) { return G == 32 && DPL == 1; }
 
 // Doubles of shared memory the staged model needs.
-__host__ __device__ inline size_t model_smem_doubles(int family, int D, int G, int DPL, int K) {
+// row_smem: stage the factor in shared memory even where dense_in_regs() would keep it in registers (warp teams:
+// two warps per chain only stay resident in one wave at <= 88 registers per thread, the 64-register row has to go).
+__host__ __device__ inline size_t model_smem_doubles(int family, int D, int G, int DPL, int K, bool row_smem = false) {
     const int DP = G * DPL;
     size_t n = 2 * (size_t) DP;
     switch (family) {
         case NSB200_FAM_GAUSS_DENSE:
-            n += 1 + DP + ((!dense_in_regs(G, DPL) && dense_in_smem(D, DP)) ? (size_t) D * DP : 0);  // c, mu, LT[D][DP]
+            n += 1 + DP + (((!dense_in_regs(G, DPL) || row_smem) && dense_in_smem(D, DP)) ? (size_t) D * DP : 0);  // c, mu, LT[D][DP]
             break;
         case NSB200_FAM_GAUSS_MIX_DIAG: n += (size_t) K * (1 + 2 * (size_t) DP); break;  // logc, mean[DP], inv[DP]
         case NSB200_FAM_SHELLS: n += (size_t) K * (3 + (size_t) DP); break;              // w, r, lognorm, c[DP]
@@ -120,7 +122,7 @@ __host__ __device__ inline size_t model_smem_doubles(int family, int D, int G, i
 
 // Cooperative (whole CTA) staging of the model into shared memory.  Padded dimensions get neutral
 // values.  Must be followed by __syncthreads().
-template <int G, int DPL>
+template <int G, int DPL, bool RS = false>
 __device__ inline void stage_model(const NsModelDesc &m, double *smem, ModelSmem &out) {
     constexpr int DP = G * DPL;
     const int D = m.D;
@@ -143,7 +145,7 @@ __device__ inline void stage_model(const NsModelDesc &m, double *smem, ModelSmem
             // src = [c, mu[D], Linv[D*D] row-major]; dst = [c, mu[DP], LT[j][i] = Linv[i][j]]
             if (threadIdx.x == 0) P[0] = src[0];
             for (int j = threadIdx.x; j < DP; j += blockDim.x) P[1 + j] = (j < D) ? src[1 + j] : 0.0;
-            if (dense_in_regs(G, DPL)) {
+            if (dense_in_regs(G, DPL) && !RS) {
                 out.dense_global = src + 1 + D;  // rows are pulled into registers by the caller
             } else if (dense_in_smem(D, DP)) {
                 double *LT = P + 1 + DP;
@@ -185,12 +187,12 @@ __device__ inline void stage_model(const NsModelDesc &m, double *smem, ModelSmem
 }
 
 // Per-thread registers of the dense factor (only meaningful for G == 32, DPL == 1).
-template <int G, int DPL>
+template <int G, int DPL, bool RS = false>
 struct DenseRow {
-    static constexpr int N = dense_in_regs(G, DPL) ? 32 : 1;
+    static constexpr int N = (dense_in_regs(G, DPL) && !RS) ? 32 : 1;
     double v[N];
     __device__ __forceinline__ void load(const ModelSmem &sm, int lane) {
-        if (dense_in_regs(G, DPL)) {
+        if (dense_in_regs(G, DPL) && !RS) {
 #pragma unroll
             for (int j = 0; j < N; ++j)
                 v[j] = (sm.family == NSB200_FAM_GAUSS_DENSE && lane < sm.D && j <= lane)
@@ -227,8 +229,8 @@ __device__ __forceinline__ void transform_dims(const ModelSmem &sm, const Grp<G>
 
 // log-likelihood of the P transformed points held across the group.  `scratch` = DP*P doubles of
 // shared memory private to the chain.  Every lane of the group gets the same values.
-template <int G, int DPL, int P, int FAM>
-__device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
+template <int G, int DPL, int P, int FAM, bool RS = false>
+__device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL, RS> &row,
                                              const double (&X)[P][DPL], double *scratch, double (&out)[P]) {
     constexpr int DP = G * DPL;
     const int D = sm.D;
@@ -249,10 +251,10 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
             double q[P];
 #pragma unroll
             for (int p = 0; p < P; ++p) q[p] = 0.0;
-            if (dense_in_regs(G, DPL)) {
+            if (dense_in_regs(G, DPL) && !RS) {
                 // z_lane = sum_j Linv[lane][j] r_j with the row in registers; two partial sums per
                 // proposal shorten the dependent FMA chain.
-                constexpr int NR = DenseRow<G, DPL>::N;
+                constexpr int NR = DenseRow<G, DPL, RS>::N;
                 constexpr int NA = NR >= 4 ? 4 : 1;  // partial sums: 8-deep FMA chains instead of 32
                 double z[NA][P];
 #pragma unroll
@@ -423,12 +425,12 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
 }
 
 // Model.forward at P U-space points held across the group.
-template <int G, int DPL, int P, int FAM>
-__device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL> &row,
+template <int G, int DPL, int P, int FAM, bool RS = false>
+__device__ __forceinline__ void forward_group(const ModelSmem &sm, const Grp<G> &g, const DenseRow<G, DPL, RS> &row,
                                               const double (&u)[P][DPL], double *scratch, double (&out)[P]) {
     double X[P][DPL];
     transform_dims<G, DPL, P>(sm, g, u, X);
-    loglik_group<G, DPL, P, FAM>(sm, g, row, X, scratch, out);
+    loglik_group<G, DPL, P, FAM, RS>(sm, g, row, X, scratch, out);
 }
 
 // Runtime family -> compile-time template argument, once per kernel.

@@ -202,7 +202,7 @@ __host__ __device__ inline size_t chain_smem_doubles(int G, int DPL, int P, bool
 // kernel time is the latency of its longest chain, so halving the sequential rounds per slice is
 // worth more than the ~15 % of evaluations that are thrown away.  Results are unchanged (first
 // accepted proposal wins, n_evals counts up to it).  Requires G == 32, P == 1, PRE.
-template <int G, int DPL, int P, int FAM, bool PRE, int W = 1>
+template <int G, int DPL, int P, int FAM, bool PRE, int W = 1, bool RS = false>
 __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *smem) {
     static_assert(W == 1 || (G == 32 && P == 1 && PRE), "warp teams need G == 32, P == 1 and precomputed streams");
     constexpr bool TEAM = W > 1;
@@ -221,7 +221,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
         live_logL = live.logL;
     }
     ModelSmem sm;
-    stage_model<G, DPL>(a.model, smem, sm);
+    stage_model<G, DPL, RS>(a.model, smem, sm);
     __syncthreads();
     const Grp<G> g;
     const int wt = TEAM ? (int) (threadIdx.x >> 5) : 0;  // warp of the team = which proposal of a round it evaluates
@@ -229,13 +229,13 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     const int local_chain = TEAM ? wt : threadIdx.x / G;     // index of this lane group's private smem slot
     const long long chain = a.chain_begin + (long long) blockIdx.x * chains_per_block + (TEAM ? 0 : local_chain);
     if (chain >= a.chain_end) return;
-    double *res = smem + model_smem_doubles(a.model.family, D, G, DPL, a.model.K) +
+    double *res = smem + model_smem_doubles(a.model.family, D, G, DPL, a.model.K, RS) +
                   (size_t) (TEAM ? W : 0) * chain_smem_doubles(G, DPL, P, true);  // [2][W] exchange buffer (TEAM)
     int par = 0;
-    DenseRow<G, DPL> row;
+    DenseRow<G, DPL, RS> row;
     row.load(sm, g.lane);
 
-    double *cs = smem + model_smem_doubles(sm.family, D, G, DPL, sm.K) +
+    double *cs = smem + model_smem_doubles(sm.family, D, G, DPL, sm.K, RS) +
                  (size_t) local_chain * chain_smem_doubles(G, DPL, P, true);
     double *scratch = cs;
     double *pre_u = cs + DP * P;                                       // [G][kPre]
@@ -373,7 +373,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     double x1[1][DPL], l1[1];
 #pragma unroll
                     for (int s = 0; s < DPL; ++s) x1[0][s] = fma(tmine, d[s], U0[s]);
-                    forward_group<G, DPL, 1, FAM>(sm, g, row, x1, scratch, l1);
+                    forward_group<G, DPL, 1, FAM, RS>(sm, g, row, x1, scratch, l1);
                     if (g.lane == 0) res[par * W + wt] = l1[0];
                     __syncthreads();
                     int hit = -1;
@@ -398,6 +398,11 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     ne += W;
                     left = l;
                     right = r;
+                    if (ne >= kMaxShrinkProposals) {  // watchdog: stay at the current point, flag the run
+                        if (a.err && g.lane == 0 && wt == 0) atomicOr(a.err, NSB200_ERR_SHRINK_LOOP);
+                        logL_acc = logL0;
+                        break;
+                    }
                 }
             } else
             for (;;) {
@@ -431,7 +436,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     double Xp[P][DPL];
                     transform_dims<G, DPL, P>(sm, g, x, Xp);
                     NSB_TICK(4)  // prior transform
-                    loglik_group<G, DPL, P, FAM>(sm, g, row, Xp, scratch, logL);
+                    loglik_group<G, DPL, P, FAM, RS>(sm, g, row, Xp, scratch, logL);
                     NSB_TICK(5)  // likelihood
                     prof[8] += 1;
                     {
@@ -445,7 +450,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     }
                 }
 #else
-                forward_group<G, DPL, P, FAM>(sm, g, row, x, scratch, logL);
+                forward_group<G, DPL, P, FAM, RS>(sm, g, row, x, scratch, logL);
 #endif
                 // ---- first accepted proposal wins (:160-166)
                 int hit = -1;
@@ -536,6 +541,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) 
     } else {
         NSB_FAMILY_SWITCH(a.model.family, slice_chains_body<G, DPL, P, kFam, false>(a, smem));
     }
+}
+
+// Warp team: one CTA = one chain run by W warps; in every shrink round warp w evaluates the w-th speculative
+// proposal (see slice_chains_body).  Dense Gaussian, 17 <= D <= 32, pre-generated streams.  The factor is staged in
+// shared memory (RS) so that the chain state fits 88 registers: W x 1600 chains have to be resident in ONE wave
+// (11 CTAs of 64 threads per SM), otherwise the second wave costs more than the halved rounds save.
+template <int W>
+__global__ void __launch_bounds__(32 * W, W == 2 ? 11 : 5) k_slice_chains_team(SliceArgs a) {
+    extern __shared__ double smem[];
+    slice_chains_body<32, 1, 1, NSB200_FAM_GAUSS_DENSE, true, W, true>(a, smem);
 }
 
 __global__ void k_alpha_table(int S, double *out) {

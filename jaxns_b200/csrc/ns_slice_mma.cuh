@@ -74,16 +74,18 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
     const double lconst = __ldg(prm);
     const double contour = *contour_ptr;
 
-    // ---- per-lane constants: prior / mean of this lane's dimensions, A fragments of L^-1 (tiles on or below the diagonal)
-    double mu[KT], pa[KT], pb[KT];
-#pragma unroll
-    for (int s = 0; s < KT; ++s) {
-        const int j = 4 * s + t;
-        const bool ok = j < D;
-        mu[s] = ok ? __ldg(prm + 1 + j) : 0.0;
-        pa[s] = ok ? __ldg(a.model.prior_a + j) : 0.0;
-        pb[s] = ok ? __ldg(a.model.prior_b + j) : 0.0;
+    // ---- per-CTA constants in shared memory (prior, mean: read once per round, 3 x KT broadcast-free LDS.64) and
+    // per-lane A fragments of L^-1 in registers (tiles on or below the diagonal).  Keeping the 3 KT prior / mean values
+    // out of the register file is what leaves the scheduler room to interleave the KT quantile chains.
+    __shared__ double s_mu[32], s_pa[32], s_pb[32];
+    if (threadIdx.x < 32) {
+        const int jj = threadIdx.x;
+        const bool ok = jj < D;
+        s_mu[jj] = ok ? __ldg(prm + 1 + jj) : 0.0;
+        s_pa[jj] = ok ? __ldg(a.model.prior_a + jj) : 0.0;
+        s_pb[jj] = ok ? __ldg(a.model.prior_b + jj) : 0.0;
     }
+    __syncthreads();
     double A[NB * (NB + 1)];
     {
         int ai = 0;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
     double uc[UPL], un[UPL];
     uint2 rkn = make_uint2(0, 0);
     Key rkey = Key{0, 0};
-    double logL0 = 0.0, left = -1.0, right = 1.0, alpha = 1.0;
+    double logL0 = 0.0, left = -1.0, right = 1.0, alpha = 1.0, alpha_n = 1.0;
     long long nev = 0;
     int j = 0, ne = 0;
 #pragma unroll
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
             un[q] = (n < kPre) ? __ldg(a.pre_us + sn * kPre + n) : 0.5;
         }
         rkn = __ldg(a.pre_rkeys + sn);
+        alpha_n = a.alpha_tab ? __ldg(a.alpha_tab + jn) : alpha_schedule(jn, S);
     };
     // slice j starts: its stream moves from the "next" registers in, the loads of slice j + 1 are issued (their
     // latency hides behind this slice's rounds) and the bracket = line /\ unit cube is computed (_slice_bounds :41-64).
@@ -143,27 +146,70 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
 #pragma unroll
         for (int q = 0; q < UPL; ++q) uc[q] = un[q];
         rkey = Key{rkn.x, rkn.y};
-        alpha = a.alpha_tab ? __ldg(a.alpha_tab + j) : alpha_schedule(j, S);
+        alpha = alpha_n;
         if (j + 1 < S) load_stream(j + 1);
-        double r = kInf, nl = kInf;  // right bound and MINUS the left bound, both >= 0
+        // this team's slots s = pme, pme + P, ...; the NS reciprocals and quotients advance together (fast_div's
+        // operations, interleaved over the slots)
+        constexpr int NS = (KT + P - 1) / P;
+        double us[NS], ds[NS], rc[NS], t1[NS], t0[NS];
+        bool ok[NS];
 #pragma unroll
-        for (int s0 = 0; s0 < KT; s0 += P) {
-            double us = U0[s0], ds = d[s0];
+        for (int i = 0; i < NS; ++i) {
+            const int s0 = i * P;
+            us[i] = U0[s0];
+            ds[i] = d[s0];
 #pragma unroll
             for (int p = 1; p < P; ++p) {
                 if (s0 + p < KT) {
-                    us = (pme == p) ? U0[s0 + p] : us;
-                    ds = (pme == p) ? d[s0 + p] : ds;
+                    us[i] = (pme == p) ? U0[s0 + p] : us[i];
+                    ds[i] = (pme == p) ? d[s0 + p] : ds[i];
                 }
             }
-            const int jj = 4 * (s0 + pme) + t;
-            if (jj < D) {
-                const double t1 = fast_div(1.0 - us, ds);
-                const double t0 = fast_div(-us, ds);
-                if (t1 >= 0.0) r = fmin(r, t1);
-                if (t1 <= 0.0) nl = fmin(nl, -t1);
-                if (t0 >= 0.0) r = fmin(r, t0);
-                if (t0 <= 0.0) nl = fmin(nl, -t0);
+            ok[i] = (s0 + pme < KT) && (4 * (s0 + pme) + t < D);
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rc[i]) : "d"(ds[i]));
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rc[i] = fma(fma(-ds[i], rc[i], 1.0), rc[i], rc[i]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) rc[i] = fma(fma(-ds[i], rc[i], 1.0), rc[i], rc[i]);
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double a1 = 1.0 - us[i], a0 = -us[i];
+            double q1 = a1 * rc[i], q0 = a0 * rc[i];
+            q1 = fma(fma(-ds[i], q1, a1), rc[i], q1);
+            q0 = fma(fma(-ds[i], q0, a0), rc[i], q0);
+            t1[i] = q1;
+            t0[i] = q0;
+        }
+        // non-finite intermediates (d = 0, denormal d): fast_div falls back to the IEEE division -- a call, so that the
+        // division sequence is not evaluated speculatively for every slot (never taken in practice)
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            if (ok[i] && !((t1[i] - t1[i] == 0.0) && (t0[i] - t0[i] == 0.0))) {
+                if (!(t1[i] - t1[i] == 0.0)) t1[i] = slow_div(1.0 - us[i], ds[i]);
+                if (!(t0[i] - t0[i] == 0.0)) t0[i] = slow_div(-us[i], ds[i]);
+            }
+        }
+        // _slice_bounds :41-64: right = min over {t >= 0}, left = max over {t <= 0} of {t0_j, t1_j}.  For a point inside
+        // the cube t0_j and t1_j have opposite signs, so per slot hi = max and lo = min are the two candidates and a
+        // zero counts on both sides; the four-compare form is kept for the rounding-level case of a coordinate a hair
+        // outside [0, 1] (uniform priors can accept one) -- selected per slot, so the common path is 2 min/max.
+        double r = kInf, nl = kInf;  // right bound and MINUS the left bound, both >= 0
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const double hi = fmax(t0[i], t1[i]), lo = fmin(t0[i], t1[i]);
+            double ri = hi, li = -lo;
+            if (!(hi > 0.0 && lo < 0.0)) {  // a zero, a NaN, or both on one side: the reference's four tests
+                ri = kInf;
+                li = kInf;
+                if (t1[i] >= 0.0) ri = t1[i];
+                if (t1[i] <= 0.0) li = -t1[i];
+                if (t0[i] >= 0.0) ri = fmin(ri, t0[i]);
+                if (t0[i] <= 0.0) li = fmin(li, -t0[i]);
+            }
+            if (ok[i]) {
+                r = fmin(r, ri);
+                nl = fmin(nl, li);
             }
         }
         right = group_min_nonneg(cmask, r + 0.0);
@@ -171,6 +217,11 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
         ne = 0;
     };
 
+#ifdef NSB_PROFILE
+    unsigned long long prof[16];
+    for (int k = 0; k < 16; ++k) prof[k] = 0;
+#endif
+    NSB_T0();
     // ---- chain prelude (bases.py:64; uni_slice_sampler.py:343-358, :410-413)
     if (!fin) {
         const Key chain_key = split_child(base_key, (uint64_t) chain);
@@ -187,26 +238,33 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
         begin_slice();
     }
 
+    NSB_TICK(0)
     while (__any_sync(kFull, !fin)) {
+#ifdef NSB_PROFILE
+        prof[8] += 1;
+#endif
         // ---- P proposals assuming each previous one is rejected (:92-111, :169-186)
-        double ts[P];
-        double l = left, r = right;
+        double ts[P], uus[P];
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
+        for (int p = 0; p < P; ++p) {  // the round's P uniforms first (independent shuffles), then the dependent chain
             const int n = ne + p;
             const int nn = n < kPre ? n : kPre - 1;
-            double uu;
             if (UPL == 1) {
-                uu = __shfl_sync(kFull, uc[0], cbase + nn);
+                uus[p] = __shfl_sync(kFull, uc[0], cbase + nn);
             } else {
-                uu = 0.0;
+                uus[p] = 0.0;
 #pragma unroll
                 for (int q = 0; q < UPL; ++q) {
                     const double v = __shfl_sync(kFull, uc[q], cbase + (nn & (G - 1)));
-                    uu = (nn / G == q) ? v : uu;
+                    uus[p] = (nn / G == q) ? v : uus[p];
                 }
             }
-            if (n >= kPre) {  // beyond the precomputed uniforms: walk the run_key chain (:169), rare
+        }
+        double l = left, r = right;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            double uu = uus[p];
+            if (ne + p >= kPre) {  // beyond the precomputed uniforms: walk the run_key chain (:169), rare
                 const Key t_key = split_child(rkey, 1);
                 rkey = split_child(rkey, 0);
                 uu = uniform01(t_key, 0);
@@ -222,22 +280,24 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
         double x[KT], X[KT];
 #pragma unroll
         for (int s = 0; s < KT; ++s) x[s] = fma(tm, d[s], U0[s]);
+        NSB_TICK(1)
         // ---- prior transform of this lane's KT dimensions (wrapped_tfp_distribution.py:77-84)
         if (normal_prior) {
             double z[KT];
             ndtri_multi<KT>(x, z);
 #pragma unroll
-            for (int s = 0; s < KT; ++s) X[s] = z[s] * pb[s] + pa[s];
+            for (int s = 0; s < KT; ++s) X[s] = z[s] * s_pb[4 * s + t] + s_pa[4 * s + t];
         } else {
 #pragma unroll
-            for (int s = 0; s < KT; ++s) X[s] = x[s] * pb[s] + pa[s];
+            for (int s = 0; s < KT; ++s) X[s] = x[s] * s_pb[4 * s + t] + s_pa[4 * s + t];
         }
+        NSB_TICK(2)
         // ---- z = L^-1 (X - mu) for the warp's 8 columns on the FP64 tensor path, then ||z||^2
         double sq0 = 0.0, sq1 = 0.0;
         {
             double rr[KT];
 #pragma unroll
-            for (int s = 0; s < KT; ++s) rr[s] = (4 * s + t < D) ? X[s] - mu[s] : 0.0;
+            for (int s = 0; s < KT; ++s) rr[s] = (4 * s + t < D) ? X[s] - s_mu[4 * s + t] : 0.0;
             int ai = 0;
 #pragma unroll
             for (int b = 0; b < NB; ++b) {
@@ -270,6 +330,7 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
             if (ll != ll) ll = -kInf;  // ops.py:323-325
             logL[p] = ll;
         }
+        NSB_TICK(3)
         // ---- first accepted proposal wins (:160-166)
         int hit = -1;
 #pragma unroll
@@ -277,6 +338,9 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
             const bool ok = (logL[p] > contour) || ((logL0 == contour) && (logL[p] == contour));
             if (ok) hit = p;
         }
+#ifdef NSB_PROFILE
+        prof[10] += __any_sync(kFull, !fin && hit >= 0) ? 1 : 0;
+#endif
         if (!fin) {
             if (hit < 0 && ne + P > kMaxShrinkProposals) {
                 // a bracket that has collapsed onto the seed point must accept (same point, same log L); it did
@@ -352,7 +416,13 @@ __global__ void __launch_bounds__(128) k_slice_chains_mma(SliceArgs a) {
                 right = r;
             }
         }
+        __syncwarp();
+        NSB_TICK(4)
     }
+#ifdef NSB_PROFILE
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int k = 0; k < 16; ++k) atomicAdd(&g_prof[k], prof[k]);
+#endif
 }
 
 }  // namespace nsb

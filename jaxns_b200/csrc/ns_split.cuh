@@ -141,7 +141,11 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         left = right = t = 0.0;
         new_slice = true;
     } else {
-        if (st[2]) return;  // chain finished: prop_U keeps its final point
+        if (st[2]) {  // chain finished: prop_U keeps its final point
+            // a chain stopped by the shrink-loop watchdog keeps reporting it through bit 62 of the active counter
+            if (st[3] && a.active && g.lane == 0) atomicOr(a.active, 1ull << 62);
+            return;
+        }
         j = (int) st[0];
         ne = (int) st[1];
         run_key = Key{st[4], st[5]};
@@ -207,6 +211,23 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
             t = left + uu * (right - left);
             ne += 1;
             new_slice = false;
+            if (ne > kMaxShrinkProposals) {
+                // watchdog (ns_slice.cuh kMaxShrinkProposals): the caller's likelihood is non-deterministic or NaN at
+                // the chain's own seed point -- stop the chain where it is and raise NSB200_ERR_SHRINK_LOOP
+                if (g.lane == 0) {
+                    st[2] = 1u;
+                    st[3] = 1u;
+                    sc[3] = logL0;
+                    a.state.nev[row] = nev + ne;
+                    if (a.active) atomicOr(a.active, 1ull << 62);
+                }
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int jj = s * G + g.lane;
+                    if (jj < D) a.prop_U[row * D + jj] = U0[s];
+                }
+                return;
+            }
         }
     }
     if (new_slice) {
@@ -245,6 +266,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         st[0] = (uint32_t) j;
         st[1] = (uint32_t) ne;
         st[2] = 0u;
+        st[3] = 0u;
         st[4] = run_key.a;
         st[5] = run_key.b;
         st[6] = after_key.a;

@@ -161,6 +161,25 @@ __device__ __forceinline__ void cluster_scan_excl_k(const double (&v)[K], double
     }
     grp.sync();
     const int lane = threadIdx.x & 31;
+    if (nranks > 16) {
+        // many CTAs (final pass over a long dead set): every CTA scans all aggregates with a block scan and keeps
+        // the exclusive prefix of its own rank (needs blockDim.x >= nranks)
+        double agg[K], pre[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+            agg[k] = (threadIdx.x < nranks) ? ((volatile double *) gpart)[threadIdx.x * K + k] : Op::id();
+        __syncthreads();  // exc[] was combined from sh[k][warp] above: everyone is done reading it
+        block_scan_excl_k<Op, K>(agg, sh, pre);
+        __syncthreads();
+        if (threadIdx.x == rank) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) sh[k][33] = pre[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) out[k] = Op::ap(sh[k][33], exc[k]);
+        return;
+    }
     if (threadIdx.x < 32) {
 #pragma unroll
         for (int k = 0; k < K; ++k) {
@@ -181,27 +200,75 @@ __device__ __forceinline__ void cluster_scan_excl_k(const double (&v)[K], double
 }
 
 // =================================================================================================
-// Stable LSD radix argsort on order-preserving u64 keys (8-bit digits, 8 passes).
+// Stable LSD radix argsort on order-preserving u64 keys (8-bit digits, up to 8 passes), HBM-shaped:
+//   * tiles of 4096 keys; every warp ranks a CONTIGUOUS 512-key chunk with __match_any_sync against warp-private
+//     counters (no block barrier inside the ranking), one block scan turns the 8 x 256 warp counts into positions,
+//     the tile is staged in shared memory in sorted order and written out in coalesced runs per digit;
+//   * the 256 x tiles histogram table is scanned by 256 CTAs (one per digit row); the last CTA to finish turns the
+//     row totals into digit bases -- no single-CTA scan over the whole table;
+//   * a pass whose digit is the same for all keys is skipped on the device (log L keys share their top bits), and
+//     an input that is already sorted skips every pass: the dead-point store of a k = 0 run IS sorted (each shell
+//     is the sorted bottom of the live set and lies above the previous one), so count_crossed_edges' argsort
+//     (tree_structure.py:39) degenerates to the identity there.  Which buffer holds the data after each pass is a
+//     device-side decision, so all kernels pick their buffers through SortCtl.
+// Algorithmic traffic per executed pass: 8 n (histogram read) + 12 n (read) + 12 n (write) bytes.
 // =================================================================================================
 constexpr int kSortThreads = 256;
-constexpr int kSortItems = 8;
-constexpr int kSortTile = kSortThreads * kSortItems;
+constexpr int kSortItems = 16;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096
+constexpr int kSortWarps = kSortThreads / 32;
+
+struct SortCtl {
+    int curs[9];        // buffer (0 / 1) holding the data at the start of pass p; curs[8] = final
+    int skip[8];        // pass p is the identity (one digit value holds all keys)
+    int sorted;         // the input was already in stable ascending order
+    unsigned done[8];   // CTAs of the row scan that have finished (last one computes the digit bases)
+    unsigned total[256];
+    unsigned base[256];
+};
+
+__global__ void k_sort_init(SortCtl *ctl) {
+    const int t = threadIdx.x;
+    if (t < 9) ctl->curs[t] = 0;
+    if (t < 8) {
+        ctl->skip[t] = 0;
+        ctl->done[t] = 0;
+    }
+    if (t == 0) ctl->sorted = 1;
+}
 
 // keys_out[i + offset] = sort_key(x[i]); vals = iota.  `lead_neg_inf` prepends the -inf root node.
-__global__ void k_sort_prep(const double *x, long long n, int lead_neg_inf, uint64_t *keys, uint32_t *vals) {
+__global__ void k_sort_prep(const double *x, long long n, int lead_neg_inf, uint64_t *keys, uint32_t *vals,
+                            SortCtl *ctl) {
     const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = n + (lead_neg_inf ? 1 : 0);
     if (i >= total) return;
-    double v;
-    if (lead_neg_inf) v = (i == 0) ? -__longlong_as_double(0x7FF0000000000000ll) : x[i - 1];
-    else v = x[i];
-    keys[i] = sort_key_f64(v);
+    const double kNegInf = -__longlong_as_double(0x7FF0000000000000ll);
+    double v, vp = kNegInf;
+    if (lead_neg_inf) {
+        v = (i == 0) ? kNegInf : x[i - 1];
+        if (i > 1) vp = x[i - 2];
+    } else {
+        v = x[i];
+        if (i > 0) vp = x[i - 1];
+    }
+    const uint64_t k = sort_key_f64(v);
+    keys[i] = k;
     vals[i] = (uint32_t) i;
+    if (i > 0 && sort_key_f64(vp) > k) ctl->sorted = 0;  // benign race: every writer stores 0
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint64_t *keys, long long n, int shift,
+__device__ __forceinline__ long long sort_item_index(long long tile_base, int warp, int r, int lane) {
+    return tile_base + (long long) warp * (kSortItems * 32) + r * 32 + lane;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint64_t *keys0, const uint64_t *keys1,
+                                                             const SortCtl *ctl, long long n, int pass,
                                                              uint32_t *hist, int nblocks) {
+    if (ctl->sorted) return;
     __shared__ uint32_t h[256];
+    const uint64_t *keys = ctl->curs[pass] ? keys1 : keys0;
+    const int shift = pass * 8;
     h[threadIdx.x] = 0;
     __syncthreads();
     const long long base = (long long) blockIdx.x * kSortTile;
@@ -214,14 +281,268 @@ __global__ void __launch_bounds__(kSortThreads) k_radix_hist(const uint64_t *key
     hist[(size_t) threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
 }
 
-// In-place exclusive scan of `cnt` uint32 entries by one CTA of 1024 threads.
+// CTA b: in-place exclusive scan of row b of the digit-major table (`cnt` entries); the last CTA to finish turns the
+// 256 row totals into digit bases and decides whether the pass is the identity.
+__global__ void __launch_bounds__(256) k_radix_scan_rows(uint32_t *hist, SortCtl *ctl, long long n, int pass, int cnt) {
+    if (ctl->sorted) return;
+    __shared__ uint32_t sh[9];
+    __shared__ int last;
+    uint32_t *row = hist + (size_t) blockIdx.x * cnt;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = 0;
+    for (int c0 = 0; c0 < cnt; c0 += 256) {
+        const int i = c0 + threadIdx.x;
+        const uint32_t v = (i < cnt) ? row[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        __syncthreads();
+        if (lane == 31) sh[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t x = sh[w];
+            if (w < warp) woff += x;
+            tot += x;
+        }
+        if (i < cnt) row[i] = carry + woff + inc - v;
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        ctl->total[blockIdx.x] = carry;
+        __threadfence();
+        last = atomicAdd(&ctl->done[pass], 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    const uint32_t v = ((volatile unsigned *) ctl->total)[threadIdx.x];
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sh[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (w < warp) woff += sh[w];
+    ctl->base[threadIdx.x] = woff + inc - v;
+    const int trivial = __syncthreads_or(v == (uint32_t) n);
+    if (threadIdx.x == 0) {
+        ctl->skip[pass] = trivial;
+        ctl->curs[pass + 1] = ctl->curs[pass] ^ (trivial ? 0 : 1);
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(uint64_t *keys0, uint64_t *keys1, uint32_t *vals0,
+                                                                uint32_t *vals1, const SortCtl *ctl, long long n,
+                                                                int pass, const uint32_t *offsets, int nblocks) {
+    if (ctl->sorted || ctl->skip[pass]) return;
+    extern __shared__ unsigned char rs_smem[];
+    uint64_t *skeys = (uint64_t *) rs_smem;                               // [kSortTile]
+    uint32_t *svals = (uint32_t *) (skeys + kSortTile);                   // [kSortTile]
+    uint32_t *wcnt = svals + kSortTile;                                   // [kSortWarps][256]
+    uint32_t *tstart = wcnt + kSortWarps * 256;                           // [256] first sorted position of a digit
+    uint32_t *gbase = tstart + 256;                                       // [256] global position of that run
+    __shared__ uint32_t sh[9];
+    const int cur = ctl->curs[pass];
+    const uint64_t *keys_in = cur ? keys1 : keys0;
+    const uint32_t *vals_in = cur ? vals1 : vals0;
+    uint64_t *keys_out = cur ? keys0 : keys1;
+    uint32_t *vals_out = cur ? vals0 : vals1;
+    const int shift = pass * 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) wcnt[w * 256 + tid] = 0;
+    gbase[tid] = ctl->base[tid] + offsets[(size_t) tid * nblocks + blockIdx.x];
+    __syncthreads();
+    const long long tile = (long long) blockIdx.x * kSortTile;
+    uint64_t key[kSortItems];
+    uint32_t val[kSortItems];
+    uint32_t meta[kSortItems];  // digit | rank inside the warp's chunk << 9
+    uint32_t *mycnt = wcnt + warp * 256;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const long long i = sort_item_index(tile, warp, r, lane);
+        const bool valid = i < n;
+        key[r] = valid ? keys_in[i] : 0;
+        val[r] = valid ? vals_in[i] : 0;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const long long i = sort_item_index(tile, warp, r, lane);
+        const bool valid = i < n;
+        const unsigned digit = valid ? (unsigned) ((key[r] >> shift) & 255u) : 256u;
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
+        const unsigned rk = __popc(peers & ((1u << lane) - 1u));
+        uint32_t before = 0;
+        if (valid) before = mycnt[digit];
+        __syncwarp();
+        if (valid && rk == 0) mycnt[digit] = before + __popc(peers);
+        __syncwarp();
+        meta[r] = digit | ((before + rk) << 9);
+    }
+    __syncthreads();
+    // digit tid: warp counts -> exclusive prefix over the warps, total -> exclusive scan over the digits
+    {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w) {
+            const uint32_t c = wcnt[w * 256 + tid];
+            wcnt[w * 256 + tid] = run;
+            run += c;
+        }
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) sh[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w)
+            if (w < warp) woff += sh[w];
+        tstart[tid] = woff + inc - run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const unsigned digit = meta[r] & 511u;
+        if (digit < 256u) {
+            const uint32_t pos = tstart[digit] + mycnt[digit] + (meta[r] >> 9);
+            skeys[pos] = key[r];
+            svals[pos] = val[r];
+        }
+    }
+    __syncthreads();
+    const int count = (int) min((long long) kSortTile, n - tile);
+    for (int q = tid; q < count; q += kSortThreads) {
+        const uint64_t k = skeys[q];
+        const unsigned digit = (unsigned) ((k >> shift) & 255u);
+        const uint32_t dst = gbase[digit] + ((uint32_t) q - tstart[digit]);
+        keys_out[dst] = k;
+        vals_out[dst] = svals[q];
+    }
+}
+
+constexpr size_t kSortScatterSmem = (size_t) kSortTile * 12 + (size_t) kSortWarps * 256 * 4 + 2 * 256 * 4;
+
+struct SortWorkspace {
+    uint64_t *keys[2];
+    uint32_t *vals[2];
+    uint32_t *hist;
+    SortCtl *ctl;
+    int nblocks;
+};
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
+
+inline size_t sort_workspace_bytes(long long n) {
+    const long long nb = (n + kSortTile - 1) / kSortTile;
+    return 2 * align256((size_t) n * 8) + 2 * align256((size_t) n * 4) + align256((size_t) 256 * nb * 4) +
+           align256(sizeof(SortCtl)) + 256;
+}
+
+inline SortWorkspace carve_sort_workspace(void *ws, long long n) {
+    SortWorkspace w;
+    char *p = (char *) ws;
+    p = (char *) align256((size_t) p);
+    w.nblocks = (int) ((n + kSortTile - 1) / kSortTile);
+    w.keys[0] = (uint64_t *) p; p += align256((size_t) n * 8);
+    w.keys[1] = (uint64_t *) p; p += align256((size_t) n * 8);
+    w.vals[0] = (uint32_t *) p; p += align256((size_t) n * 4);
+    w.vals[1] = (uint32_t *) p; p += align256((size_t) n * 4);
+    w.hist = (uint32_t *) p; p += align256((size_t) 256 * w.nblocks * 4);
+    w.ctl = (SortCtl *) p;
+    return w;
+}
+
+// Sorts keys[0]/vals[0] (n entries, written by k_sort_prep after k_sort_init); the result is in
+// keys[ctl->curs[8]] / vals[ctl->curs[8]].  Returns a CUDA error code.
+inline cudaError_t radix_sort_pairs(const SortWorkspace &w, long long n, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t err = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int) kSortScatterSmem);
+        if (err != cudaSuccess) return err;
+        attr_set = true;
+    }
+    for (int pass = 0; pass < 8; ++pass) {
+        k_radix_hist<<<w.nblocks, kSortThreads, 0, st>>>(w.keys[0], w.keys[1], w.ctl, n, pass, w.hist, w.nblocks);
+        k_radix_scan_rows<<<256, 256, 0, st>>>(w.hist, w.ctl, n, pass, w.nblocks);
+        k_radix_scatter<<<w.nblocks, kSortThreads, kSortScatterSmem, st>>>(w.keys[0], w.keys[1], w.vals[0], w.vals[1],
+                                                                            w.ctl, n, pass, w.hist, w.nblocks);
+    }
+    return cudaGetLastError();
+}
+
+__global__ void k_vals_to_i64(const uint32_t *vals0, const uint32_t *vals1, const SortCtl *ctl, long long n,
+                              long long *out) {
+    const uint32_t *vals = ctl->curs[8] ? vals1 : vals0;
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (long long) vals[i];
+}
+
+// =================================================================================================
+// Tree-structure live-point counting.
+// =================================================================================================
+// out_degree[sender] += 1 (tree_structure.py:54-56).  All replacements of a shell share one sender, so the
+// increments come in runs of thousands on one address: equal values inside a warp are combined first.
+__global__ void k_out_degree(const long long *sender, long long M, int *outdeg) {
+    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < M;
+    long long s = valid ? sender[i] : -1;
+    if (valid && s < 0) s = 0;  // lax.max(sender, 0)
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
+    if (valid && __popc(peers & ((1u << lane) - 1u)) == 0) atomicAdd(&outdeg[s], __popc(peers));
+}
+
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 16;
+constexpr int kScanTile = kScanThreads * kScanItems;
+
+// pass 1: per-tile sums of delta_i = outdeg[sort_idx[i]] - 1
+__global__ void __launch_bounds__(kScanThreads) k_tree_tile_sums(const uint32_t *idx0, const uint32_t *idx1,
+                                                                 const SortCtl *ctl, const int *outdeg, long long n,
+                                                                 int *tile_sums) {
+    __shared__ int sh[kScanThreads / 32];
+    const uint32_t *sort_idx = ctl->curs[8] ? idx1 : idx0;
+    const long long base = (long long) blockIdx.x * kScanTile + (long long) threadIdx.x * kScanItems;
+    int s = 0;
+#pragma unroll
+    for (int r = 0; r < kScanItems; ++r) {
+        const long long i = base + r;
+        if (i < n) s += outdeg[sort_idx[i]] - 1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// In-place exclusive scan of `cnt` uint32 entries by one CTA of 1024 threads (tile sums: n / 4096 entries).
 __global__ void __launch_bounds__(1024) k_scan_u32_excl(uint32_t *data, long long cnt) {
     __shared__ uint32_t sh[33];
     const long long per = (cnt + blockDim.x - 1) / blockDim.x;
     const long long b = (long long) threadIdx.x * per, e = min(cnt, b + per);
     uint32_t s = 0;
     for (long long i = b; i < e; ++i) s += data[i];
-    // block exclusive scan of s
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = s;
 #pragma unroll
@@ -249,142 +570,14 @@ __global__ void __launch_bounds__(1024) k_scan_u32_excl(uint32_t *data, long lon
     }
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_radix_scatter(const uint64_t *keys_in, const uint32_t *vals_in,
-                                                                uint64_t *keys_out, uint32_t *vals_out,
-                                                                long long n, int shift, const uint32_t *offsets,
-                                                                int nblocks) {
-    __shared__ uint32_t base[256];
-    __shared__ uint32_t wcnt[kSortThreads / 32][256];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    base[tid] = offsets[(size_t) tid * nblocks + blockIdx.x];
-#pragma unroll
-    for (int w = 0; w < kSortThreads / 32; ++w) wcnt[w][tid] = 0;
-    __syncthreads();
-    const long long tile = (long long) blockIdx.x * kSortTile;
-    for (int r = 0; r < kSortItems; ++r) {
-        const long long i = tile + (long long) r * kSortThreads + tid;
-        const bool valid = i < n;
-        uint64_t key = 0;
-        uint32_t val = 0;
-        unsigned digit = 256u;  // sentinel for out-of-range lanes
-        if (valid) {
-            key = keys_in[i];
-            val = vals_in[i];
-            digit = (unsigned) ((key >> shift) & 255u);
-        }
-        const unsigned peers = __match_any_sync(0xFFFFFFFFu, digit);
-        const unsigned rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) wcnt[warp][digit] = __popc(peers);
-        __syncthreads();
-        if (valid) {
-            uint32_t off = base[digit];
-            for (int w = 0; w < warp; ++w) off += wcnt[w][digit];
-            keys_out[off + rank] = key;
-            vals_out[off + rank] = val;
-        }
-        __syncthreads();
-        uint32_t add = 0;
-#pragma unroll
-        for (int w = 0; w < kSortThreads / 32; ++w) {
-            add += wcnt[w][tid];
-            wcnt[w][tid] = 0;
-        }
-        base[tid] += add;
-        __syncthreads();
-    }
-}
-
-struct SortWorkspace {
-    uint64_t *keys[2];
-    uint32_t *vals[2];
-    uint32_t *hist;
-    int nblocks;
-};
-
-inline size_t align256(size_t x) { return (x + 255) & ~(size_t) 255; }
-
-inline size_t sort_workspace_bytes(long long n) {
-    const long long nb = (n + kSortTile - 1) / kSortTile;
-    return 2 * align256((size_t) n * 8) + 2 * align256((size_t) n * 4) + align256((size_t) 256 * nb * 4) + 256;
-}
-
-inline SortWorkspace carve_sort_workspace(void *ws, long long n) {
-    SortWorkspace w;
-    char *p = (char *) ws;
-    p = (char *) align256((size_t) p);
-    w.nblocks = (int) ((n + kSortTile - 1) / kSortTile);
-    w.keys[0] = (uint64_t *) p; p += align256((size_t) n * 8);
-    w.keys[1] = (uint64_t *) p; p += align256((size_t) n * 8);
-    w.vals[0] = (uint32_t *) p; p += align256((size_t) n * 4);
-    w.vals[1] = (uint32_t *) p; p += align256((size_t) n * 4);
-    w.hist = (uint32_t *) p;
-    return w;
-}
-
-// Sorts keys[0]/vals[0] (n entries); result ends in keys[0]/vals[0] (8 passes = even).
-inline void radix_sort_pairs(const SortWorkspace &w, long long n, cudaStream_t st) {
-    if (n <= 0) return;
-    int cur = 0;
-    for (int pass = 0; pass < 8; ++pass) {
-        const int shift = pass * 8;
-        k_radix_hist<<<w.nblocks, kSortThreads, 0, st>>>(w.keys[cur], n, shift, w.hist, w.nblocks);
-        k_scan_u32_excl<<<1, 1024, 0, st>>>(w.hist, (long long) 256 * w.nblocks);
-        k_radix_scatter<<<w.nblocks, kSortThreads, 0, st>>>(w.keys[cur], w.vals[cur], w.keys[cur ^ 1], w.vals[cur ^ 1],
-                                                             n, shift, w.hist, w.nblocks);
-        cur ^= 1;
-    }
-}
-
-__global__ void k_vals_to_i64(const uint32_t *vals, long long n, long long *out) {
-    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = (long long) vals[i];
-}
-
-// =================================================================================================
-// Tree-structure live-point counting.
-// =================================================================================================
-__global__ void k_out_degree(const long long *sender, long long M, int *outdeg) {
-    const long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < M) {
-        long long s = sender[i];
-        if (s < 0) s = 0;  // lax.max(sender, 0), tree_structure.py:54-56
-        atomicAdd(&outdeg[s], 1);
-    }
-}
-
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
-constexpr int kScanTile = kScanThreads * kScanItems;
-
-// pass 1: per-tile sums of delta_i = outdeg[sort_idx[i]] - 1
-__global__ void __launch_bounds__(kScanThreads) k_tree_tile_sums(const uint32_t *sort_idx, const int *outdeg,
-                                                                 long long n, int *tile_sums) {
-    __shared__ int sh[kScanThreads / 32];
-    const long long base = (long long) blockIdx.x * kScanTile + (long long) threadIdx.x * kScanItems;
-    int s = 0;
-#pragma unroll
-    for (int r = 0; r < kScanItems; ++r) {
-        const long long i = base + r;
-        if (i < n) s += outdeg[sort_idx[i]] - 1;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < kScanThreads / 32; ++w) t += sh[w];
-        tile_sums[blockIdx.x] = t;
-    }
-}
-
-// pass 2: exclusive scan of tile sums by a single CTA (reuses the u32 scan; int32 wraps identically)
 // pass 3: per-tile inclusive scan + outputs
-__global__ void __launch_bounds__(kScanThreads) k_tree_apply(const uint32_t *sort_idx, const int *outdeg, long long n,
+__global__ void __launch_bounds__(kScanThreads) k_tree_apply(const uint32_t *idx0, const uint32_t *idx1,
+                                                             const SortCtl *ctl, const int *outdeg, long long n,
                                                              const int *tile_offsets, long long M,
                                                              long long num_samples, long long *out_idx,
                                                              int *out_nlive) {
     __shared__ int sh[kScanThreads / 32 + 1];
+    const uint32_t *sort_idx = ctl->curs[8] ? idx1 : idx0;
     const long long base = (long long) blockIdx.x * kScanTile + (long long) threadIdx.x * kScanItems;
     int loc[kScanItems];
     int s = 0;
@@ -505,6 +698,9 @@ __global__ void k_ev_tables(long long nmax, double *tabT, double *tabT2, double 
     }
 }
 
+// doubles of global scratch per cluster-level scan (K <= 3 values per rank); 16 ranks -> the historic 48
+__host__ __device__ inline size_t ev_gpart_stride(unsigned nranks) { return 3 * (size_t) (nranks < 16 ? 16 : nranks); }
+
 struct EvOut {
     NsEvidenceCalc *mid;     // state after element index mark-1 (nullable)
     long long mark;
@@ -590,7 +786,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in3[3] = {sa, sb, sw}, ex3[3];
-    cluster_scan_excl_k<OpLae, 3>(in3, sh, gpart + 48, ex3, grp);
+    cluster_scan_excl_k<OpLae, 3>(in3, sh, gpart + ev_gpart_stride(grp.nranks()), ex3, grp);
     const double Z0 = logaddexp(init.log_Z_mean, ex3[0]);
     const double dZ20 = logaddexp(init.log_dZ2_mean, ex3[1]);
     const double W0 = logaddexp(init.log_ZX_mean - init.log_X_mean, ex3[2]);
@@ -608,7 +804,7 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
         })
     }
     double in1[1] = {sc}, ex1[1];
-    cluster_scan_excl_k<OpLae, 1>(in1, sh, gpart + 96, ex1, grp);
+    cluster_scan_excl_k<OpLae, 1>(in1, sh, gpart + 2 * ev_gpart_stride(grp.nranks()), ex1, grp);
     const double Z20 = logaddexp(init.log_Z2_mean, ex1[0]);
     // pass 4: outputs (skipped by threads that own neither a requested position nor per-sample rows)
     const bool wanted = out.per_sample || (out.mid && out.mark - 1 >= b && out.mark - 1 < e) || (out.fin && M - 1 >= b && M - 1 < e);
@@ -658,12 +854,23 @@ __device__ inline void evidence_scan_block(const EvSeq &q, const NsEvidenceCalc 
 }
 
 constexpr int kEvCluster = 8;    // CTAs per cluster (portable maximum)
+constexpr int kEvMaxGrid = 256;  // CTAs of the cooperative form (<= kEvThreads: the rank scan is one block scan)
 constexpr int kEvThreads = 512;  // threads per CTA
 
 __global__ void __cluster_dims__(kEvCluster, 1, 1) __launch_bounds__(kEvThreads)
 k_evidence_stats(EvSeq q, NsEvidenceCalc init, EvOut out, double *gpart) {
     __shared__ double sh[3][34];
     ClusterSync grp;
+    evidence_scan_block<0>(q, init, out, sh, gpart, grp);
+}
+
+// Long dead sets (final pass, M up to 1e7): up to one CTA per SM, launched cooperatively (co-residency is what
+// the software barrier needs).  The scans are bound by the FP64 pipe (about 25 log / exp per element and pass),
+// not by HBM: 80 M bytes of traffic against ~3000 FP64 instructions per element.
+__global__ void __launch_bounds__(kEvThreads)
+k_evidence_stats_grid(EvSeq q, NsEvidenceCalc init, EvOut out, double *gpart, unsigned *bar) {
+    __shared__ double sh[3][34];
+    GridSync grp{bar, 0u};
     evidence_scan_block<0>(q, init, out, sh, gpart, grp);
 }
 

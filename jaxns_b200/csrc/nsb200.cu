@@ -55,7 +55,7 @@ extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
 // it at run time (tests A/B kernels inside one process).  None of them changes results.
 enum {
     OPT_SPEC, OPT_TPB, OPT_SLICE_MMA, OPT_MMA_P, OPT_MMA_WPB, OPT_MERGE_BRUTE, OPT_GEN_MODE, OPT_GEN_SMS, OPT_GEN_TPB,
-    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_SORT_LEGACY, OPT_COUNT
+    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_COUNT
 };
 struct NsOption {
     const char *name;
@@ -64,11 +64,10 @@ struct NsOption {
     bool loaded;
 };
 static NsOption g_opts[OPT_COUNT] = {
-    {"NSB200_SPEC", 0, 0, false},        {"NSB200_TPB", 0, 0, false},         {"NSB200_SLICE_MMA", 1, 0, false},
+    {"NSB200_SPEC", 0, 0, false},        {"NSB200_TPB", 0, 0, false},         {"NSB200_SLICE_MMA", 8, 0, false},
     {"NSB200_MMA_P", 0, 0, false},       {"NSB200_MMA_WPB", 4, 0, false},     {"NSB200_MERGE_BRUTE", 0, 0, false},
     {"NSB200_GEN_MODE", 3, 0, false},    {"NSB200_GEN_SMS", 0, 0, false},     {"NSB200_GEN_TPB", 0, 0, false},
     {"NSB200_EPI_CLUSTER", 0, 0, false}, {"NSB200_DEPTH", 4, 0, false},       {"NSB200_TRACE", 0, 0, false},
-    {"NSB200_SORT_LEGACY", 0, 0, false},
 };
 static int opt(int id) {
     NsOption &o = g_opts[id];
@@ -280,21 +279,70 @@ extern "C" int nsb200_forward_batch(const NsModelDesc *model, const double *U, i
     return 0;
 }
 
-__global__ void k_seed_table(long long N, double *out) {
+// c[q] = logaddexp-cumsum of q + 1 zeros, continued from c[start - 1] (start = 0: from -inf).  The recurrence is
+// serial by definition (it has to round like the reference's sequential cumulative_logsumexp, log_semiring.py:51-92).
+__global__ void k_seed_table(long long start, long long N, double *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double acc = -__longlong_as_double(0x7FF0000000000000ll);
-    for (long long q = 0; q < N; ++q) {
+    double acc = start > 0 ? out[start - 1] : -__longlong_as_double(0x7FF0000000000000ll);
+    for (long long q = start; q < N; ++q) {
         acc = logaddexp(acc, 0.0);
         out[q] = acc;
     }
 }
 
+// The table for N is a prefix of the table for any N' > N and depends on nothing else, so the library keeps ONE per
+// process and device and only ever computes the missing tail (0.36 us per entry on one thread: 1.2 ms at N = 3200,
+// 36 ms at N = 1e5 -- paid once instead of by every new engine).
+struct SeedTableCache {
+    double *ptr = nullptr;
+    long long n = 0;
+    int device = -1;
+    cudaEvent_t ready = nullptr;
+};
+static SeedTableCache g_seed_cache;
+static std::mutex g_seed_mutex;
+
+// Enqueues on `st` a copy of the first N table entries into `out` (device), extending the cache first if needed.
+static int seed_table_into(long long N, double *out, cudaStream_t st) {
+    std::lock_guard<std::mutex> lock(g_seed_mutex);
+    int dev = -1;
+    NSB_CUDA(cudaGetDevice(&dev));
+    SeedTableCache &c = g_seed_cache;
+    if (c.device != dev) {  // one device per process in this framework: a device switch simply starts over
+        if (c.ptr) cudaFree(c.ptr);
+        if (c.ready) cudaEventDestroy(c.ready);
+        c = SeedTableCache();
+        c.device = dev;
+        NSB_CUDA(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
+    }
+    if (N > c.n) {
+        const long long n_new = N > 2 * c.n ? N : 2 * c.n;
+        double *q = nullptr;
+        NSB_CUDA(cudaMalloc(&q, (size_t) n_new * 8));
+        if (c.n > 0) {
+            NSB_CUDA(cudaStreamWaitEvent(st, c.ready, 0));
+            NSB_CUDA(cudaMemcpyAsync(q, c.ptr, (size_t) c.n * 8, cudaMemcpyDeviceToDevice, st));
+        }
+        k_seed_table<<<1, 1, 0, st>>>(c.n, n_new, q);
+        NSB_LAUNCH_CHECK();
+        NSB_CUDA(cudaEventRecord(c.ready, st));
+        if (c.ptr) {
+            NSB_CUDA(cudaDeviceSynchronize());  // the old table may still be read by copies enqueued on other streams
+            cudaFree(c.ptr);
+        }
+        c.ptr = q;
+        c.n = n_new;
+    } else {
+        NSB_CUDA(cudaStreamWaitEvent(st, c.ready, 0));
+    }
+    NSB_CUDA(cudaMemcpyAsync(out, c.ptr, (size_t) N * 8, cudaMemcpyDeviceToDevice, st));
+    return 0;
+}
+
 extern "C" int nsb200_seed_table(int64_t N, double *out, nsb200_stream_t stream) {
     if (N <= 0) return 0;
     if (!out) return fail("out is NULL");
-    k_seed_table<<<1, 1, 0, (cudaStream_t) stream>>>(N, out);
-    NSB_LAUNCH_CHECK();
-    return 0;
+    return seed_table_into(N, out, (cudaStream_t) stream);
 }
 
 static int launch_draw(const NsModelDesc *model, Key key, const double *contour, long long begin, long long end,
@@ -368,9 +416,20 @@ static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st
 }
 
 // ---- FP64 tensor-core slice kernel (ns_slice_mma.cuh): dense Gaussian, D <= 32, pre-generated streams ----------
+// Which slice kernel runs the dense Gaussian family with D <= 32 (NSB200_SLICE_MMA): 0 = lane-per-dimension kernel,
+// 1 = DMMA kernel, 2 / 4 = warp teams, 8 (default) = by size.  The DMMA kernel is a THROUGHPUT design: a warp
+// carries 8 proposal columns and issues ~1150 instructions per round with little instruction-level parallelism in
+// its bookkeeping, so a round takes ~5400 cycles against ~2400 for the lane kernel's one-chain warp
+// (profiles/r2/mma_cycles_r2.txt).  A nested-sampling launch is S sequential slices per chain: with 1600 chains
+// (config 2: 400 DMMA warps on 592 sub-partitions) the launch time is rounds x round latency and the lane kernel
+// wins 0.55 ms to 0.77 ms; once the chains fill the machine several times over (>= 8192 per GPU) the DMMA
+// kernel's lower instruction count per evaluation wins (profiles/r2/slice_crossover_r2.txt).
+constexpr long long kSliceMmaMinChains = 8192;
+
 static bool slice_mma_eligible(const SliceArgs &a) {
-    // NSB200_SLICE_MMA=0: always the lane-per-dimension kernel (A/B, parity)
-    return opt(OPT_SLICE_MMA) != 0 && a.model.family == NSB200_FAM_GAUSS_DENSE && a.model.D <= 32 && a.pre_dirs != nullptr;
+    const int mode = opt(OPT_SLICE_MMA);
+    const bool by_size = mode == 8 && (a.chain_end - a.chain_begin) >= kSliceMmaMinChains;
+    return (mode == 1 || by_size) && a.model.family == NSB200_FAM_GAUSS_DENSE && a.model.D <= 32 && a.pre_dirs != nullptr;
 }
 
 // Speculative proposals per chain and round: a warp carries 8 proposal columns = 8 / P chains.  One warp per SM
@@ -432,10 +491,36 @@ static int launch_slice_mma(const SliceArgs &a, cudaStream_t st, bool pdl) {
     return 0;
 }
 
+// ---- warp teams (ns_slice.cuh k_slice_chains_team): W warps per chain, one speculative proposal each ------------
+template <int W>
+static int launch_slice_team_t(const SliceArgs &a, cudaStream_t st, bool pdl) {
+    const long long n = a.chain_end - a.chain_begin;
+    const size_t smem = 8 * (model_smem_doubles(a.model.family, a.model.D, 32, 1, a.model.K, true) +
+                             (size_t) W * chain_smem_doubles(32, 1, 1, true) + 2 * W);
+    if (set_smem(k_slice_chains_team<W>, smem)) return 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned) n);
+    cfg.blockDim = dim3((unsigned) (32 * W));
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    NSB_CUDA(cudaLaunchKernelEx(&cfg, k_slice_chains_team<W>, a));
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
 static int launch_slice(const SliceArgs &a, cudaStream_t st, bool pdl = false) {
     Geometry g;
     if (pick_geometry(a.model.D, g)) return 1;
     if (a.chain_end <= a.chain_begin) return 0;
+    if ((opt(OPT_SLICE_MMA) == 2 || opt(OPT_SLICE_MMA) == 4) && a.model.family == NSB200_FAM_GAUSS_DENSE && g.G == 32 && g.DPL == 1 && a.pre_dirs) {
+        return opt(OPT_SLICE_MMA) == 4 ? launch_slice_team_t<4>(a, st, pdl) : launch_slice_team_t<2>(a, st, pdl);
+    }
     if (slice_mma_eligible(a)) return launch_slice_mma(a, st, pdl);
     const int P = pick_spec(g);
     if (g.G == 32 && g.DPL == 1) {
@@ -744,7 +829,7 @@ extern "C" int64_t nsb200_workspace_bytes(int32_t op, int64_t n) {
     switch (op) {
         case NSB200_WS_ARGSORT: return (int64_t) sort_workspace_bytes(n > 0 ? n : 1);
         case NSB200_WS_COUNT_CROSSED_EDGES: return (int64_t) tree_workspace_bytes(n);
-        case NSB200_WS_EVIDENCE_STATS: return 144 * 8 + 256;
+        case NSB200_WS_EVIDENCE_STATS: return (int64_t) (3 * ev_gpart_stride(kEvMaxGrid) * 8 + 512);
         case NSB200_WS_LOGSUMEXP: return 256;
         default: return -1;
     }
@@ -758,9 +843,10 @@ extern "C" int nsb200_argsort_f64(const double *keys, int64_t n, int64_t *out_id
     if (workspace_bytes < (int64_t) sort_workspace_bytes(n)) return fail("workspace too small: %lld < %zu", (long long) workspace_bytes, sort_workspace_bytes(n));
     cudaStream_t st = (cudaStream_t) stream;
     SortWorkspace w = carve_sort_workspace(workspace, n);
-    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(keys, n, 0, w.keys[0], w.vals[0]);
-    radix_sort_pairs(w, n, st);
-    k_vals_to_i64<<<grid_for(n, 256), 256, 0, st>>>(w.vals[0], n, (long long *) out_idx);
+    k_sort_init<<<1, 32, 0, st>>>(w.ctl);
+    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(keys, n, 0, w.keys[0], w.vals[0], w.ctl);
+    NSB_CUDA(radix_sort_pairs(w, n, st));
+    k_vals_to_i64<<<grid_for(n, 256), 256, 0, st>>>(w.vals[0], w.vals[1], w.ctl, n, (long long *) out_idx);
     NSB_LAUNCH_CHECK();
     return 0;
 }
@@ -777,18 +863,19 @@ extern "C" int nsb200_count_crossed_edges(const int64_t *sender_node_idx, const 
     cudaStream_t st = (cudaStream_t) stream;
     const long long n = M + 1;
     SortWorkspace w = carve_sort_workspace(workspace, n);
-    char *p = (char *) w.hist + align256((size_t) 256 * w.nblocks * 4);
+    char *p = (char *) w.ctl + align256(sizeof(SortCtl));
     int *outdeg = (int *) p;
     p += align256((size_t) n * 4);
     int *tile_sums = (int *) p;
     const int tiles = (int) ((n + kScanTile - 1) / kScanTile);
-    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(log_L, M, 1, w.keys[0], w.vals[0]);
-    radix_sort_pairs(w, n, st);
+    k_sort_init<<<1, 32, 0, st>>>(w.ctl);
+    k_sort_prep<<<grid_for(n, 256), 256, 0, st>>>(log_L, M, 1, w.keys[0], w.vals[0], w.ctl);
+    NSB_CUDA(radix_sort_pairs(w, n, st));
     NSB_CUDA(cudaMemsetAsync(outdeg, 0, (size_t) n * 4, st));
     k_out_degree<<<grid_for(M, 256), 256, 0, st>>>((const long long *) sender_node_idx, M, outdeg);
-    k_tree_tile_sums<<<tiles, kScanThreads, 0, st>>>(w.vals[0], outdeg, n, tile_sums);
+    k_tree_tile_sums<<<tiles, kScanThreads, 0, st>>>(w.vals[0], w.vals[1], w.ctl, outdeg, n, tile_sums);
     k_scan_u32_excl<<<1, 1024, 0, st>>>((uint32_t *) tile_sums, tiles);
-    k_tree_apply<<<tiles, kScanThreads, 0, st>>>(w.vals[0], outdeg, n, tile_sums, M, num_samples,
+    k_tree_apply<<<tiles, kScanThreads, 0, st>>>(w.vals[0], w.vals[1], w.ctl, outdeg, n, tile_sums, M, num_samples,
                                                  (long long *) out_samples_indices, out_num_live_points);
     NSB_LAUNCH_CHECK();
     return 0;
@@ -813,7 +900,8 @@ extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *l
     if (M < 0) return fail("M < 0");
     if (M > 0 && (!log_L || !num_live_points)) return fail("NULL input");
     if (!out_final) return fail("out_final is NULL");
-    if (!workspace || workspace_bytes < 144 * 8 + 256) return fail("workspace too small (nsb200_workspace_bytes(NSB200_WS_EVIDENCE_STATS, M))");
+    if (!workspace || workspace_bytes < (int64_t) (3 * ev_gpart_stride(kEvMaxGrid) * 8 + 512))
+        return fail("workspace too small (nsb200_workspace_bytes(NSB200_WS_EVIDENCE_STATS, M))");
     EvSeq q;
     q.la = log_L;
     q.na = num_live_points;
@@ -830,8 +918,29 @@ extern "C" int nsb200_evidence_stats(const NsEvidenceCalc *init, const double *l
     o.fin = out_final;
     o.per_sample = out_per_sample;
     double *gpart = (double *) align256((size_t) workspace);
-    k_evidence_stats<<<kEvCluster, kEvThreads, 0, (cudaStream_t) stream>>>(q, init ? *init : init_evidence_calc(), o, gpart);
-    NSB_LAUNCH_CHECK();
+    cudaStream_t st = (cudaStream_t) stream;
+    NsEvidenceCalc init_v = init ? *init : init_evidence_calc();
+    // a thread should own at least ~8 elements before more CTAs pay for their barrier trips
+    long long want = (M + (long long) kEvThreads * 8 - 1) / ((long long) kEvThreads * 8);
+    static int max_coresident = 0;
+    if (!max_coresident) {
+        int sms = 148, per_sm = 1;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_evidence_stats_grid, kEvThreads, 0) != cudaSuccess || per_sm < 1)
+            per_sm = 1;
+        max_coresident = sms;  // one CTA per SM: the scans are latency / FP64 bound, more resident CTAs only add barrier cost
+        if (max_coresident > kEvMaxGrid) max_coresident = kEvMaxGrid;
+    }
+    if (want <= kEvCluster) {
+        k_evidence_stats<<<kEvCluster, kEvThreads, 0, st>>>(q, init_v, o, gpart);
+        NSB_LAUNCH_CHECK();
+        return 0;
+    }
+    int ctas = want > max_coresident ? max_coresident : (int) want;
+    unsigned *bar = (unsigned *) ((char *) gpart + 3 * ev_gpart_stride(kEvMaxGrid) * 8);
+    NSB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    void *args[] = {&q, &init_v, &o, &gpart, &bar};
+    NSB_CUDA(cudaLaunchCooperativeKernel((void *) k_evidence_stats_grid, dim3((unsigned) ctas), dim3(kEvThreads), args, 0, st));
     return 0;
 }
 
@@ -952,6 +1061,7 @@ struct NsEngine {
     std::vector<std::pair<void **, size_t>> arena_slots;  // pointer location, byte offset in the arena
     size_t arena_bytes = 0;
     int arena_device = -1;
+    bool arena_exported = false;  // its IPC handle went to peer processes: never freed (see ArenaEntry)
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     double slice_ms = 0.0;
@@ -984,16 +1094,21 @@ static int dev_alloc(NsEngine *e, T **p, size_t count) {
     return 0;
 }
 
-// The arena of the most recently destroyed engine is kept (one per process and device) and handed to the next
-// engine of exactly the same size: a sampler rebuilt for every run -- what the public API invites -- then pays no
-// cudaMalloc / cudaFree (each 1-10 ms of driver time for a 100 MB arena, and a device-wide synchronisation).
-struct ArenaCache {
+// Arenas of destroyed engines are kept in a small per-process pool and handed to the next engine of exactly the
+// same size: a sampler rebuilt for every run -- what the public API invites -- then pays no cudaMalloc / cudaFree
+// (each 1-10 ms of driver time for a 100 MB arena, and a device-wide synchronisation).  An arena whose CUDA IPC
+// handle has been given to peer processes (fused all-gather) is never freed: the peers keep their mappings for the
+// life of the process (see open_peer_arena), and a rebuilt engine of the same size gets the same arena, so its
+// handle -- and the peers' mappings -- stay valid without any re-wiring.
+struct ArenaEntry {
     void *ptr = nullptr;
     size_t bytes = 0;
     int device = -1;
+    bool exported = false;
 };
-static ArenaCache g_arena_cache;
+static std::vector<ArenaEntry> g_arena_pool;
 static std::mutex g_arena_mutex;
+constexpr size_t kArenaPoolMax = 4;
 
 static int arena_commit(NsEngine *e) {
     void *q = nullptr;
@@ -1001,9 +1116,13 @@ static int arena_commit(NsEngine *e) {
     cudaGetDevice(&dev);
     {
         std::lock_guard<std::mutex> lock(g_arena_mutex);
-        if (g_arena_cache.ptr && g_arena_cache.bytes == e->arena_bytes && g_arena_cache.device == dev) {
-            q = g_arena_cache.ptr;
-            g_arena_cache = ArenaCache();
+        for (size_t i = 0; i < g_arena_pool.size(); ++i) {
+            if (g_arena_pool[i].bytes == e->arena_bytes && g_arena_pool[i].device == dev) {
+                q = g_arena_pool[i].ptr;
+                e->arena_exported = g_arena_pool[i].exported;
+                g_arena_pool.erase(g_arena_pool.begin() + i);
+                break;
+            }
         }
     }
     if (!q) {
@@ -1016,10 +1135,41 @@ static int arena_commit(NsEngine *e) {
     return 0;
 }
 
+// Peer arenas opened through CUDA IPC, by handle: opened once per process and never closed (opening costs ~15 ms
+// and closing the last mapping of a peer device tears its peer access down -- 100 ms stalls in the middle of a run).
+struct PeerMapping {
+    uint8_t handle[64];
+    void *ptr;
+};
+static std::vector<PeerMapping> g_peer_maps;
+static std::mutex g_peer_mutex;
+
+static int open_peer_arena(const uint8_t *handle, void **out) {
+    std::lock_guard<std::mutex> lock(g_peer_mutex);
+    for (const auto &m : g_peer_maps) {
+        if (memcmp(m.handle, handle, 64) == 0) {
+            *out = m.ptr;
+            return 0;
+        }
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *q = nullptr;
+    cudaError_t err = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        return fail("cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(err));
+    }
+    PeerMapping m;
+    memcpy(m.handle, handle, 64);
+    m.ptr = q;
+    g_peer_maps.push_back(m);
+    *out = q;
+    return 0;
+}
+
 extern "C" void nsb200_engine_destroy(NsEngine *e) {
     if (!e) return;
-    for (int r = 0; r < 8; ++r)
-        if (e->peer_base[r]) cudaIpcCloseMemHandle(e->peer_base[r]);
     for (void *p : e->allocs) {
         // kernels of this engine may still be running on the caller's stream: the next owner of the arena is only
         // safe after they are done (cudaFree would have waited for them as well)
@@ -1028,10 +1178,22 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
         {
             std::lock_guard<std::mutex> lock(g_arena_mutex);
             if (e->arena_bytes && e->arena_device >= 0) {
-                evict = g_arena_cache.ptr;
-                g_arena_cache.ptr = p;
-                g_arena_cache.bytes = e->arena_bytes;
-                g_arena_cache.device = e->arena_device;
+                evict = nullptr;
+                ArenaEntry a;
+                a.ptr = p;
+                a.bytes = e->arena_bytes;
+                a.device = e->arena_device;
+                a.exported = e->arena_exported;
+                g_arena_pool.push_back(a);
+                if (g_arena_pool.size() > kArenaPoolMax) {  // evict the oldest arena no peer can be mapping
+                    for (size_t i = 0; i < g_arena_pool.size(); ++i) {
+                        if (!g_arena_pool[i].exported) {
+                            evict = g_arena_pool[i].ptr;
+                            g_arena_pool.erase(g_arena_pool.begin() + i);
+                            break;
+                        }
+                    }
+                }
             }
         }
         if (evict) cudaFree(evict);
@@ -1104,7 +1266,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
             if (!rc) rc |= dev_alloc(e, &e->packed_buf[b], (size_t) e->m * e->row_doubles);
         }
         e->off_flags = e->arena_bytes;
-        if (!rc) rc |= dev_alloc(e, &e->p2p_flags, 8);
+        if (!rc) rc |= dev_alloc(e, &e->p2p_flags, 16);  // [0..8) arrival epochs, [8..16) the peers' contours
         if (!rc) rc |= dev_alloc(e, &e->p2p_epoch_dev, 1);
         if (!rc) rc |= dev_alloc(e, &e->p2p_err, 1);
     }
@@ -1135,7 +1297,7 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
     if (!rc) rc |= arena_commit(e);
     if (!rc) e->packed_home = e->packed;
     if (!rc && e->p2p_flags) {
-        if (cudaMemset(e->p2p_flags, 0, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        if (cudaMemset(e->p2p_flags, 0, 16 * sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(e->p2p_epoch_dev, 0, sizeof(unsigned long long)) != cudaSuccess ||
             cudaMemset(e->p2p_err, 0, sizeof(int)) != cudaSuccess)
             rc = fail("cudaMemset failed");
@@ -1169,6 +1331,7 @@ extern "C" int nsb200_engine_p2p_export(NsEngine *e, uint8_t handle[64], int64_t
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
     cudaIpcMemHandle_t h;
     NSB_CUDA(cudaIpcGetMemHandle(&h, e->allocs[0]));
+    e->arena_exported = true;
     memcpy(handle, &h, 64);
     offsets[0] = (int64_t) e->off_packed[0];
     offsets[1] = (int64_t) e->off_packed[1];
@@ -1185,14 +1348,8 @@ extern "C" int nsb200_engine_p2p_connect(NsEngine *e, const uint8_t *handles, co
         if (r == me) {
             base = (char *) e->allocs[0];
         } else {
-            cudaIpcMemHandle_t h;
-            memcpy(&h, handles + (size_t) r * 64, 64);
             void *q = nullptr;
-            cudaError_t err = cudaIpcOpenMemHandle(&q, h, cudaIpcMemLazyEnablePeerAccess);
-            if (err != cudaSuccess) {
-                cudaGetLastError();
-                return fail("cudaIpcOpenMemHandle(rank %d) failed: %s", r, cudaGetErrorString(err));
-            }
+            if (open_peer_arena(handles + (size_t) r * 64, &q)) return 1;
             e->peer_base[r] = q;
             base = (char *) q;
         }
@@ -1833,10 +1990,14 @@ extern "C" int nsb200_debug_timeline(unsigned long long *out4, int reset) {
 
 #ifdef NSB_PROFILE
 extern "C" int nsb200_debug_profile(unsigned long long *out16, int reset) {
-    if (out16) cudaMemcpyFromSymbol(out16, nsb::g_prof, 16 * 8);
+    if (out16) {
+        cudaMemcpyFromSymbol(out16, nsb::g_prof, 16 * 8);
+        cudaMemcpyFromSymbol(out16 + 9, nsb::g_tail_trips, 8);
+    }
     if (reset) {
         unsigned long long z[16] = {0};
         cudaMemcpyToSymbol(nsb::g_prof, z, 16 * 8);
+        cudaMemcpyToSymbol(nsb::g_tail_trips, z, 8);
     }
     return 0;
 }

@@ -112,3 +112,26 @@ class GaussianShellsLikelihood(RegisteredLikelihood):
             raise ValueError(f"Shells are {self.centres.shape[1]}-D but the prior has {D} dims.")
         return np.concatenate([np.concatenate([[self.widths[k], self.radii[k]], self.centres[k]])
                                for k in range(self.K)])
+
+
+def jaxify_likelihood(log_likelihood, vectorised: bool = False):
+    """framework/jaxify.py:15-53: wraps a host (numpy) log-likelihood so that Model accepts it.  The reference routes
+    it through jax.pure_callback; here the split slice step hands the transformed batch to the host function and
+    takes the values back to the device.  `vectorised`: the function handles a leading batch dimension itself."""
+    import warnings
+    import torch
+    warnings.warn(
+        "You're using a non-JAX log-likelihood function. This may be slower than a JAX log-likelihood function. "
+        "Also, you are responsible for ensuring that the function is deterministic. "
+        "Also, you cannot use learnable parameters in the likelihood call."
+    )
+
+    def _log_likelihood(*args):
+        host = [a.detach().cpu().numpy() for a in args]
+        if vectorised:
+            out = np.asarray(log_likelihood(*host), np.float64)
+        else:
+            out = np.asarray([log_likelihood(*[h[i] for h in host]) for i in range(host[0].shape[0])], np.float64)
+        return torch.from_numpy(out.reshape(-1)).to(args[0].device)
+
+    return _log_likelihood

@@ -361,7 +361,11 @@ class ShardedStaticNestedSampler:
                 if world > 1:  # every rank leaves the rounds together (the all-gather below must stay matched)
                     import torch.distributed as dist
                     dist.all_reduce(active, op=dist.ReduceOp.MAX)
-                if int(active.item()) == 0:
+                n_active = int(active.item())
+                if n_active & (1 << 62):
+                    raise RuntimeError("nsb200: a slice chain did not accept within 65536 proposals: the likelihood is "
+                                       "non-deterministic or NaN at its seed point")
+                if n_active == 0:
                     break
             _lib.check(L.nsb200_engine_split_finish(eng.h, stream))
             if world > 1:
@@ -398,11 +402,14 @@ class ShardedStaticNestedSampler:
         v = _lib.NsStateView()
         _lib.check(_lib.lib().nsb200_engine_state(eng.h, ctypes.byref(v), _lib.stream_arg()))
         cap, D = v.capacity, v.D
+        # The state owns its arrays (device-to-device copies, ~30 us for the 92 MB store of config 2): the engine's
+        # arena is refilled by the next run of the same sampler, and the reference returns immutable arrays -- a state
+        # kept from an earlier run must stay valid (tests/test_gpu_parity.py::test_state_survives_the_next_run).
         sc = SampleCollection(
-            sender_node_idx=_view(v.sender_node_idx, (cap,), "<i8", eng),
-            log_L=_view(v.log_L, (cap,), "<f8", eng),
-            U_samples=_view(v.U_samples, (cap, D), "<f8", eng),
-            num_likelihood_evaluations=_view(v.num_likelihood_evaluations, (cap,), "<i8", eng),
+            sender_node_idx=_view(v.sender_node_idx, (cap,), "<i8", eng).clone(),
+            log_L=_view(v.log_L, (cap,), "<f8", eng).clone(),
+            U_samples=_view(v.U_samples, (cap, D), "<f8", eng).clone(),
+            num_likelihood_evaluations=_view(v.num_likelihood_evaluations, (cap,), "<i8", eng).clone(),
             phantom=_view(v.phantom, (cap,), "|u1", eng).bool(),
         )
         return NestedSamplerState(key=np.array([v.key[0], v.key[1]], dtype=np.uint32),

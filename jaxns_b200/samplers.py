@@ -161,7 +161,11 @@ class UniDimSliceSampler(AbstractSampler):
                                                  _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(prop_U),
                                                  _lib.ptr(prop_X), _lib.ptr(active) if last else ctypes.c_void_p(0),
                                                  st))
-            if int(active.item()) == 0:
+            n_active = int(active.item())
+            if n_active & (1 << 62):
+                raise RuntimeError("nsb200: a slice chain did not accept within 65536 proposals: the likelihood is "
+                                   "non-deterministic or NaN at its seed point")
+            if n_active == 0:
                 break
         _lib.check(L.nsb200_split_finish(ctypes.byref(d), ctypes.byref(p), _lib.ptr(ws), ctypes.c_int64(nbytes),
                                          _lib.ptr(out_U), _lib.ptr(out_logL), _lib.ptr(out_nev),

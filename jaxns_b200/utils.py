@@ -21,7 +21,8 @@ from jaxns_b200.types import NestedSamplerResults
 
 __all__ = ["resample_indicies", "resample", "marginalise_static", "marginalise_dynamic",
            "maximum_a_posteriori_point", "maximum_a_posteriori_point_U", "evaluate_map_estimate", "summary",
-           "sample_evidence", "save_pytree", "save_results", "load_pytree", "load_results"]
+           "sample_evidence", "bruteforce_evidence", "bruteforce_posterior_samples", "save_pytree", "save_results",
+           "load_pytree", "load_results"]
 
 
 def _tree_map(f, tree):
@@ -233,6 +234,33 @@ def _ser_array(a: np.ndarray, kind: str):
             '__shape__': list(a.shape)}
 
 
+def _bruteforce_grid(model, S: int):
+    eps = float(np.finfo(np.float64).eps)
+    u_vec = torch.linspace(eps, 1.0 - eps, S, dtype=torch.float64, device="cuda")
+    du = u_vec[1] - u_vec[0]
+    D = model.U_ndims
+    if S ** D > 2 ** 28:
+        raise ValueError(f"bruteforce grid of {S}^{D} points is too large")
+    args = torch.stack([x.flatten() for x in torch.meshgrid(*([u_vec] * D), indexing='ij')], dim=-1).contiguous()
+    return args, du
+
+
+def bruteforce_posterior_samples(model, S: int = 60):
+    """utils.py:479-496: posterior over a regular grid in U space -> (samples, log weights)."""
+    args, du = _bruteforce_grid(model, S)
+    samples = model.transform(args)
+    log_L = model.forward(args)
+    return samples, log_L + model.U_ndims * torch.log(du)
+
+
+def bruteforce_evidence(model, S: int = 60) -> float:
+    """utils.py:499-516: log of sum_grid L du^D (NaN grid values are skipped, as LogSpace.nansum does)."""
+    args, du = _bruteforce_grid(model, S)
+    log_L = model.forward(args)
+    log_L = log_L[~torch.isnan(log_L)]
+    return float(torch.logsumexp(log_L, dim=0).item() + model.U_ndims * math.log(float(du.item())))
+
+
 def _serialise(obj, field=None):
     if isinstance(obj, tuple) and hasattr(obj, '_asdict') and hasattr(obj, '_fields'):
         name = obj.__class__.__name__
@@ -265,6 +293,10 @@ def _deserialise(obj, device):
         if cls is None:  # a namedtuple of the caller's own module
             module_name = obj['__class__'].rsplit('.', 1)[0]
             cls = getattr(importlib.import_module(module_name), cls_name)
+        # the file names the class to build: only NamedTuple classes are ever constructed (a results file is data,
+        # it must not be able to call arbitrary callables with arguments of its choosing)
+        if not (isinstance(cls, type) and issubclass(cls, tuple) and hasattr(cls, '_fields')):
+            raise ValueError(f"{obj['__class__']} is not a NamedTuple class; refusing to deserialise it")
         return cls(**{k: _deserialise(v, device) for k, v in obj['__data__'].items()})
     if isinstance(obj, dict) and obj.get('type') in ('__ndarray__', '__jax_ndarray__'):
         a = np.frombuffer(base64.b64decode(obj['__data__']), dtype=obj['__dtype__']).reshape(obj['__shape__']).copy()

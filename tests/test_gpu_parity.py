@@ -225,7 +225,7 @@ def test_slice_mma_kernel_parity(torch_cuda, oracle, D, N, S, k, prior):
     exp = oracle.slice_batch(om, random.PRNGKey(13), contour, live_U, live_logL, S, k, True, num_samples=m)
     outs = {}
     try:
-        for impl, P in [(0, 0), (1, 1), (1, 2), (1, 4)]:
+        for impl, P in [(0, 0), (1, 1), (1, 2), (1, 4), (2, 0)]:  # 2 = warp team (17 <= D <= 32, else lane kernel)
             _lib.set_option("NSB200_SLICE_MMA", impl)
             _lib.set_option("NSB200_MMA_P", P)
             sample, phantom = sampler.get_samples_batch(random.PRNGKey(13), contour, state, m)
@@ -241,6 +241,9 @@ def test_slice_mma_kernel_parity(torch_cuda, oracle, D, N, S, k, prior):
         if k:
             np.testing.assert_allclose(phU.cpu().numpy(), exp["ph_U"], rtol=1e-7, atol=1e-9, err_msg=str(key))
             np.testing.assert_allclose(phL.cpu().numpy(), exp["ph_log_L"], rtol=1e-7, atol=1e-7, err_msg=str(key))
+    # the warp team runs the lane kernel's arithmetic with the factor in shared memory: same sums, same bits
+    for a, b in zip(outs[(0, 0)][:3], outs[(2, 0)][:3]):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-9, atol=1e-12)
     # the speculation width of the MMA kernel changes no bit either
     for P in (2, 4):
         for a, b in zip(outs[(1, 1)], outs[(1, P)]):
@@ -753,3 +756,135 @@ def test_resample_and_summary_and_wire_format(torch_cuda, oracle, tmp_path, caps
     # sample_evidence of the run agrees with the analytic evidence statistics
     lz = utils.sample_evidence(random.PRNGKey(1), res.num_live_points_per_sample, res.log_L_samples, S=64)
     assert abs(float(lz.mean()) - res.log_Z_mean) < 4 * res.log_Z_uncert
+
+
+# ---------------------------------------------------------------------------------------------------
+# every field of TerminationCondition decided on the device (determine_termination, termination.py:13-147)
+# ---------------------------------------------------------------------------------------------------
+TERM_FIELDS = ["ess", "evidence_uncert", "dlogZ", "max_samples", "max_num_likelihood_evaluations", "log_L_contour",
+               "efficiency_threshold", "rtol", "atol", "peak_XL_frac"]
+TERM_BIT = dict(max_samples=0, evidence_uncert=1, dlogZ=2, ess=3, max_num_likelihood_evaluations=4, log_L_contour=5,
+                efficiency_threshold=6, rtol=8, atol=9, peak_XL_frac=11)
+
+
+@pytest.mark.parametrize("field", TERM_FIELDS)
+def test_termination_field_on_device_matches_oracle(torch_cuda, oracle, field):
+    """One run per termination field, stopped by that field within the horizon where GPU and oracle trajectories
+    agree value for value: identical reason bits, iteration count and sample bookkeeping.  The threshold is placed
+    between the oracle's register values after 4 and after 5 shells, so the bit has to flip at the right shell."""
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    D, N, S = 2, 100, 10
+    # a broad likelihood (H ~ 1 nat) so that X L peaks, the evidence converges and the live set flattens early
+    model = product_models()["gauss"](D, mu=0.5, rho=0.5)
+    om = to_oracle(model, oracle)
+    key = random.PRNGKey(7)
+    max_samples = N * 40
+
+    def probe(iters):
+        ons = oracle.OracleNestedSampler(om, N, S, 0, True, max_samples=max_samples)
+        ons.run(key, oracle.TermCond(max_samples=float(max_samples)), max_iterations=iters)
+        return ons.register
+
+    r4, r5 = probe(4), probe(5)
+
+    def mid(f):
+        return 0.5 * (f(r4) + f(r5))
+
+    def var_rem(r):
+        return oracle.linear_to_log_stats(r["evidence_calc_with_remaining"][3], r["evidence_calc_with_remaining"][5])[1]
+
+    def dlogz(r):
+        m1 = oracle.linear_to_log_stats(r["evidence_calc_with_remaining"][3], r["evidence_calc_with_remaining"][5])[0]
+        m0 = oracle.linear_to_log_stats(r["evidence_calc"][3], r["evidence_calc"][5])[0]
+        return m1 - m0
+
+    value = dict(
+        ess=lambda: mid(lambda r: oracle.ess_kish(r["evidence_calc_with_remaining"][3], r["evidence_calc_with_remaining"][7])),
+        evidence_uncert=lambda: float(np.sqrt(mid(var_rem))),
+        dlogZ=lambda: mid(dlogz),
+        max_samples=lambda: float(5 * (N // 2)),
+        max_num_likelihood_evaluations=lambda: mid(lambda r: float(r["num_likelihood_evaluations"])),
+        log_L_contour=lambda: mid(lambda r: r["log_L_contour"]),
+        efficiency_threshold=lambda: mid(lambda r: r["efficiency"]),
+        rtol=lambda: mid(lambda r: r["relative_spread"]),
+        atol=lambda: mid(lambda r: r["absolute_spread"]),
+        peak_XL_frac=lambda: 0.9,
+    )[field]()
+    otc = oracle.TermCond(**{field: float(value)})
+    ons = oracle.OracleNestedSampler(om, N, S, 0, True, max_samples=max_samples)
+    oreason, ost = ons.run(key, otc, max_iterations=12)
+    assert ons.iterations < 12, f"{field}={value} did not stop the oracle within the comparison horizon"
+    assert oreason & (1 << TERM_BIT[field]), (field, value, oreason)
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=0, midpoint_shrink=True, perfect=True)
+    ns = j.ShardedStaticNestedSampler(model=model, max_samples=max_samples, init_efficiency_threshold=0.1,
+                                      sampler=sampler, num_live_points=N)
+    reason, register, state = ns._run(key, j.TerminationCondition(**{field: float(value)}))
+    assert reason == oreason, (field, value, reason, oreason)
+    assert ns.last_profile["iterations"] == ons.iterations
+    assert state.num_samples == ost["num_samples"] and state.next_sample_idx == ost["next_sample_idx"]
+    assert register.num_likelihood_evaluations == ons.register["num_likelihood_evaluations"]
+    np.testing.assert_allclose(np.array(register.evidence_calc_with_remaining),
+                               ons.register["evidence_calc_with_remaining"], rtol=1e-8, atol=1e-8)
+
+
+def test_state_survives_the_next_run(torch_cuda):
+    """A NestedSamplerState owns its arrays: running the same sampler again (the engine refills its arena) must not
+    change the state returned by an earlier call (the reference returns immutable arrays)."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    ns = j.NestedSampler(model=product_models()["gauss"](2), num_live_points=100, max_samples=2000)
+    r1, s1 = ns(random.PRNGKey(1))
+    keep = [x.clone() for x in s1.sample_collection]
+    res1 = ns.to_results(r1, s1)
+    r2, s2 = ns(random.PRNGKey(2))
+    for a, b in zip(keep, s1.sample_collection):
+        assert torch.equal(a, b)
+    assert not torch.equal(s1.sample_collection.log_L, s2.sample_collection.log_L)
+    again = ns.to_results(r1, s1)
+    assert again.log_Z_mean == res1.log_Z_mean and again.total_num_samples == res1.total_num_samples
+
+
+def test_same_key_twice_is_bitwise_identical(torch_cuda):
+    """Determinism: no atomics-ordered floating point, no scheduling dependence -- a key selects one run."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    for name, D, N in [("gauss", 32, 256), ("eggbox", 2, 4096), ("rosenbrock", 10, 200)]:
+        outs = []
+        for _ in range(2):
+            ns = j.NestedSampler(model=product_models()[name](D), num_live_points=N, max_samples=N * 8)
+            reason, state = ns(random.PRNGKey(5), j.TerminationCondition(max_samples=float(N * 6)))
+            outs.append((reason, state.num_samples) + tuple(state.sample_collection))
+        assert outs[0][0] == outs[1][0] and outs[0][1] == outs[1][1]
+        for a, b in zip(outs[0][2:], outs[1][2:]):
+            assert torch.equal(a, b), name
+
+
+def test_shrink_loop_watchdog_flags_a_nondeterministic_likelihood(torch_cuda):
+    """A likelihood that is NaN at its own seed can never accept: the reference's while_loop would spin forever
+    (uni_slice_sampler.py:160-196); here the chain stops after 65536 proposals and the error surfaces."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd, random
+    from jaxns_b200.types import LivePointCollection
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(low=np.zeros(2), high=np.ones(2)), name="x")
+        return x
+
+    calls = {"n": 0}
+
+    def flaky(x):  # satisfied at the seed draw, never again
+        calls["n"] += 1
+        return torch.full((x.shape[0],), -1.0e9, dtype=torch.float64, device=x.device)
+
+    model = j.Model(prior_model, flaky)
+    sampler = j.UniDimSliceSampler(model=model, num_slices=2, num_phantom_save=0, midpoint_shrink=True, perfect=True)
+    live_U = torch.rand((8, 2), dtype=torch.float64, device="cuda")
+    live_logL = torch.arange(8, dtype=torch.float64, device="cuda")
+    state = LivePointCollection(None, live_U, None, live_logL, None)
+    with pytest.raises(RuntimeError, match="did not accept"):
+        sampler.get_samples_batch(random.PRNGKey(0), 3.5, state, 4)
+    assert calls["n"] < 70000
