@@ -170,9 +170,21 @@ def run_reference(args, emit=print):
                              "sample": "whole runs, jaxns 2.6.9 on the JAX CPU backend"},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
-    iters = 20
-    for _ in range(args.warmup):
+    # Bounded sample: whole runs to dlogZ when K of them fit ~3 minutes on this host, otherwise the prior draws + the
+    # first `iters` shells of every run (evals/s is flat over a run: the chains do the same work per slice).
+    t0 = time.perf_counter()
+    e_w, t_w, cores = oracle_sample(num_live, 4)
+    rate = e_w / t_w
+    for _ in range(max(0, args.warmup - 1)):
         oracle_sample(num_live, 1)
+    full_evals = 1.32e8 * args.gpus  # evaluations of one whole run of this workload (bench line of the native arm)
+    budget = 180.0
+    if args.steps * full_evals / rate <= budget:
+        iters, sample = None, "whole runs to dlogZ=log(1+1e-3)"
+    else:
+        per_shell = full_evals / 136.0
+        iters = int(max(4, min(136, budget / args.steps * rate / per_shell)))
+        sample = f"prior draws + first {iters} shells of the run per step (whole run: ~136 shells)"
     tot_e, tot_t = 0, 0.0
     for s in range(args.steps):
         e, t, cores = oracle_sample(num_live, iters, seed=s)
@@ -183,10 +195,11 @@ def run_reference(args, emit=print):
         "impl": "reference", "metric": "likelihood_evals_per_sec", "value": value, "unit": "evals/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"32-D correlated Gaussian, num_live_points={num_live}, s=5, k=0 (BASELINE configs[1])",
-                   "sample": f"prior draws + first {iters} shells of the run per step"},
+        "config": {"workload": f"32-D correlated Gaussian (dense cov, rho=0.99, mu=15), num_live_points={num_live}, "
+                               "num_slices=160, k=0, run to dlogZ=log(1+1e-3) (BASELINE configs[1])",
+                   "sample": sample},
         "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": f"init + first {iters} shells per step, {args.steps} steps"},
+                         "sample": f"{sample}, {args.steps} steps"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "oracle port of jaxns 2.6.9 (reference needs jax/tfp: not installable offline)",
     }
@@ -273,6 +286,26 @@ def run_native(args, emit=print):
     tot_ms_max = float(t.item())
     value = tot_evals / (tot_ms_max * 1e-3)
 
+    # ---- strong scaling (N > 1): the headline workload itself (num_live_points = 3200) sharded over the ranks ----
+    strong = None
+    if world > 1:
+        ns_weak = ns
+        ns = j.NestedSampler(model=model, num_live_points=BASE_LIVE)
+        one_run(2000)
+        s_ms, s_evals, s_runs = 0.0, 0, max(1, min(args.steps, 3))
+        barrier()
+        for s_i in range(s_runs):
+            ms, evals, prof, reason, state, loop_evals = one_run(s_i)
+            s_ms += ms
+            s_evals += evals
+        ts = torch.tensor([s_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        strong = {"num_live_points": BASE_LIVE, "runs": s_runs, "time_to_logZ_ms": float(ts.item()) / s_runs,
+                  "evals_per_sec": s_evals / (float(ts.item()) * 1e-3),
+                  "note": "fixed total work (BASELINE configs[1]) sharded over the ranks: 1600 / n_gpus chains per GPU and body"}
+        del state, reason
+        ns = ns_weak
+
     # ---- e2e through the public API with host buffers --------------------------------------------
     e2e_t, e2e_evals, h2d, d2h = 0.0, 0, 0, 0
     n_e2e = max(1, min(args.steps, 3))
@@ -340,7 +373,10 @@ def run_native(args, emit=print):
         except Exception:
             pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
-                    "frac": achieved / tf.value if tf.value else None, "traffic": None,
+                    "frac": achieved / tf.value if tf.value else None,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r2/): the
+                    # pre-generated chain streams (directions, uniforms, keys), read once; algorithmic bytes ~0.4 MB
+                    "traffic": 86.8e6,
                     "kernel": "k_slice_chains<32,1,P> (fused slice chains)",
                     "kernel_share_of_step": slice_ms / tot_ms,
                     "peak_source": "FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
@@ -363,7 +399,7 @@ def run_native(args, emit=print):
                                    "num_slices=160, k=0, run to dlogZ=log(1+1e-3) (BASELINE configs[1])",
                        "l2": "256 MB buffer written between timed runs (L2 flush)",
                        "iterations_per_step": iters / args.steps, "evals_per_step": tot_evals / args.steps,
-                       "time_to_logZ_ms": tot_ms_max / args.steps,
+                       "time_to_logZ_ms": tot_ms_max / args.steps, "strong_scaling": strong,
                        "logZ": [{"mean": m, "uncert": u, "analytic": ANALYTIC_LOGZ} for m, u in logZ]},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

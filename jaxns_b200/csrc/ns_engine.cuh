@@ -16,9 +16,7 @@ namespace nsb {
 struct EpiScratch {
     double gpart[144];  // CTA aggregates of the three cluster scans
     NsEvidenceCalc mid, fin;
-    unsigned long long sum_new, sum_live;
     int not_plateau;
-    unsigned bar;  // arrival counter of the register update's software grid barrier (zeroed by the prologue)
 };
 
 __device__ __forceinline__ long long clampll(long long v, long long lo, long long hi) {
@@ -31,12 +29,25 @@ __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSe
                                 long long m, long long kph, long long capacity, int intended_sender,
                                 EpiScratch *epi) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    ctl->active = reg->done ? 0 : 1;
+    (void) reg;
+    (void) epi;
+    // The loop condition this body runs under is the register of the body BEFORE the previous one (the host makes
+    // this kernel wait for that update; done_iter = 0: the condition was already false at loop entry).  The previous
+    // body's update may or may not have finished by now -- it is ignored on purpose, so that the decision does not
+    // depend on timing: every rank of a multi-GPU run must take it identically (their chains meet at a barrier).
+    {
+        const long long dm = *(volatile long long *) &ctl->done_iter;
+        const long long it = ctl->iteration + 1;
+        ctl->active = (dm >= 0 && (dm == 0 || dm <= it - 2)) ? 0 : 1;
+    }
     if (!ctl->active) return;
-    epi->sum_new = 0;
-    epi->sum_live = 0;
-    epi->not_plateau = 0;
-    epi->bar = 0;
+    {
+        EpiJob &job = ctl->job[(ctl->iteration + 1) & 1];  // this body's slot (its previous user has been waited for)
+        job.sum_new = 0;
+        job.sum_live = 0;
+        job.bar = 0;
+        job.armed = 0;
+    }
     const LiveSet &live = ctl->cur ? live1 : live0;
     Key k = split_child(ctl->key, 0);      // :491  key, ephemeral_key = split(state.key)
     ctl->sample_key = split_child(k, 1);   // :248  key, sample_key = split(state.key)
@@ -243,13 +254,14 @@ __global__ void __launch_bounds__(256) k_merge_rank_tiles(const DevCtl *ctl, con
 
 // Scatter rows into the other live buffer at their rank; phantom rows go to the dead store
 // (add_phantom_samples_to_state, sharded_static.py:181-207).
-__global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const LiveSet live1, const double *packed,
+__global__ void k_merge_scatter(DevCtl *ctl, const LiveSet live0, const LiveSet live1, const double *packed,
                                 long long row_doubles, int D, long long m, long long N, int kph,
-                                const unsigned *rank, DeadStore dead) {
+                                const unsigned *rank, DeadStore dead, int count_evals) {
     if (!ctl->active) return;
     const LiveSet &src = ctl->cur ? live1 : live0;
     const LiveSet &dst = ctl->cur ? live0 : live1;
     const long long total = N * D;
+    long long sum_new = 0, sum_live = 0;  // n_evals of the new rows / of the merged live set (:301-304)
     for (long long t = (long long) blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (long long) gridDim.x * blockDim.x) {
         const long long e = t / D;
@@ -258,17 +270,34 @@ __global__ void k_merge_scatter(const DevCtl *ctl, const LiveSet live0, const Li
         const bool is_new = e < m;
         dst.U[r * D + j] = is_new ? packed[e * row_doubles + j] : src.U[e * D + j];
         if (j == 0) {
+            long long nev;
             if (is_new) {
+                nev = __double_as_longlong(packed[e * row_doubles + D + 1]);
                 dst.sender[r] = ctl->sender;
                 dst.logL[r] = packed[e * row_doubles + D];
                 dst.logL_constraint[r] = ctl->contour;
-                dst.nevals[r] = __double_as_longlong(packed[e * row_doubles + D + 1]);
+                dst.nevals[r] = nev;
+                sum_new += nev;
             } else {
+                nev = src.nevals[e];
                 dst.sender[r] = src.sender[e];
                 dst.logL[r] = src.logL[e];
                 dst.logL_constraint[r] = src.logL_constraint[e];
-                dst.nevals[r] = src.nevals[e];
+                dst.nevals[r] = nev;
             }
+            sum_live += nev;
+        }
+    }
+    if (count_evals) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum_new += __shfl_xor_sync(0xFFFFFFFFu, sum_new, o);
+            sum_live += __shfl_xor_sync(0xFFFFFFFFu, sum_live, o);
+        }
+        if ((threadIdx.x & 31) == 0 && sum_live != 0) {
+            EpiJob &job = ctl->job[ctl->iteration & 1];
+            if (sum_new) atomicAdd(&job.sum_new, (unsigned long long) sum_new);
+            atomicAdd(&job.sum_live, (unsigned long long) sum_live);
         }
     }
     if (kph > 0) {
@@ -346,7 +375,8 @@ __global__ void k_peer_barrier(DevCtl *ctl, unsigned long long *epoch_dev, volat
 // linear_to_log_stats (stats.py:55-74)
 __device__ __forceinline__ void linear_to_log_stats(double log_f_mean, double log_f2_mean, double &mu, double &var) {
     mu = 2.0 * log_f_mean - 0.5 * log_f2_mean;
-    var = fmax(log_f2_mean - 2.0 * log_f_mean, 2.220446049250313e-16);
+    const double d = log_f2_mean - 2.0 * log_f_mean;
+    var = (d != d) ? d : fmax(d, 2.220446049250313e-16);  // jnp.maximum propagates NaN (-inf - -inf before any evidence), fmax would not
 }
 
 // determine_termination (termination.py:13-147)
@@ -402,7 +432,6 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
                                                    const double *tabT, const double *tabT2, const double *tabt,
                                                    long long tab_n, EpiScratch *epi, volatile long long *progress) {
     __shared__ double sh[3][34];
-    if (!init_only && !ctl->active) return;
     const long long gtid = (long long) grp.rank() * blockDim.x + threadIdx.x;
     const long long nthreads = (long long) blockDim.x * grp.nranks();
     if (init_only) {
@@ -411,6 +440,7 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
             const LiveSet &live = ctl->cur ? live1 : live0;
             reg->no_seed_points = live.logL[m - 1] >= live.logL[N - 1];
             determine_termination(tc, *reg);
+            if (reg->done) ctl->done_iter = 0;
             if (progress) {
                 progress[1] = reg->done;
                 __threadfence_system();
@@ -420,8 +450,19 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
         }
         return;
     }
-    const LiveSet &old = ctl->cur ? live1 : live0;
-    const LiveSet &cur = ctl->cur ? live0 : live1;
+    // the job armed by this body's k_iter_advance (at most one is armed: the host orders the next advance after
+    // this kernel); none = the body was a no-op
+    const int slot = ctl->job[0].armed ? 0 : (ctl->job[1].armed ? 1 : -1);
+    if (slot < 0) return;
+    EpiJob &job = ctl->job[slot];
+    if (*(volatile long long *) &ctl->done_iter >= 0) {
+        // the loop had already ended when this body started (it ran speculatively and will be rolled back); every CTA
+        // takes this exit (done_iter was written by an earlier kernel), so no barrier is involved
+        if (gtid == 0) job.armed = 0;
+        return;
+    }
+    const LiveSet &old = job.old_cur ? live1 : live0;
+    const LiveSet &cur = job.old_cur ? live0 : live1;
     EvSeq q;
     q.la = old.logL;
     q.na = nullptr;
@@ -441,50 +482,32 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
     out.per_sample = nullptr;
     if (m + N <= 8 * nthreads) evidence_scan_block<8>(q, reg->evidence_calc, out, sh, epi->gpart, grp);
     else evidence_scan_block<0>(q, reg->evidence_calc, out, sh, epi->gpart, grp);
-    // sums of likelihood evaluations, plateau flag
-    long long sum_new = 0, sum_live = 0;
-    int not_plateau = 0;
-    const double l0 = cur.logL[0];
-    for (long long i = gtid; i < N; i += nthreads) {
-        sum_live += cur.nevals[i];
-        not_plateau |= !(cur.logL[i] == l0);
-        if (i < m) sum_new += __double_as_longlong(packed[i * row_doubles + D + 1]);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum_new += __shfl_xor_sync(0xFFFFFFFFu, sum_new, o);
-        sum_live += __shfl_xor_sync(0xFFFFFFFFu, sum_live, o);
-        not_plateau |= __shfl_xor_sync(0xFFFFFFFFu, not_plateau, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&epi->sum_new, (unsigned long long) sum_new);
-        atomicAdd(&epi->sum_live, (unsigned long long) sum_live);
-        if (not_plateau) atomicOr(&epi->not_plateau, 1);
-    }
     __threadfence();
     grp.sync();
     if (gtid == 0) {
         NsRegister r = *reg;
         const NsEvidenceCalc s_mid = epi->mid;
         const NsEvidenceCalc s_fin = epi->fin;
-        r.num_samples_used = ctl->num_samples;
+        r.num_samples_used = job.num_samples;
         r.evidence_calc = s_mid;
         r.evidence_calc_with_remaining = s_fin;
-        r.num_likelihood_evaluations += (long long) *(volatile unsigned long long *) &epi->sum_new;
-        r.log_L_contour = ctl->contour;
-        r.efficiency = (double) N / (double) (long long) *(volatile unsigned long long *) &epi->sum_live;
-        r.plateau = (*(volatile int *) &epi->not_plateau) ? 0 : 1;
+        r.num_likelihood_evaluations += (long long) *(volatile unsigned long long *) &job.sum_new;  // :301-302
+        r.log_L_contour = job.contour;
+        r.efficiency = (double) N / (double) (long long) *(volatile unsigned long long *) &job.sum_live;  // :304
         const double lo = cur.logL[0], hi = cur.logL[N - 1];
+        r.plateau = (lo == hi) ? 1 : 0;  // :306 all(log_L == log_L[0]) on a sorted live set
         r.absolute_spread = fabs(hi - lo);
         r.relative_spread = 2.0 * r.absolute_spread / fabs(lo + hi);
         r.no_seed_points = cur.logL[m - 1] >= hi;
         r.peak_log_XL = fmax(r.peak_log_XL, s_mid.log_X_mean + s_mid.log_L);
-        r.iteration = ctl->iteration;
+        r.iteration = job.iteration;
         r.error_flags = *(volatile int *) &ctl->err;
         determine_termination(tc, r);
         if (r.error_flags) r.done = 1;  // a flagged run stops at once (the host turns the flags into an error)
         *reg = r;
-        ctl->cur ^= 1;
+        job.armed = 0;
+        __threadfence();
+        if (r.done) *(volatile long long *) &ctl->done_iter = r.iteration;
         if (progress) {
             // host-mapped pinned words: the host keeps a few bodies in flight and polls these instead of
             // synchronising the stream (progress[0] = bodies completed, progress[1] = done flag)
@@ -492,6 +515,67 @@ __device__ __forceinline__ void iter_epilogue_body(Sync &grp, DevCtl *ctl, NsReg
             __threadfence_system();
             progress[0] = r.iteration;
             __threadfence_system();
+        }
+    }
+}
+
+// End of a body on the main stream: freezes what the register update needs (it runs on its own stream while the
+// next body starts), flips the live buffers and records the state a rollback would return to.
+__global__ void k_iter_advance(DevCtl *ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!ctl->active) return;
+    const int slot = (int) (ctl->iteration & 1);
+    EpiJob &job = ctl->job[slot];
+    job.num_samples = ctl->num_samples;
+    job.iteration = ctl->iteration;
+    job.contour = ctl->contour;
+    job.old_cur = ctl->cur;
+    ctl->cur ^= 1;
+    CtlSnap &sn = ctl->snap[slot];
+    sn.key = ctl->key;
+    sn.next_idx = ctl->next_idx;
+    sn.num_samples = ctl->num_samples;
+    sn.iteration = ctl->iteration;
+    sn.cur = ctl->cur;
+    __threadfence();
+    job.armed = 1;
+}
+
+// Discards the speculative body, if one ran (DevCtl::done_iter): the control block returns to the state after the
+// body whose register ended the loop; k_blank_rows then resets the dead-store rows the speculative body appended.
+__global__ void k_rollback(DevCtl *ctl, long long m, long long kph) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->spec_ran = 0;
+    if (ctl->done_iter < 0 || ctl->iteration <= ctl->done_iter) return;
+    ctl->spec_ran = 1;
+    ctl->spec_disc_start = ctl->disc_start;
+    ctl->spec_ph_start = kph > 0 ? ctl->ph_start : -1;
+    (void) m;
+    const CtlSnap &sn = ctl->snap[ctl->done_iter & 1];
+    ctl->key = sn.key;
+    ctl->next_idx = sn.next_idx;
+    ctl->num_samples = sn.num_samples;
+    ctl->iteration = sn.iteration;
+    ctl->cur = sn.cur;
+}
+
+// create_init_state's empty rows (common/initialisation.py:38-45): sender 0, log L +inf, U 0, n_evals 0, not phantom
+__global__ void k_blank_rows(const DevCtl *ctl, DeadStore dead, long long m, long long kph, int D) {
+    if (!ctl->spec_ran) return;
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+    for (int part = 0; part < 2; ++part) {
+        const long long start = part == 0 ? ctl->spec_disc_start : ctl->spec_ph_start;
+        const long long count = part == 0 ? m : m * kph;
+        if (start < 0 || count <= 0) continue;
+        for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < count * D;
+             e += (long long) gridDim.x * blockDim.x) {
+            dead.U[start * D + e] = 0.0;
+            if (e < count) {
+                dead.sender[start + e] = 0;
+                dead.logL[start + e] = kInf;
+                dead.nevals[start + e] = 0;
+                dead.phantom[start + e] = 0;
+            }
         }
     }
 }
@@ -513,7 +597,7 @@ k_iter_epilogue_grid(DevCtl *ctl, NsRegister *reg, const LiveSet live0, const Li
                      long long row_doubles, int D, long long m, long long N, NsTermCond tc, int init_only,
                      const double *tabT, const double *tabT2, const double *tabt, long long tab_n, EpiScratch *epi,
                      volatile long long *progress) {
-    GridSync grp{&epi->bar, 0u};
+    GridSync grp{&ctl->job[ctl->job[0].armed ? 0 : 1].bar, 0u};
     iter_epilogue_body(grp, ctl, reg, live0, live1, packed, row_doubles, D, m, N, tc, init_only, tabT, tabT2, tabt, tab_n,
                        epi, progress);
 }

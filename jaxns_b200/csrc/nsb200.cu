@@ -55,7 +55,7 @@ extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
 // it at run time (tests A/B kernels inside one process).  None of them changes results.
 enum {
     OPT_SPEC, OPT_TPB, OPT_SLICE_MMA, OPT_MMA_P, OPT_MMA_WPB, OPT_MERGE_BRUTE, OPT_GEN_MODE, OPT_GEN_SMS, OPT_GEN_TPB,
-    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_COUNT
+    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_GEN_FENCE, OPT_COUNT
 };
 struct NsOption {
     const char *name;
@@ -64,10 +64,11 @@ struct NsOption {
     bool loaded;
 };
 static NsOption g_opts[OPT_COUNT] = {
-    {"NSB200_SPEC", 0, 0, false},        {"NSB200_TPB", 0, 0, false},         {"NSB200_SLICE_MMA", 8, 0, false},
+    {"NSB200_SPEC", 0, 0, false},        {"NSB200_TPB", 0, 0, false},         {"NSB200_SLICE_MMA", 0, 0, false},
     {"NSB200_MMA_P", 0, 0, false},       {"NSB200_MMA_WPB", 4, 0, false},     {"NSB200_MERGE_BRUTE", 0, 0, false},
     {"NSB200_GEN_MODE", 3, 0, false},    {"NSB200_GEN_SMS", 0, 0, false},     {"NSB200_GEN_TPB", 0, 0, false},
     {"NSB200_EPI_CLUSTER", 0, 0, false}, {"NSB200_DEPTH", 4, 0, false},       {"NSB200_TRACE", 0, 0, false},
+    {"NSB200_GEN_FENCE", 0, 0, false},
 };
 static int opt(int id) {
     NsOption &o = g_opts[id];
@@ -416,15 +417,16 @@ static int launch_slice_t(const SliceArgs &a, const Geometry &g, cudaStream_t st
 }
 
 // ---- FP64 tensor-core slice kernel (ns_slice_mma.cuh): dense Gaussian, D <= 32, pre-generated streams ----------
-// Which slice kernel runs the dense Gaussian family with D <= 32 (NSB200_SLICE_MMA): 0 = lane-per-dimension kernel,
-// 1 = DMMA kernel, 2 / 4 = warp teams, 8 (default) = by size.  The DMMA kernel is a THROUGHPUT design: a warp
-// carries 8 proposal columns and issues ~1150 instructions per round with little instruction-level parallelism in
-// its bookkeeping, so a round takes ~5400 cycles against ~2400 for the lane kernel's one-chain warp
-// (profiles/r2/mma_cycles_r2.txt).  A nested-sampling launch is S sequential slices per chain: with 1600 chains
-// (config 2: 400 DMMA warps on 592 sub-partitions) the launch time is rounds x round latency and the lane kernel
-// wins 0.55 ms to 0.77 ms; once the chains fill the machine several times over (>= 8192 per GPU) the DMMA
-// kernel's lower instruction count per evaluation wins (profiles/r2/slice_crossover_r2.txt).
-constexpr long long kSliceMmaMinChains = 8192;
+// Which slice kernel runs the dense Gaussian family with D <= 32 (NSB200_SLICE_MMA): 0 (default) = lane-per-dimension
+// kernel, 1 = DMMA kernel, 2 / 4 = warp teams, 8 = DMMA from kSliceMmaMinChains chains per GPU.  The DMMA kernel is a
+// THROUGHPUT design: a warp carries 8 proposal columns and issues ~1150 instructions per round with little
+// instruction-level parallelism in its bookkeeping, so a round takes ~5400 cycles against ~2400 for the lane
+// kernel's one-chain warp (profiles/r2/mma_cycles_r2.txt).  A nested-sampling launch is S sequential slices per
+// chain, so with few chains the launch time is rounds x round latency (config 2: 0.55 ms lane, 0.77 ms DMMA); with
+// many chains the lane kernel's 2.7x more warps hide the same latencies, and the two meet only at 25600 chains per
+// GPU (8.07 vs 8.18 ms, profiles/r2/slice_crossover_r2.txt).  Measured, not assumed: the lane kernel is the default
+// at every size, the DMMA kernel stays selectable and parity-tested.
+constexpr long long kSliceMmaMinChains = 32768;
 
 static bool slice_mma_eligible(const SliceArgs &a) {
     const int mode = opt(OPT_SLICE_MMA);
@@ -993,6 +995,10 @@ __global__ void k_init_ctl(DevCtl *ctl, Key key) {
     ctl->sender = 0;
     ctl->active = 1;
     ctl->err = 0;
+    ctl->done_iter = -1;
+    ctl->spec_ran = 0;
+    ctl->spec_disc_start = ctl->spec_ph_start = -1;
+    ctl->job[0].armed = ctl->job[1].armed = 0;
     ctl->cur = 1;  // the init scatter writes live0 ("other" buffer of cur = 1)
 }
 
@@ -1053,6 +1059,10 @@ struct NsEngine {
     EpiScratch *epi = nullptr;
     double *alpha_tab = nullptr;
     cudaStream_t side = nullptr;
+    // register update of body b on its own stream, next to the slice kernel of body b + 1 (DevCtl::done_iter)
+    cudaStream_t epi_stream = nullptr;
+    cudaEvent_t ev_adv = nullptr, ev_epi[2] = {nullptr, nullptr};
+    int slot = 0;  // parity of the body between step_begin and step_end
     cudaEvent_t ev_keys = nullptr, ev_streams[3] = {nullptr, nullptr, nullptr};
     long long body = 0;       // host mirror of the next body index (its streams live in buffer body % 3)
     NsTermCond tc;
@@ -1207,6 +1217,10 @@ extern "C" void nsb200_engine_destroy(NsEngine *e) {
     for (int b = 0; b < 3; ++b)
         if (e->ev_streams[b]) cudaEventDestroy(e->ev_streams[b]);
     if (e->side) cudaStreamDestroy(e->side);
+    if (e->ev_adv) cudaEventDestroy(e->ev_adv);
+    for (int b = 0; b < 2; ++b)
+        if (e->ev_epi[b]) cudaEventDestroy(e->ev_epi[b]);
+    if (e->epi_stream) cudaStreamDestroy(e->epi_stream);
     delete e;
 }
 
@@ -1294,6 +1308,10 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         for (int b = 0; b < 3; ++b)
             if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     }
+    if (!rc && cudaStreamCreateWithFlags(&e->epi_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate failed");
+    if (!rc && cudaEventCreateWithFlags(&e->ev_adv, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
+    for (int b = 0; b < 2; ++b)
+        if (!rc && cudaEventCreateWithFlags(&e->ev_epi[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     if (!rc) rc |= arena_commit(e);
     if (!rc) e->packed_home = e->packed;
     if (!rc && e->p2p_flags) {
@@ -1448,6 +1466,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     e->ev_used = 0;
     e->packed = e->packed_home;
     e->body = 0;
+    NSB_CUDA(cudaStreamSynchronize(e->epi_stream));  // register updates of a previous run on this engine
     if (e->p2p) {  // run-entry barrier: peers may only store rows of this run once every rank has left the previous one
         PeerFlags pf;
         for (int r = 0; r < 8; ++r) pf.p[r] = e->peer_flags[r];
@@ -1492,7 +1511,7 @@ static int engine_init_common(NsEngine *e, const uint32_t key[2], const NsTermCo
     launch_merge_rank(e, e->N, st);
     DeadStore nodead = e->dead;
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->N, e->N, 0,
-                                          e->rank, nodead);
+                                          e->rank, nodead, 0);
     k_set_cur<<<1, 1, 0, st>>>(e->ctl, 0);
     // create_init_termination_register + the loop-entry no_seed_points and first cond
     *e->reg_host = init_register_host();
@@ -1633,6 +1652,15 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     const bool own_stream = e->gen_mode == 0 || e->gen_mode >= 3;
     if (e->pre_dirs[0] && own_stream) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[e->body % 3], 0));
     trace_mark(e, "after wait streams", st);
+    // the loop condition this body starts under is the register of the body before the previous one (same slot):
+    // the previous body's register update may still be running next to this body's chains (DevCtl::done_iter)
+    e->slot = (int) (e->body & 1);
+    NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot], 0));
+    // NSB200_GEN_FENCE=1: the generator launched behind the previous slice kernel (streams of body + 1) gets the GPU to
+    // itself before this body's chains start.  Measured slower (105 vs 93 ms per config-2 run): with the register
+    // update off the main stream the chains of body b + 1 simply start under the generator's tail.
+    if (e->pre_dirs[0] && e->gen_mode == 3 && opt(OPT_GEN_FENCE) && e->body >= 1)
+        NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[(e->body + 1) % 3], 0));
     k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
@@ -1718,24 +1746,31 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
         e->all_launches += 1;
         trace_mark(e, "peer barrier end", st);
     }
+    // the merge overwrites the live buffer whose first m rows the previous body's register update reads
+    NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot ^ 1], 0));
     launch_merge_rank(e, e->m, st);
     trace_mark(e, "merge_rank end", st);
     k_merge_scatter<<<592, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->packed, e->row_doubles, D, e->m, e->N,
-                                          (int) e->k, e->rank, e->dead);
+                                          (int) e->k, e->rank, e->dead, 1);
     trace_mark(e, "merge_scatter end", st);
-    // grid form: 8 CTAs on ANY free SMs (a cluster has to wait until the generator has drained one GPC)
+    k_iter_advance<<<1, 1, 0, st>>>(e->ctl);
+    NSB_CUDA(cudaEventRecord(e->ev_adv, st));
+    // register update + loop condition on their own stream: the next body's chains start right away.  Grid form:
+    // 8 CTAs on ANY free SMs (a cluster would wait until one GPC has 8 free SMs)
+    NSB_CUDA(cudaStreamWaitEvent(e->epi_stream, e->ev_adv, 0));
     if (opt(OPT_EPI_CLUSTER))
-        k_iter_epilogue<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles, D,
-                                                           e->m, e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N, e->epi,
-                                                           e->progress_dev);
+        k_iter_epilogue<<<kEvCluster, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
+                                                                      e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
+                                                                      e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     else
-        k_iter_epilogue_grid<<<kEvCluster, kEvThreads, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed, e->row_doubles,
-                                                                D, e->m, e->N, e->tc, 0, e->tabT, e->tabT2, e->tabt, e->N,
-                                                                e->epi, e->progress_dev);
+        k_iter_epilogue_grid<<<kEvCluster, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
+                                                                           e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
+                                                                           e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
+    NSB_CUDA(cudaEventRecord(e->ev_epi[e->slot], e->epi_stream));
     NSB_LAUNCH_CHECK();
     trace_mark(e, "epilogue end", st);
     if (e->slice_launches == 64) trace_dump();
-    e->all_launches += 3;
+    e->all_launches += 4;
     return 0;
 }
 
@@ -1815,6 +1850,8 @@ extern "C" int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *r
 extern "C" int nsb200_engine_register(NsEngine *e, NsRegister *out, nsb200_stream_t stream) {
     if (!e || !out) return fail("NULL argument");
     cudaStream_t st = (cudaStream_t) stream;
+    NSB_CUDA(cudaStreamSynchronize(st));
+    NSB_CUDA(cudaStreamSynchronize(e->epi_stream));  // the register update of the last body runs there
     NSB_CUDA(cudaMemcpyAsync(e->reg_host, e->reg, sizeof(NsRegister), cudaMemcpyDeviceToHost, st));
     NSB_CUDA(cudaStreamSynchronize(st));
     drain_events(e);
@@ -1834,10 +1871,15 @@ extern "C" int nsb200_engine_progress(NsEngine *e, int64_t *completed, int32_t *
 extern "C" int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream) {
     if (!e || !e->initialised) return fail("engine not initialised");
     cudaStream_t st = (cudaStream_t) stream;
+    NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[0], 0));
+    NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[1], 0));
+    // a body that started before the register of its predecessor said "done" is discarded (DevCtl::done_iter)
+    k_rollback<<<1, 1, 0, st>>>(e->ctl, e->m, e->k);
+    k_blank_rows<<<148, 256, 0, st>>>(e->ctl, e->dead, e->m, e->k, e->D);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->N, e->D, 1);
     k_finalize_ctl<<<1, 1, 0, st>>>(e->ctl, e->N, e->cap);
     NSB_LAUNCH_CHECK();
-    e->all_launches += 2;
+    e->all_launches += 4;
     return 0;
 }
 
@@ -1893,6 +1935,7 @@ extern "C" int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTer
 extern "C" int nsb200_engine_state(NsEngine *e, NsStateView *out, nsb200_stream_t stream) {
     if (!e || !out) return fail("NULL argument");
     cudaStream_t st = (cudaStream_t) stream;
+    NSB_CUDA(cudaStreamSynchronize(e->epi_stream));
     NSB_CUDA(cudaMemcpyAsync(e->ctl_host, e->ctl, sizeof(DevCtl), cudaMemcpyDeviceToHost, st));
     NSB_CUDA(cudaStreamSynchronize(st));
     drain_events(e);

@@ -265,13 +265,14 @@ class ShardedStaticNestedSampler:
     def _connect_peers(self, eng, world) -> bool:
         """Wire the engines of all ranks together for the fused all-gather (include/nsb200.h, nsb200_engine_p2p_*):
         CUDA IPC handles of the engine arenas are exchanged once per engine through the process group; every rank
-        must succeed, otherwise all of them keep the host-issued NCCL all-gather.  Opt-in (NSB200_P2P=1) in this
-        round: results are identical, but the wiring costs ~15 ms per new engine."""
+        must succeed, otherwise all of them keep the host-issued NCCL all-gather (NSB200_P2P=0 forces that path).
+        Peer mappings and exported arenas are cached per process by the library (csrc/nsb200.cu open_peer_arena),
+        so a sampler rebuilt for every run re-wires in ~1 ms instead of ~15 ms."""
         if getattr(self, "_p2p_state", None) is not None:
             return self._p2p_state
         import torch.distributed as dist
         L = _lib.lib()
-        if os.environ.get("NSB200_P2P", "0") != "1" or world > 8 or dist.get_backend() != "nccl":
+        if os.environ.get("NSB200_P2P", "1") != "1" or world > 8 or dist.get_backend() != "nccl":
             self._p2p_state = False  # same decision on every rank (launcher environment), no communication needed
             return False
         ok = True
