@@ -464,7 +464,13 @@ static void slice_bounds_(const double *U0, const double *d, int D, double *left
 
 /* jnp.linspace(0.5, 1., S)[j] (jax/_src/numpy/lax_numpy.py _linspace): start*(1-step)+stop*step
  * with step = j/div, endpoint appended exactly. */
+/* Test knob (tests/test_oracle_cpu.py::test_notebook_runs_*): a constant shrink factor instead of the 2.6.9
+ * schedule -- the plain midpoint rule of the jaxns versions the example notebooks were run with.  < 0 = off. */
+static double g_fixed_alpha = -1.0;
+void o_set_fixed_alpha(double a) { g_fixed_alpha = a; }
+
 static double alpha_(int j, int S) {
+    if (g_fixed_alpha >= 0.0) return g_fixed_alpha;
     if (S == 1) return 0.5;
     int div = S - 1;
     if (j == div) return 1.0;

@@ -619,3 +619,8 @@ def num_threads() -> int:
 
 def set_num_threads(n: int):
     lib().o_set_num_threads(ctypes.c_int(int(n)))
+
+
+def set_fixed_alpha(a: float):
+    """Test knob: constant midpoint-shrink factor instead of linspace(0.5, 1, S) (a < 0 restores the schedule)."""
+    lib().o_set_fixed_alpha(ctypes.c_double(float(a)))

@@ -379,3 +379,63 @@ def test_golden_fixture_whole_run(oracle):
         np.testing.assert_allclose(r[name], g[name], rtol=1e-9)
     assert r["total_num_likelihood_evaluations"] == g["total_num_likelihood_evaluations"]
     assert r["total_phantom_samples"] == g["total_phantom_samples"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# The only whole-run outputs the reference holds: the example notebooks (PRNGKey(42), outputs stored in the .ipynb)
+# ---------------------------------------------------------------------------------------------------
+def _notebook_run(oracle, model_name, N, S, midpoint, seeds):
+    from tests.models import product_models, to_oracle
+    model = product_models()[model_name](2)
+    om = to_oracle(model, oracle)
+    out = []
+    for seed in seeds:
+        ons = oracle.OracleNestedSampler(om, N, S, 0, midpoint, max_samples=100000)
+        reason, st = ons.run(oracle.PRNGKey(seed))
+        res = ons.to_results(reason, st)
+        out.append((reason, res["total_num_samples"], res["total_num_likelihood_evaluations"], res["log_Z_mean"],
+                    res["log_Z_uncert"]))
+    return out
+
+
+def test_notebook_run_egg_box(oracle):
+    """/root/reference/docs/examples/egg_box.ipynb cells 4-5: NestedSampler(model, max_samples=1e5,
+    difficult_model=True) with PRNGKey(42) -> c = 200, s = 10 (20 slices), plain shrink; stored output: 2700 samples,
+    441896 likelihood evaluations, logZ = 236.02 +- 0.21 (bruteforce 236.048), "Small remaining evidence"."""
+    runs = _notebook_run(oracle, "eggbox", 200, 20, False, [42, 43, 44, 45, 46, 47])
+    evals = np.array([r[2] for r in runs], float)
+    for reason, nsamp, _, logZ, sig in runs:
+        assert reason == 4  # dlogZ
+        assert nsamp == 2700  # sample count of the stored run, exactly
+        assert abs(logZ - 236.0483738381629) < 3.5 * sig
+        assert abs(sig - 0.21) < 0.03
+    # plain shrink has no version-dependent knob: the stored eval count sits inside the oracle's seed scatter
+    assert abs(441896 - evals.mean()) < 3.0 * max(evals.std(ddof=1), 15000.0)
+
+
+def test_notebook_run_gaussian_shells_and_the_midpoint_rule(oracle):
+    """/root/reference/docs/examples/gaussian_shells.ipynb cells 4-5: NestedSampler(model, max_samples=1e5, k=0, s=5,
+    c=200), PRNGKey(42); stored output: 2100 samples, 182018 evaluations, logZ = -1.66 +- 0.14 (bruteforce -1.7456).
+    Sample count and log Z are reproduced by the oracle of jaxns 2.6.9.  The stored evaluation count is not: with the
+    2.6.9 shrink schedule alpha_j = linspace(0.5, 1, S)[j] (uni_slice_sampler.py:102-110,422) the oracle needs
+    204e3 +- 4e3 evaluations (182018 is 6 sigma below), with the plain midpoint rule alpha = 0.5 it needs
+    173e3 +- 5e3 and 182018 is inside the seed range.  The notebook output predates the schedule (its stored warning
+    "Found samples with zero likelihood evaluations" comes from an older plotting / evaluation-count layout as well),
+    so the gap is a version difference of the midpoint path, not a discrepancy of the restatement: the egg-box
+    notebook, which runs WITHOUT midpoint shrink, agrees on evaluations too (test above)."""
+    seeds = [42, 43, 44, 45, 46, 47, 48, 49]
+    sched = _notebook_run(oracle, "shells", 200, 10, True, seeds)
+    oracle.set_fixed_alpha(0.5)
+    try:
+        mid = _notebook_run(oracle, "shells", 200, 10, True, seeds)
+    finally:
+        oracle.set_fixed_alpha(-1.0)
+    for runs in (sched, mid):
+        for reason, nsamp, _, logZ, sig in runs:
+            assert reason == 4 and nsamp == 2100
+            assert abs(logZ - (-1.7456418720467646)) < 3.5 * sig
+            assert abs(sig - 0.14) < 0.03
+    e_sched = np.array([r[2] for r in sched], float)
+    e_mid = np.array([r[2] for r in mid], float)
+    assert (182018 - e_sched.mean()) < -4.0 * e_sched.std(ddof=1)  # far below the 2.6.9 schedule's cost
+    assert e_mid.min() - 2 * e_mid.std(ddof=1) < 182018 < e_mid.max() + 2 * e_mid.std(ddof=1)  # inside the midpoint rule's
