@@ -172,6 +172,10 @@ const char *nsb200_last_error(void);
  * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_GEN_FENCE, NSB200_EPI_CLUSTER, NSB200_DEPTH, NSB200_TRACE. */
 int nsb200_set_option(const char *name, int32_t value);
 
+/* Copies the two words of a PRNG key from DEVICE memory (where XLA keeps keys) to the host; synchronises `stream`.
+ * For bindings that receive keys as device operands (csrc/xla_ffi_shim.cc): the entry points take keys by value. */
+int nsb200_read_key(const uint32_t *device_key, uint32_t out[2], nsb200_stream_t stream);
+
 /* ---- jax.random under jax_threefry_partitionable=True (internals/mixed_precision.py:11-15) --- */
 /* threefry2x32 primitive over n counter pairs (device arrays). */
 int nsb200_threefry2x32(const uint32_t key[2], const uint32_t *x0, const uint32_t *x1, int64_t n,

@@ -8,6 +8,9 @@ from jaxns_b200.nested_sampler import ShardedStaticNestedSampler  # noqa: F401
 from jaxns_b200.public import DefaultNestedSampler, NestedSampler  # noqa: F401
 from jaxns_b200.samplers import UniDimSliceSampler, UniformSampler  # noqa: F401
 from jaxns_b200.types import (NestedSamplerResults, NestedSamplerState, TerminationCondition)  # noqa: F401
+from jaxns_b200.experimental import (DefaultGlobalOptimisation, GlobalOptimisation,  # noqa: F401
+                                     GlobalOptimisationResults, GlobalOptimisationTerminationCondition,
+                                     SimpleGlobalOptimisation)
 from jaxns_b200.likelihoods import jaxify_likelihood  # noqa: F401
 from jaxns_b200.utils import (bruteforce_evidence, bruteforce_posterior_samples, evaluate_map_estimate,  # noqa: F401
                               load_pytree, load_results, marginalise_dynamic, marginalise_static,

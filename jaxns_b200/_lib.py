@@ -78,7 +78,7 @@ WS_ARGSORT, WS_COUNT_CROSSED_EDGES, WS_EVIDENCE_STATS, WS_LOGSUMEXP = 0, 1, 2, 3
 
 # every symbol include/nsb200.h declares
 EXPORTS = (
-    "nsb200_abi_version", "nsb200_last_error", "nsb200_set_option", "nsb200_threefry2x32", "nsb200_random_split",
+    "nsb200_abi_version", "nsb200_last_error", "nsb200_set_option", "nsb200_read_key", "nsb200_threefry2x32", "nsb200_random_split",
     "nsb200_random_bits64", "nsb200_random_uniform", "nsb200_random_normal", "nsb200_forward_batch",
     "nsb200_seed_table", "nsb200_init_batch", "nsb200_slice_batch", "nsb200_uniform_batch",
     "nsb200_workspace_bytes", "nsb200_argsort_f64", "nsb200_count_crossed_edges", "nsb200_evidence_stats",

@@ -14,7 +14,7 @@ namespace nsb {
 
 // Global scratch of the cluster-wide register update (k_iter_epilogue).
 struct EpiScratch {
-    double gpart[144];  // CTA aggregates of the three cluster scans
+    double gpart[3 * 3 * 64];  // CTA aggregates of the three group-wide scans (up to 64 CTAs, ev_gpart_stride)
     NsEvidenceCalc mid, fin;
     int not_plateau;
 };
@@ -27,7 +27,7 @@ __device__ __forceinline__ long long clampll(long long v, long long lo, long lon
 // (:250-251) and the dead-store bookkeeping of _add_samples_to_state (:54,76-78).
 __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSet live0, const LiveSet live1,
                                 long long m, long long kph, long long capacity, int intended_sender,
-                                EpiScratch *epi) {
+                                EpiScratch *epi, int no_speculation) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     (void) reg;
     (void) epi;
@@ -38,7 +38,9 @@ __global__ void k_iter_prologue(DevCtl *ctl, const NsRegister *reg, const LiveSe
     {
         const long long dm = *(volatile long long *) &ctl->done_iter;
         const long long it = ctl->iteration + 1;
-        ctl->active = (dm >= 0 && (dm == 0 || dm <= it - 2)) ? 0 : 1;
+        // no_speculation: the host made this kernel wait for the previous body's update as well (runs whose store wraps
+        // around cannot be rolled back: a speculative body would overwrite live rows of the ring)
+        ctl->active = (dm >= 0 && (dm == 0 || dm <= it - 2 || no_speculation)) ? 0 : 1;
     }
     if (!ctl->active) return;
     {

@@ -193,6 +193,13 @@ static int pick_spec(const Geometry &g) {
     return 2;
 }
 
+extern "C" int nsb200_read_key(const uint32_t *device_key, uint32_t out[2], nsb200_stream_t stream) {
+    if (!device_key || !out) return fail("NULL argument");
+    NSB_CUDA(cudaMemcpyAsync(out, device_key, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t) stream));
+    NSB_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    return 0;
+}
+
 // -------------------------------------------------------------------------------------------------
 // jax.random primitives
 // -------------------------------------------------------------------------------------------------
@@ -1063,6 +1070,7 @@ struct NsEngine {
     cudaStream_t epi_stream = nullptr;
     cudaEvent_t ev_adv = nullptr, ev_epi[2] = {nullptr, nullptr};
     int slot = 0;  // parity of the body between step_begin and step_end
+    int epi_ctas = 8;
     cudaEvent_t ev_keys = nullptr, ev_streams[3] = {nullptr, nullptr, nullptr};
     long long body = 0;       // host mirror of the next body index (its streams live in buffer body % 3)
     NsTermCond tc;
@@ -1308,7 +1316,19 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         for (int b = 0; b < 3; ++b)
             if (!rc && cudaEventCreateWithFlags(&e->ev_streams[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     }
-    if (!rc && cudaStreamCreateWithFlags(&e->epi_stream, cudaStreamNonBlocking) != cudaSuccess) rc = fail("cudaStreamCreate failed");
+    {
+        // the register update has 8-64 CTAs that meet at software barriers: highest priority, so that they are placed
+        // ahead of the thousands of chain CTAs of the next body that are enqueued right behind them
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (!rc && cudaStreamCreateWithPriority(&e->epi_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) rc = fail("cudaStreamCreate failed");
+    }
+    // CTAs of the in-loop register update: ~6 elements of the m + N scanned per thread (the 8-element register cache
+    // of evidence_scan_block), between the 8 of config 2 and 64
+    {
+        const long long want = (e->m + e->N + (long long) kEvThreads * 6 - 1) / ((long long) kEvThreads * 6);
+        e->epi_ctas = (int) (want < kEvCluster ? kEvCluster : (want > 64 ? 64 : want));
+    }
     if (!rc && cudaEventCreateWithFlags(&e->ev_adv, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     for (int b = 0; b < 2; ++b)
         if (!rc && cudaEventCreateWithFlags(&e->ev_epi[b], cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
@@ -1656,12 +1676,17 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     // the previous body's register update may still be running next to this body's chains (DevCtl::done_iter)
     e->slot = (int) (e->body & 1);
     NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot], 0));
+    // A store that wraps around (no max_samples bound: SimpleGlobalOptimisation, sharded_static.py:76-78) cannot be
+    // rolled back -- the speculative body would overwrite the oldest rows of the ring -- so such runs are sequential
+    const int no_spec = (e->tc.mask & (1u << 4)) ? 0 : 1;
+    if (no_spec) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot ^ 1], 0));
     // NSB200_GEN_FENCE=1: the generator launched behind the previous slice kernel (streams of body + 1) gets the GPU to
     // itself before this body's chains start.  Measured slower (105 vs 93 ms per config-2 run): with the register
     // update off the main stream the chains of body b + 1 simply start under the generator's tail.
     if (e->pre_dirs[0] && e->gen_mode == 3 && opt(OPT_GEN_FENCE) && e->body >= 1)
         NSB_CUDA(cudaStreamWaitEvent(st, e->ev_streams[(e->body + 1) % 3], 0));
-    k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi);
+    k_iter_prologue<<<1, 1, 0, st>>>(e->ctl, e->reg, e->live[0], e->live[1], e->m, e->k, e->cap, e->cfg.intended_sender, e->epi,
+                                     no_spec);
     k_append_live<<<296, 256, 0, st>>>(e->ctl, e->live[0], e->live[1], e->dead, e->m, D, 0);
     NSB_LAUNCH_CHECK();
     if (e->external) {  // the chains are run by the caller through nsb200_engine_split_*
@@ -1758,17 +1783,17 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     // register update + loop condition on their own stream: the next body's chains start right away.  Grid form:
     // 8 CTAs on ANY free SMs (a cluster would wait until one GPC has 8 free SMs)
     NSB_CUDA(cudaStreamWaitEvent(e->epi_stream, e->ev_adv, 0));
-    if (opt(OPT_EPI_CLUSTER))
+    if (opt(OPT_EPI_CLUSTER) && e->epi_ctas == kEvCluster)
         k_iter_epilogue<<<kEvCluster, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
                                                                       e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
                                                                       e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     else
-        k_iter_epilogue_grid<<<kEvCluster, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
+        k_iter_epilogue_grid<<<e->epi_ctas, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
                                                                            e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
                                                                            e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     NSB_CUDA(cudaEventRecord(e->ev_epi[e->slot], e->epi_stream));
     NSB_LAUNCH_CHECK();
-    trace_mark(e, "epilogue end", st);
+    trace_mark(e, "  register update end (own stream)", e->epi_stream);
     if (e->slice_launches == 64) trace_dump();
     e->all_launches += 4;
     return 0;

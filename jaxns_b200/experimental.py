@@ -1,0 +1,236 @@
+"""
+Callers of the hot path: global optimisation on top of the static nested-sampling loop, name for
+name with /root/reference/src/jaxns/experimental/global_optimisation.py:28-182 and experimental/public.py:20-140.
+
+SimpleGlobalOptimisation IS the nested-sampling engine with three twists the engine supports natively: a dead-point
+store of only 10 x num_search_chains rows that wraps around (max_samples=None turns the sample cap off,
+sharded_static.py:76-78, global_optimisation.py:163-172), termination on likelihood evaluations / contour / spread /
+efficiency, and "the result" = the best stored point instead of an evidence.
+
+Not built: the gradient-based fine-tune (global_optimisation.py:56-73: Newton-CG on jax.grad of the user likelihood)
+and gradient_slice / gradient_guided chains (uni_slice_sampler.py:202-214,255-269) -- they need gradients of the
+likelihood, which the fused families do not provide yet; asking for them raises NotImplementedError.  EvidenceMaximisation
+needs parametrised models (framework/context.py), out of the hot-path scope.
+"""
+import dataclasses
+import io
+import math
+from typing import Any, NamedTuple, Optional, TextIO, Union
+
+import torch
+
+from jaxns_b200.nested_sampler import ShardedStaticNestedSampler
+from jaxns_b200.samplers import AbstractSampler, UniDimSliceSampler
+from jaxns_b200.types import SampleCollection, TerminationCondition
+
+__all__ = ["GlobalOptimisationResults", "GlobalOptimisationTerminationCondition", "GlobalOptimisationState",
+           "SimpleGlobalOptimisation", "GlobalOptimisation", "DefaultGlobalOptimisation", "go_summary"]
+
+
+class GlobalOptimisationState(NamedTuple):
+    key: Any
+    samples: SampleCollection
+    num_samples: int
+    relative_spread: float
+    absolute_spread: float
+    num_likelihood_evaluations: int
+
+
+class GlobalOptimisationResults(NamedTuple):
+    U_solution: Any
+    X_solution: Any
+    solution: Any
+    log_L_solution: float
+    log_L_progress: Any
+    num_likelihood_evaluations: int
+    num_samples: int
+    termination_reason: int
+    relative_spread: float
+    absolute_spread: float
+
+
+class GlobalOptimisationTerminationCondition(NamedTuple):
+    max_likelihood_evaluations: Optional[float] = None
+    log_likelihood_contour: Optional[float] = None
+    rtol: Optional[float] = None
+    atol: Optional[float] = None
+    min_efficiency: Optional[float] = None
+
+
+@dataclasses.dataclass(eq=False)
+class SimpleGlobalOptimisation:
+    """global_optimisation.py:76-182."""
+    sampler: AbstractSampler
+    num_search_chains: int
+    model: Any
+    shell_frac: float = 0.5
+    devices: Optional[Any] = None
+    verbose: bool = False
+
+    def __post_init__(self):
+        if self.num_search_chains < 1:
+            raise ValueError("num_search_chains must be >= 1.")
+        self.num_search_chains = int(self.num_search_chains)
+        self._nested_sampler = ShardedStaticNestedSampler(
+            model=self.model,
+            max_samples=self.num_search_chains * 10,
+            init_efficiency_threshold=0.1,
+            sampler=self.sampler,
+            num_live_points=self.num_search_chains,
+            shell_fraction=self.shell_frac,
+            devices=self.devices,
+            verbose=self.verbose
+        )
+
+    def _gradient_descent(self, results: GlobalOptimisationResults) -> GlobalOptimisationResults:
+        raise NotImplementedError("The Newton-CG fine-tune needs gradients of the likelihood (not built).")
+
+    def _to_results(self, termination_reason, state: GlobalOptimisationState) -> GlobalOptimisationResults:
+        """global_optimisation.py:118-147: best stored point; the store may have wrapped, so only the rows written
+        so far (num_samples, capped at the capacity) are looked at."""
+        log_L = state.samples.log_L
+        cap = log_L.numel()
+        is_sample = torch.arange(cap, device=log_L.device) < state.num_samples
+        masked = torch.where(is_sample, log_L, torch.full_like(log_L, math.nan))
+        best_idx = int(torch.argmax(torch.nan_to_num(masked, nan=-math.inf)).item())
+        U_solution = state.samples.U_samples[best_idx]
+        X_solution = self.model.transform(U_solution)
+        solution = self.model.prepare_input(U_solution)
+        log_L_progress = torch.sort(masked).values  # low to high likelihoods, NaN (unused rows) at the end
+        return GlobalOptimisationResults(
+            U_solution=U_solution, X_solution=X_solution, solution=solution,
+            log_L_solution=float(log_L[best_idx].item()), log_L_progress=log_L_progress,
+            num_likelihood_evaluations=int(state.num_likelihood_evaluations), num_samples=int(state.num_samples),
+            relative_spread=float(state.relative_spread), absolute_spread=float(state.absolute_spread),
+            termination_reason=int(termination_reason))
+
+    def _run(self, key, term_cond: GlobalOptimisationTerminationCondition):
+        """global_optimisation.py:149-182."""
+        termination_reason, termination_register, state = self._nested_sampler._run(
+            key=key,
+            term_cond=TerminationCondition(
+                max_num_likelihood_evaluations=term_cond.max_likelihood_evaluations,
+                log_L_contour=term_cond.log_likelihood_contour,
+                efficiency_threshold=term_cond.min_efficiency,
+                atol=term_cond.atol,
+                rtol=term_cond.rtol,
+                max_samples=None  # turn off max samples for global optimisation: the store index wraps
+            )
+        )
+        go_state = GlobalOptimisationState(
+            key=state.key, samples=state.sample_collection, num_samples=state.num_samples,
+            absolute_spread=termination_register.absolute_spread, relative_spread=termination_register.relative_spread,
+            num_likelihood_evaluations=termination_register.num_likelihood_evaluations)
+        return termination_reason, go_state
+
+
+def _bit_mask(int_mask, width=8):
+    return list(map(int, '{:0{size}b}'.format(int_mask, size=width)))[::-1]
+
+
+def go_summary(results: GlobalOptimisationResults, f_obj: Optional[Union[str, TextIO]] = None) -> str:
+    """global_optimisation.py:200-300: the text report of a global-optimisation run, same lines and rounding."""
+    main_s = []
+
+    def _print(msg):
+        print(msg)
+        main_s.append(msg)
+
+    def _round(v, uncert_v):
+        v, uncert_v = float(v), float(uncert_v)
+        try:
+            sig_figs = -int("{:e}".format(uncert_v).split('e')[1]) + 1
+            return round(v, sig_figs)
+        except Exception:
+            return v
+
+    _print("--------")
+    _print("Termination Conditions:")
+    names = ['Reached max samples', 'Evidence uncertainty low enough', 'Small remaining evidence', 'Reached ESS',
+             "Used max num likelihood evaluations", 'Likelihood contour reached', 'Sampler efficiency too low',
+             'All live-points are on a single plateau (sign of possible precision error)',
+             'relative spread of live points < rtol', 'absolute spread of live points < atol',
+             'no seed points left (consider decreasing shell_fraction)']
+    for bit, description in zip(_bit_mask(int(results.termination_reason), width=11), names):
+        if bit == 1:
+            _print(description)
+    _print("--------")
+    _print(f"likelihood evals: {int(results.num_likelihood_evaluations):d}")
+    _print(f"samples: {int(results.num_samples):d}")
+    _print(f"likelihood evals / sample: {float(results.num_likelihood_evaluations / results.num_samples):.1f}")
+    _print("--------")
+    _print(f"max(log_L)={_round(results.log_L_solution, results.log_L_solution)}")
+    _print(f"relative spread: {_round(results.relative_spread, results.relative_spread)}")
+    _print(f"absolute spread: {_round(results.absolute_spread, results.absolute_spread)}")
+    for name, value in results.X_solution.items():
+        v = value.detach().cpu().numpy()
+        if v.size == 0:
+            continue
+        _print("--------")
+        is_shaped = v.ndim > 0
+        var_name = f"{name}[{','.join(['#'] * v.ndim)}]" if is_shaped else name
+        _print(f"{var_name}: max(L) est.")
+        if is_shaped:
+            import numpy as np
+            for inds in np.indices(v.shape).reshape((v.ndim, -1)).T:
+                point = v[tuple(inds)]
+                _print(f"{name}[{','.join(str(i) for i in inds)}]: {_round(point, 0.1 * point)}")
+        else:
+            _print(f"{name}: {_round(v, 0.1 * v)}")
+    _print("--------")
+    out = "\n".join(main_s)
+    if f_obj is not None:
+        if isinstance(f_obj, str):
+            with open(f_obj, "w") as f:
+                f.write(out)
+        elif isinstance(f_obj, io.TextIOBase):
+            f_obj.write(out)
+        else:
+            raise TypeError(f"Invalid f_obj: {type(f_obj)}")
+    return out
+
+
+@dataclasses.dataclass(eq=False)
+class GlobalOptimisation:
+    """experimental/public.py:20-140.  `gradient_slice` defaults to False here (the reference's default True needs
+    gradients of the likelihood); the other defaults follow the reference's non-gradient branch."""
+    model: Any
+    num_search_chains: Optional[int] = None
+    s: Optional[int] = None
+    k: Optional[int] = None
+    gradient_slice: bool = False
+    shell_frac: Optional[float] = None
+    devices: Optional[Any] = None
+    verbose: bool = False
+
+    def __post_init__(self):
+        if self.gradient_slice:
+            raise NotImplementedError("gradient_slice=True needs gradients of the likelihood (SURVEY §8(f) row 2, not built).")
+        if self.num_search_chains is None:
+            self.num_search_chains = self.model.U_ndims * 100
+        if self.s is None:
+            self.s = 10
+        if self.shell_frac is None:
+            self.shell_frac = 0.5
+        if self.k is None:
+            self.k = self.model.U_ndims * self.s - 1
+        sampler = UniDimSliceSampler(model=self.model, num_slices=self.model.U_ndims * int(self.s),
+                                     num_phantom_save=int(self.k), midpoint_shrink=True, perfect=True,
+                                     gradient_slice=False)
+        self._global_optimiser = SimpleGlobalOptimisation(
+            sampler=sampler, num_search_chains=int(self.num_search_chains), shell_frac=float(self.shell_frac),
+            model=self.model, devices=self.devices, verbose=self.verbose)
+        self.summary = go_summary
+
+    def __call__(self, key, term_cond: Optional[GlobalOptimisationTerminationCondition] = None,
+                 finetune: bool = False) -> GlobalOptimisationResults:
+        if term_cond is None:
+            term_cond = GlobalOptimisationTerminationCondition(min_efficiency=3e-2)
+        termination_reason, state = self._global_optimiser._run(key, term_cond)
+        results = self._global_optimiser._to_results(termination_reason, state)
+        if finetune:
+            results = self._global_optimiser._gradient_descent(results=results)
+        return results
+
+
+DefaultGlobalOptimisation = GlobalOptimisation

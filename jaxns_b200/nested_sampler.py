@@ -197,9 +197,20 @@ class ShardedStaticNestedSampler:
         if external:
             host_tc = self._effective_host_cond(term_cond) if not plain else None
             self._run_external(eng, key, tc, reg, stream, world, host_tc)
-        elif plain and (world == 1 or p2p):
+        elif plain and (world == 1 or p2p) and not self.verbose:
             _lib.check(L.nsb200_engine_run(eng.h, _lib.key_arg(key), ctypes.byref(tc), ctypes.c_int64(-1),
                                            ctypes.byref(reg), stream))
+        elif plain and (world == 1 or p2p):
+            # verbose: one body at a time, the register read back and printed after each (sharded_static.py:519-549)
+            _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
+            _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+            while not reg.done:
+                _lib.check(L.nsb200_engine_step(eng.h, stream))
+                _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                if self._rank == 0:
+                    self._print_register(termination.register_from_c(reg))
+            _lib.check(L.nsb200_engine_finalize(eng.h, stream))
+            _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
         else:
             _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
             gather = self._gather_tensor(eng) if (world > 1 and not p2p) else None
@@ -261,6 +272,24 @@ class ShardedStaticNestedSampler:
         self.last_profile = dict(slice_ms=ms.value, slice_launches=nsl.value, all_launches=nall.value,
                                  iterations=int(reg.iteration))
         return termination_reason, register, state
+
+    @staticmethod
+    def _print_register(r: TerminationRegister):
+        """The per-iteration printout of verbose=True (sharded_static.py:519-549), same fields and wording."""
+        ecr, ec = r.evidence_calc_with_remaining, r.evidence_calc
+        log_Z_mean, log_Z_var = linear_to_log_stats(ecr.log_Z_mean, log_f2_mean=ecr.log_Z2_mean)
+        log_Z_mean0, log_Z_var0 = linear_to_log_stats(ec.log_Z_mean, log_f2_mean=ec.log_Z2_mean)
+        with np.errstate(all="ignore"):
+            ess = float(np.exp(np.float64(2.0) * ecr.log_Z_mean - ecr.log_dZ2_mean))
+            print("-------\n"
+                  f"Num samples: {r.num_samples_used}\n"
+                  f"Num likelihood evals: {r.num_likelihood_evaluations}\n"
+                  f"Efficiency: {r.efficiency}\n"
+                  f"log(L) contour: {r.log_L_contour}\n"
+                  f"log(Z) est.: {log_Z_mean} +- {float(np.sqrt(np.float64(log_Z_var)))}\n"
+                  f"log(Z | remaining) est.: {log_Z_mean - log_Z_mean0} +- "
+                  f"{float(np.sqrt(np.float64(log_Z_var) + np.float64(log_Z_var0)))}\n"
+                  f"ESS: {ess}\n", flush=True)
 
     def _connect_peers(self, eng, world) -> bool:
         """Wire the engines of all ranks together for the fused all-gather (include/nsb200.h, nsb200_engine_p2p_*):

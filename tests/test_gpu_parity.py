@@ -931,7 +931,7 @@ def test_slice_batch_parity_at_config_size(torch_cuda, oracle, name, D, N, S, mi
     assert int(exp["n_evals"].sum()) > 150000
 
 
-@pytest.mark.parametrize("name,D,N,S,midpoint,shells", [("gauss", 32, 3200, 160, True, 4), ("eggbox", 2, 10000, 20, False, 6)])
+@pytest.mark.parametrize("name,D,N,S,midpoint,shells", [("gauss", 32, 3200, 160, True, 2), ("eggbox", 2, 10000, 20, False, 4)])
 def test_engine_run_matches_oracle_at_config_size(torch_cuda, oracle, name, D, N, S, midpoint, shells):
     """The first shells of the device-resident loop at config 2 / config 3 size against the oracle's loop: sample
     bookkeeping, sender indices, tree counts and n_evals exact, evidence register to 1e-8 (the tiled merge path runs
@@ -1018,3 +1018,49 @@ def test_reference_notebook_runs(torch_cuda, name, kw, samples, ref_evals, ref_l
         assert abs(utils.bruteforce_evidence(model, S=250) - true) < 1e-6  # the notebook's own check value
     else:
         assert 1.03 < ratio < 1.22, ratio
+
+
+# ---------------------------------------------------------------------------------------------------
+# callers: SimpleGlobalOptimisation on the wrap-around store
+# ---------------------------------------------------------------------------------------------------
+def test_global_optimisation_wraparound_store_matches_oracle(torch_cuda, oracle):
+    """SimpleGlobalOptimisation._run (experimental/global_optimisation.py:149-182): max_samples=None, a store of
+    10 x num_search_chains rows whose write index wraps (sharded_static.py:76-78).  26 shells into a 20-shell ring
+    against the oracle's loop: same termination, bookkeeping and ring contents; then the best point."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.experimental import GlobalOptimisationTerminationCondition, SimpleGlobalOptimisation
+    D, N, S = 2, 40, 4
+    model = product_models()["gauss"](D, mu=0.5, rho=0.5)
+    om = to_oracle(model, oracle)
+    key = random.PRNGKey(3)
+    probe = oracle.OracleNestedSampler(om, N, S, 0, True, max_samples=N * 10)
+    probe.run(key, oracle.TermCond(), max_iterations=26)
+    budget = float(probe.register["num_likelihood_evaluations"]) - 0.5  # reached by the 26th shell
+    ons = oracle.OracleNestedSampler(om, N, S, 0, True, max_samples=N * 10)
+    oreason, ost = ons.run(key, oracle.TermCond(max_num_likelihood_evaluations=budget), max_iterations=40)
+    assert ons.iterations == 26 and oreason & 16 and ost["num_samples"] > ons.max_samples  # wrapped
+    sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=0, midpoint_shrink=True, perfect=True)
+    go = SimpleGlobalOptimisation(sampler=sampler, num_search_chains=N, model=model)
+    reason, state = go._run(key, GlobalOptimisationTerminationCondition(max_likelihood_evaluations=budget))
+    assert int(reason) == oreason
+    assert state.num_samples == ost["num_samples"]
+    assert state.num_likelihood_evaluations == ons.register["num_likelihood_evaluations"]
+    np.testing.assert_array_equal(state.samples.sender_node_idx.cpu().numpy(), ost["sender"])
+    np.testing.assert_allclose(state.samples.log_L.cpu().numpy(), ost["log_L"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(state.samples.U_samples.cpu().numpy(), ost["U"], rtol=1e-6, atol=1e-8)
+    res = go._to_results(reason, state)
+    assert abs(res.log_L_solution - np.max(ost["log_L"])) < 1e-6
+    assert res.num_samples == state.num_samples and torch.isfinite(res.log_L_progress).all()
+    x = res.X_solution["x"].cpu().numpy()
+    assert np.all(np.abs(x - 0.5) < 0.6)  # near the likelihood's peak at (0.5, 0.5)
+    # the public facade with an explicit condition (its default min_efficiency=3e-2 stops before the first iteration,
+    # like the reference's: SURVEY App. E #19)
+    opt = j.GlobalOptimisation(model=model, num_search_chains=200, s=4)
+    out = opt(random.PRNGKey(0), GlobalOptimisationTerminationCondition(max_likelihood_evaluations=2e5, atol=1e-4))
+    assert out.termination_reason & (16 | 512)
+    assert out.log_L_solution > float(model.forward(torch.full((2,), 0.5, dtype=torch.float64, device="cuda")).item()) - 10.0
+    assert len(opt.summary(out)) > 50
+    stopped = opt(random.PRNGKey(0))
+    assert stopped.termination_reason == 64 and stopped.num_samples == 200

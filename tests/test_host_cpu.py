@@ -250,3 +250,27 @@ def test_load_results_written_by_the_reference_serialiser(tmp_path):
     tc = utils.load_pytree(f, device="cpu")
     assert type(tc).__name__ == "TerminationCondition" and tc.ess == 100.0 and tc.max_samples == 5000
     assert tc.evidence_uncert is None and isinstance(tc.peak_XL_frac, np.ndarray)
+
+
+def test_xla_ffi_shim_compiles(tmp_path):
+    """csrc/xla_ffi_shim.cc (the jax.ffi custom-call handlers of the north star) compiles against the stand-in of
+    XLA's FFI header, which checks every handler's signature against its Bind().Ctx().Arg().Ret().Attr() chain, and
+    every nsb200_* function it forwards to is declared in include/nsb200.h with matching arguments."""
+    import subprocess
+    src = os.path.join(ROOT, "jaxns_b200", "csrc", "xla_ffi_shim.cc")
+    obj = os.path.join(tmp_path, "shim.o")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-c", "-fPIC",
+                           "-I" + os.path.join(ROOT, "jaxns_b200", "csrc", "ffi_stub"), "-I" + os.path.join(ROOT, "include"),
+                           src, "-o", obj])
+    syms = subprocess.run(["nm", "-g", "--defined-only", obj], capture_output=True, text=True, check=True).stdout
+    for name in ("slice_batch", "init_batch", "forward_batch", "count_crossed_edges", "evidence_stats", "sample_evidence"):
+        assert f"nsb200_ffi_{name}" in syms
+    # a handler whose signature drifts from its binding must not compile
+    bad = os.path.join(tmp_path, "bad.cc")
+    text = open(src).read().replace("ffi::ResultBuffer<ffi::F64> out) {", "ffi::ResultBuffer<ffi::S64> out) {")
+    assert text != open(src).read()
+    open(bad, "w").write(text.replace('"../../include/nsb200.h"', '"nsb200.h"'))
+    rc = subprocess.run(["g++", "-std=c++17", "-c", "-fPIC", "-I" + os.path.join(ROOT, "jaxns_b200", "csrc", "ffi_stub"),
+                         "-I" + os.path.join(ROOT, "include"), bad, "-o", os.path.join(tmp_path, "bad.o")],
+                        capture_output=True, text=True)
+    assert rc.returncode != 0 and "does not match its FFI binding" in rc.stderr
