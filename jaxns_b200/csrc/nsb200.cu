@@ -55,7 +55,7 @@ extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
 // it at run time (tests A/B kernels inside one process).  None of them changes results.
 enum {
     OPT_SPEC, OPT_TPB, OPT_SLICE_MMA, OPT_MMA_P, OPT_MMA_WPB, OPT_MERGE_BRUTE, OPT_GEN_MODE, OPT_GEN_SMS, OPT_GEN_TPB,
-    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_GEN_FENCE, OPT_COUNT
+    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_GEN_FENCE, OPT_SPECULATE, OPT_COUNT
 };
 struct NsOption {
     const char *name;
@@ -68,7 +68,7 @@ static NsOption g_opts[OPT_COUNT] = {
     {"NSB200_MMA_P", 0, 0, false},       {"NSB200_MMA_WPB", 4, 0, false},     {"NSB200_MERGE_BRUTE", 0, 0, false},
     {"NSB200_GEN_MODE", 3, 0, false},    {"NSB200_GEN_SMS", 0, 0, false},     {"NSB200_GEN_TPB", 0, 0, false},
     {"NSB200_EPI_CLUSTER", 0, 0, false}, {"NSB200_DEPTH", 4, 0, false},       {"NSB200_TRACE", 0, 0, false},
-    {"NSB200_GEN_FENCE", 0, 0, false},
+    {"NSB200_GEN_FENCE", 0, 0, false},  {"NSB200_SPECULATE", 2, 0, false},
 };
 static int opt(int id) {
     NsOption &o = g_opts[id];
@@ -1071,6 +1071,7 @@ struct NsEngine {
     cudaEvent_t ev_adv = nullptr, ev_epi[2] = {nullptr, nullptr};
     int slot = 0;  // parity of the body between step_begin and step_end
     int epi_ctas = 8;
+    bool no_spec = true;  // this run's bodies are sequential: the register update stays on the caller's stream
     cudaEvent_t ev_keys = nullptr, ev_streams[3] = {nullptr, nullptr, nullptr};
     long long body = 0;       // host mirror of the next body index (its streams live in buffer body % 3)
     NsTermCond tc;
@@ -1678,7 +1679,16 @@ extern "C" int nsb200_engine_step_begin(NsEngine *e, nsb200_stream_t stream) {
     NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot], 0));
     // A store that wraps around (no max_samples bound: SimpleGlobalOptimisation, sharded_static.py:76-78) cannot be
     // rolled back -- the speculative body would overwrite the oldest rows of the ring -- so such runs are sequential
-    const int no_spec = (e->tc.mask & (1u << 4)) ? 0 : 1;
+    // NSB200_SPECULATE: 1 = always overlap the register update with the next body, 0 = never, 2 (default) = when the
+    // live set is replicated over several GPUs.  On one GPU the update (75 us) already hides behind the chain-stream
+    // generator (139 us on the side stream), so overlapping it with the next chains only makes chains and generator
+    // collide: same 93 ms per config-2 run either way, and one wasted body at the end.  From 2 GPUs on the update
+    // (100-140 us over the larger replicated live set) is the longer of the two and comes off the critical path:
+    // 8-GPU weak scaling 0.79 -> 0.92 (profiles/r2/).
+    const int spec_mode = opt(OPT_SPECULATE);
+    const bool speculate = spec_mode == 1 || (spec_mode == 2 && e->cfg.world_size > 1);
+    const int no_spec = ((e->tc.mask & (1u << 4)) && speculate) ? 0 : 1;
+    e->no_spec = no_spec != 0;
     if (no_spec) NSB_CUDA(cudaStreamWaitEvent(st, e->ev_epi[e->slot ^ 1], 0));
     // NSB200_GEN_FENCE=1: the generator launched behind the previous slice kernel (streams of body + 1) gets the GPU to
     // itself before this body's chains start.  Measured slower (105 vs 93 ms per config-2 run): with the register
@@ -1782,18 +1792,20 @@ extern "C" int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream) {
     NSB_CUDA(cudaEventRecord(e->ev_adv, st));
     // register update + loop condition on their own stream: the next body's chains start right away.  Grid form:
     // 8 CTAs on ANY free SMs (a cluster would wait until one GPC has 8 free SMs)
-    NSB_CUDA(cudaStreamWaitEvent(e->epi_stream, e->ev_adv, 0));
+    // sequential runs keep the update on the caller's stream (round 1's schedule: it then runs in the generator's shadow)
+    cudaStream_t es = e->no_spec ? st : e->epi_stream;
+    if (!e->no_spec) NSB_CUDA(cudaStreamWaitEvent(es, e->ev_adv, 0));
     if (opt(OPT_EPI_CLUSTER) && e->epi_ctas == kEvCluster)
-        k_iter_epilogue<<<kEvCluster, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
+        k_iter_epilogue<<<kEvCluster, kEvThreads, 0, es>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
                                                                       e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
                                                                       e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
     else
-        k_iter_epilogue_grid<<<e->epi_ctas, kEvThreads, 0, e->epi_stream>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
+        k_iter_epilogue_grid<<<e->epi_ctas, kEvThreads, 0, es>>>(e->ctl, e->reg, e->live[0], e->live[1], e->packed,
                                                                            e->row_doubles, D, e->m, e->N, e->tc, 0, e->tabT,
                                                                            e->tabT2, e->tabt, e->N, e->epi, e->progress_dev);
-    NSB_CUDA(cudaEventRecord(e->ev_epi[e->slot], e->epi_stream));
+    NSB_CUDA(cudaEventRecord(e->ev_epi[e->slot], es));
     NSB_LAUNCH_CHECK();
-    trace_mark(e, "  register update end (own stream)", e->epi_stream);
+    trace_mark(e, "  register update end", es);
     if (e->slice_launches == 64) trace_dump();
     e->all_launches += 4;
     return 0;

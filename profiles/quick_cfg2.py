@@ -42,4 +42,5 @@ for s in range(-3, reps):
         lz.append(round(r.log_Z_mean, 3))
 print(f"lib={os.path.basename(_lib.so_path())} runs={reps} ms/run={np.mean(ms_all):.2f} (min {np.min(ms_all):.2f}) "
       f"slice_ms/iter={np.sum(sl_all) / np.sum(it_all):.4f} iters={np.mean(it_all):.1f} "
-      f"evals/s={np.sum(ev_all) / np.sum(ms_all) * 1e3:.4g} slice_evals/s={np.sum(ev_all) / np.sum(sl_all) * 1e3:.4g} logZ={lz}")
+      f"evals/s={np.sum(ev_all) / np.sum(ms_all) * 1e3:.4g} slice_evals/s={np.sum(ev_all) / np.sum(sl_all) * 1e3:.4g} logZ={lz} "
+      f"runs_ms={[round(x, 1) for x in ms_all]}")

@@ -931,11 +931,13 @@ def test_slice_batch_parity_at_config_size(torch_cuda, oracle, name, D, N, S, mi
     assert int(exp["n_evals"].sum()) > 150000
 
 
-@pytest.mark.parametrize("name,D,N,S,midpoint,shells", [("gauss", 32, 3200, 160, True, 2), ("eggbox", 2, 10000, 20, False, 4)])
+@pytest.mark.parametrize("name,D,N,S,midpoint,shells", [("gauss", 32, 3200, 160, True, 1), ("eggbox", 2, 10000, 20, False, 3)])
 def test_engine_run_matches_oracle_at_config_size(torch_cuda, oracle, name, D, N, S, midpoint, shells):
     """The first shells of the device-resident loop at config 2 / config 3 size against the oracle's loop: sample
     bookkeeping, sender indices, tree counts and n_evals exact, evidence register to 1e-8 (the tiled merge path runs
-    for m = 5000)."""
+    for m = 5000).  The horizon is short on purpose: at S = 160 a chain amplifies rounding-level differences of its
+    seed point, so in the SECOND shell of config 2 one chain of 1600 already ends 4e-3 away in log L (same n_evals)
+    and in the third 59 do (profiles/dbg_cfgsize.py) -- CPU and GPU runs are then different realisations."""
     import os
     import jaxns_b200 as j
     from jaxns_b200 import random
