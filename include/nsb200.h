@@ -169,7 +169,8 @@ const char *nsb200_last_error(void);
 /* Tuning / A-B knobs (launch geometry, kernel selection: results never depend on them).  Every knob is also an
  * environment variable of the same name, read once per process; value < 0 returns to that default.  Names:
  * NSB200_SPEC, NSB200_TPB, NSB200_SLICE_MMA, NSB200_MMA_P, NSB200_MMA_WPB, NSB200_MERGE_BRUTE, NSB200_GEN_MODE,
- * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_GEN_FENCE, NSB200_SPECULATE, NSB200_EPI_CLUSTER, NSB200_DEPTH, NSB200_TRACE. */
+ * NSB200_GEN_SMS, NSB200_GEN_TPB, NSB200_GEN_FENCE, NSB200_SPECULATE, NSB200_EPI_CLUSTER, NSB200_EPI_CTAS,
+ * NSB200_EPI_PRIO, NSB200_DEPTH, NSB200_TRACE. */
 int nsb200_set_option(const char *name, int32_t value);
 
 /* Copies the two words of a PRNG key from DEVICE memory (where XLA keeps keys) to the host; synchronises `stream`.

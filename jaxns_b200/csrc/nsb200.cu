@@ -55,7 +55,7 @@ extern "C" const char *nsb200_last_error(void) { return g_last_error.c_str(); }
 // it at run time (tests A/B kernels inside one process).  None of them changes results.
 enum {
     OPT_SPEC, OPT_TPB, OPT_SLICE_MMA, OPT_MMA_P, OPT_MMA_WPB, OPT_MERGE_BRUTE, OPT_GEN_MODE, OPT_GEN_SMS, OPT_GEN_TPB,
-    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_GEN_FENCE, OPT_SPECULATE, OPT_COUNT
+    OPT_EPI_CLUSTER, OPT_DEPTH, OPT_TRACE, OPT_GEN_FENCE, OPT_SPECULATE, OPT_EPI_CTAS, OPT_EPI_PRIO, OPT_COUNT
 };
 struct NsOption {
     const char *name;
@@ -68,7 +68,8 @@ static NsOption g_opts[OPT_COUNT] = {
     {"NSB200_MMA_P", 0, 0, false},       {"NSB200_MMA_WPB", 4, 0, false},     {"NSB200_MERGE_BRUTE", 0, 0, false},
     {"NSB200_GEN_MODE", 3, 0, false},    {"NSB200_GEN_SMS", 0, 0, false},     {"NSB200_GEN_TPB", 0, 0, false},
     {"NSB200_EPI_CLUSTER", 0, 0, false}, {"NSB200_DEPTH", 4, 0, false},       {"NSB200_TRACE", 0, 0, false},
-    {"NSB200_GEN_FENCE", 0, 0, false},  {"NSB200_SPECULATE", 2, 0, false},
+    {"NSB200_GEN_FENCE", 0, 0, false},  {"NSB200_SPECULATE", 2, 0, false},  {"NSB200_EPI_CTAS", 0, 0, false},
+    {"NSB200_EPI_PRIO", 1, 0, false},
 };
 static int opt(int id) {
     NsOption &o = g_opts[id];
@@ -619,7 +620,9 @@ static int launch_chain_streams(const StreamArgs &sa, int ctas, int tpb, size_t 
     const long long wpc = tpb / 32;
     if ((long long) ctas * wpc > warps) ctas = (int) ((warps + wpc - 1) / wpc);
     if (ctas < 1) return 0;
-    k_chain_streams<<<ctas, tpb, smem, st>>>(sa);
+    if (sa.D <= 32) k_chain_streams<1><<<ctas, tpb, smem, st>>>(sa);
+    else if (sa.D <= 128) k_chain_streams<4><<<ctas, tpb, smem, st>>>(sa);
+    else k_chain_streams<8><<<ctas, tpb, smem, st>>>(sa);
     NSB_LAUNCH_CHECK();
     return 0;
 }
@@ -1322,13 +1325,20 @@ extern "C" int nsb200_engine_create(const NsEngineConfig *cfg, NsEngine **out) {
         // ahead of the thousands of chain CTAs of the next body that are enqueued right behind them
         int prio_lo = 0, prio_hi = 0;
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        if (!rc && cudaStreamCreateWithPriority(&e->epi_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) rc = fail("cudaStreamCreate failed");
+        if (!rc && cudaStreamCreateWithPriority(&e->epi_stream, cudaStreamNonBlocking, opt(OPT_EPI_PRIO) ? prio_hi : prio_lo) != cudaSuccess)
+            rc = fail("cudaStreamCreate failed");
     }
     // CTAs of the in-loop register update: ~6 elements of the m + N scanned per thread (the 8-element register cache
     // of evidence_scan_block), between the 8 of config 2 and 64
     {
+        // ... but never more than the SMs the chain-stream generator leaves free (enqueue_streams: 28 while it is
+        // short, 8 when it is long): the CTAs meet at a spinning barrier, so all of them have to be resident at once --
+        // 49 CTAs at config 5 sat behind the 5 ms generator and cost 17 ms per body (profiles/r2/config5_n8_49cta_epilogue.json)
         const long long want = (e->m + e->N + (long long) kEvThreads * 6 - 1) / ((long long) kEvThreads * 6);
-        e->epi_ctas = (int) (want < kEvCluster ? kEvCluster : (want > 64 ? 64 : want));
+        const bool short_gen = (double) e->rows_per_rank * cfg->num_slices * e->D < 32e6;
+        const long long room = short_gen ? 24 : kEvCluster;
+        e->epi_ctas = (int) (want < kEvCluster ? kEvCluster : (want > room ? room : want));
+        if (opt(OPT_EPI_CTAS) >= 1 && opt(OPT_EPI_CTAS) <= 64) e->epi_ctas = opt(OPT_EPI_CTAS);
     }
     if (!rc && cudaEventCreateWithFlags(&e->ev_adv, cudaEventDisableTiming) != cudaSuccess) rc = fail("cudaEventCreate failed");
     for (int b = 0; b < 2; ++b)
@@ -1634,7 +1644,9 @@ static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t af
             int optin = 0;
             optin_smem = 227 * 1024;
             if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, 0) == cudaSuccess && optin > 0) optin_smem = (size_t) optin;
-            NSB_CUDA(cudaFuncSetAttribute(k_chain_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) optin_smem));
+            NSB_CUDA(cudaFuncSetAttribute(k_chain_streams<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) optin_smem));
+            NSB_CUDA(cudaFuncSetAttribute(k_chain_streams<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) optin_smem));
+            NSB_CUDA(cudaFuncSetAttribute(k_chain_streams<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) optin_smem));
         }
         gen_smem = e->gen_mode == 1 ? optin_smem : 200 * 1024;
     } else {
@@ -1653,9 +1665,8 @@ static int enqueue_streams(NsEngine *e, int buf, cudaStream_t st, cudaEvent_t af
     if (opt(OPT_GEN_SMS) > 0) gen_ctas = opt(OPT_GEN_SMS);
     if (opt(OPT_GEN_TPB) >= 32 && opt(OPT_GEN_TPB) <= 1024) tpb = (opt(OPT_GEN_TPB) / 32) * 32;
     const long long wpc = tpb / 32;
-    if ((long long) gen_ctas * wpc > warps) gen_ctas = (int) ((warps + wpc - 1) / wpc);
-    k_chain_streams<<<gen_ctas, tpb, gen_smem, gs>>>(sa);
-    NSB_LAUNCH_CHECK();
+    (void) wpc;
+    if (launch_chain_streams(sa, gen_ctas, tpb, gen_smem, gs)) return 1;
     if (own_stream) {
         NSB_CUDA(cudaEventRecord(e->ev_streams[buf], e->side));
         trace_mark(e, "  generator end (side)", e->side);

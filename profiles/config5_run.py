@@ -33,21 +33,38 @@ model = product_models()["mixture"](D)
 # component needs ~233 nats -- size the store for 500 shells
 ns = j.NestedSampler(model=model, num_live_points=N, max_samples=N * 250)
 assert ns.num_slices == 500 and ns.k == 0
-torch.cuda.synchronize()
-if world > 1:
-    dist.barrier()
+def sync():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+
+# engine creation (one ~30 GB arena: 21 GB dead store + 3 x 2.5 GB chain streams) and peer wiring, outside the timed runs
+sync()
 t0 = time.perf_counter()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-reason, state = ns(random.PRNGKey(seed))
-e1.record()
-torch.cuda.synchronize()
-wall = time.perf_counter() - t0
-ms = e0.elapsed_time(e1)
-t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+inner = ns.nested_sampler
+eng = inner._make_engine()
 if world > 1:
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-ms = float(t.item())
+    inner._connect_peers(eng, world)
+sync()
+t_engine = time.perf_counter() - t0
+runs = []
+for rep in range(2):  # run 0 pays lazy module loads, the seed table (36 ms) and the first torch allocations of the state
+    sync()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    reason, state = ns(random.PRNGKey(seed))
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    runs.append(float(t.item()))
+    if rep == 0:
+        del state, reason
+ms = runs[-1]
 prof = ns.nested_sampler.last_profile
 reg = ns.nested_sampler.last_register
 if rank == 0:
@@ -69,7 +86,8 @@ if rank == 0:
         "exchange_bytes_per_body": rows * (D + 2) * 8,
         "log_Z": res.log_Z_mean, "log_Z_uncert": res.log_Z_uncert, "log_Z_closed_form": logZ_true,
         "sigma_off": (res.log_Z_mean - logZ_true) / res.log_Z_uncert, "ESS": res.ESS,
-        "total_samples": res.total_num_samples, "to_results_s": t_res, "wall_s": wall,
+        "total_samples": res.total_num_samples, "to_results_s": t_res, "wall_s": wall, "engine_create_s": t_engine,
+        "first_run_ms": runs[0],
     }
     print(json.dumps(line))
 if world > 1:
