@@ -162,6 +162,9 @@ __device__ __noinline__ double slow_div(double a, double b) { return a / b; }
 // its slow-path check, ~125 cycles).  Result within 1 ulp of a / b; non-finite intermediates (b = 0,
 // inf, denormal) fall back to the IEEE division.
 __device__ __forceinline__ double fast_div(double a, double b) {
+#ifdef NSB_EXACT_MATH
+    return a / b;  // parity build: IEEE division (see cephes_ndtri below)
+#endif
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);
@@ -174,6 +177,9 @@ __device__ __forceinline__ double fast_div(double a, double b) {
 // Same without the fallback, for denominators known to be finite, normal and non-zero (the AS241
 // denominators are polynomials bounded away from zero on their intervals).
 __device__ __forceinline__ double fast_div_finite(double a, double b) {
+#ifdef NSB_EXACT_MATH
+    return a / b;
+#endif
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);
@@ -217,8 +223,66 @@ __device__ __forceinline__ double horner8(const double *c, double x) {
     return r;
 }
 
+#ifdef NSB_EXACT_MATH
+// -DNSB_EXACT_MATH (parity build, tests/test_gpu_exact_math.py): the reference's own quantile -- Cephes ndtri as
+// tfp.math.ndtri evaluates it (central rational in (p - 1/2)^2 for exp(-2) < p < 1 - exp(-2), two tail rationals in
+// 1 / sqrt(-2 log p)) -- and IEEE divisions everywhere, instead of AS241 and the reciprocal-Newton division.  What
+// still differs from a CPU evaluation of the same formulas: libdevice's log / exp / log1p (<= 1 ulp, like glibc's,
+// but not the same bits), FMA contraction and the order of the 32-lane sums.
+__constant__ double kCephesP0[5] = {-5.99633501014107895267E1, 9.80010754185999661536E1, -5.66762857469070293439E1,
+                                    1.39312609387279679503E1, -1.23916583867381258016E0};
+__constant__ double kCephesQ0[9] = {1.0, 1.95448858338141759834E0, 4.67627912898881538453E0, 8.63602421390890590575E1,
+                                    -2.25462687854119370527E2, 2.00260212380060660359E2, -8.20372256168333339912E1,
+                                    1.59056225126211695515E1, -1.18331621121330003142E0};
+__constant__ double kCephesP1[9] = {4.05544892305962419923E0, 3.15251094599893866154E1, 5.71628192246421288162E1,
+                                    4.40805073893200834700E1, 1.46849561928858024014E1, 2.18663306850790267539E0,
+                                    -1.40256079171354495875E-1, -3.50424626827848203418E-2, -8.57456785154685413611E-4};
+__constant__ double kCephesQ1[9] = {1.0, 1.57799883256466749731E1, 4.53907635128879210584E1, 4.13172038254672030440E1,
+                                    1.50425385692907503408E1, 2.50464946208309415979E0, -1.42182922854787788574E-1,
+                                    -3.80806407691578277194E-2, -9.33259480895457427372E-4};
+__constant__ double kCephesP2[9] = {3.23774891776946035970E0, 6.91522889068984211695E0, 3.93881025292474443415E0,
+                                    1.33303460815807542389E0, 2.01485389549179081538E-1, 1.23716634817820021358E-2,
+                                    3.01581553508235416007E-4, 2.65806974686737550832E-6, 6.23974539184983293730E-9};
+__constant__ double kCephesQ2[9] = {1.0, 6.02427039364742014255E0, 3.67983563856160859403E0, 1.37702099489081330271E0,
+                                    2.16236993594496635890E-1, 1.34204006088543189037E-2, 3.28014464682127739104E-4,
+                                    2.89247864745380683936E-6, 6.79019408009981274425E-9};
+
+__device__ __noinline__ double cephes_ndtri(double p) {
+    const double kInf = __longlong_as_double(0x7FF0000000000000ll);
+    if (p == 0.0) return -kInf;
+    if (p == 1.0) return kInf;
+    if (!(p > 0.0 && p < 1.0)) return __longlong_as_double(0x7FF8000000000000ll);
+    const bool upper = p > 0.8646647167633873;  // 1 - exp(-2)
+    const double q = upper ? 1.0 - p : p;
+    double x;
+    if (q > 0.1353352832366127) {  // exp(-2)
+        const double w = q - 0.5, ww = w * w;
+        double num = kCephesP0[0], den = kCephesQ0[0];
+        for (int i = 1; i < 5; ++i) num = num * ww + kCephesP0[i];
+        for (int i = 1; i < 9; ++i) den = den * ww + kCephesQ0[i];
+        x = w + w * ww * (num / den);
+        x *= -2.5066282746310002;  // -sqrt(2 pi)
+    } else {
+        const double z = sqrt(-2.0 * log(q));
+        const double first = z - log(z) / z;
+        const double rz = 1.0 / z;
+        const double *P = (z >= 8.0) ? kCephesP2 : kCephesP1;
+        const double *Q = (z >= 8.0) ? kCephesQ2 : kCephesQ1;
+        double num = P[0], den = Q[0];
+        for (int i = 1; i < 9; ++i) num = num * rz + P[i];
+        for (int i = 1; i < 9; ++i) den = den * rz + Q[i];
+        x = first - num / den / z;
+    }
+    return upper ? x : -x;
+}
+#endif
+
 // `mask` = lanes that execute this call together (the chain's lane group).
 __device__ __forceinline__ double ndtri(double p, unsigned mask) {
+#ifdef NSB_EXACT_MATH
+    (void) mask;
+    return cephes_ndtri(p);
+#endif
     const double q = p - 0.5;
     const double r = fma(-q, q, 0.180625);
     double x = fast_div_finite(q * horner8(kPpndA, r), horner8(kPpndB, r));
@@ -249,6 +313,12 @@ __device__ __forceinline__ double ndtri(double p, unsigned mask) {
 // region, so the tail must stay skippable.)  Same operations per element as ndtri(): bit-identical results.
 template <int P>
 __device__ __forceinline__ void ndtri_batch(const double (&p)[P], unsigned mask, double (&x)[P]) {
+#ifdef NSB_EXACT_MATH
+    (void) mask;
+#pragma unroll
+    for (int i = 0; i < P; ++i) x[i] = cephes_ndtri(p[i]);
+    return;
+#endif
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
     double q[P];
     bool tail[P], any_tail = false;
@@ -307,6 +377,11 @@ __device__ unsigned long long g_tail_trips;
 #endif
 template <int K>
 __device__ __forceinline__ void ndtri_multi(const double (&p)[K], double (&x)[K]) {
+#ifdef NSB_EXACT_MATH
+#pragma unroll
+    for (int i = 0; i < K; ++i) x[i] = cephes_ndtri(p[i]);
+    return;
+#endif
     const double kInf = __longlong_as_double(0x7FF0000000000000ll);
     unsigned pend = 0;
     {

@@ -186,13 +186,49 @@ __device__ inline void stage_model(const NsModelDesc &m, double *smem, ModelSmem
     }
 }
 
-// Per-thread registers of the dense factor (only meaningful for G == 32, DPL == 1).
+// Matvec of the D <= 32 dense factor on the FP64 tensor-core path (mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) INSIDE the
+// lane-per-dimension kernel: the P proposals of a round are columns 0..P-1 of the B operand (the other columns are
+// zero), L^-1 is 20 lower-triangular 8x4 A tiles per lane (40 registers instead of the 64-register row), the
+// residuals reach the B layout with one shuffle per k tile and proposal instead of a shared-memory exchange, and
+// ||z||^2 needs a 3-step butterfly instead of 5.  This is a LATENCY trade: 20 DMMAs occupy the FP64 pipe for 320
+// cycles where 32 P DFMAs need 64 P, but the dependent chain of a round (exchange -> 32-deep FMA row -> butterfly)
+// gets shorter, and the round's latency is what bounds this kernel.  MEASURED (config 2, -DNSB_LANE_MMA=1):
+// 140 registers instead of 166, same results, slice kernel 0.617 ms instead of 0.537 ms -- with 2.7 warps per
+// sub-partition the 320 pipe cycles per round and warp contend (FP64 pipe 40 % -> ~66 %) and cost more than the
+// shorter chain saves.  Off by default; kept because it is the cheapest way to re-measure on other shapes.
+#ifndef NSB_LANE_MMA
+#define NSB_LANE_MMA 0
+#endif
+constexpr bool kLaneMma = NSB_LANE_MMA != 0;
+
+__device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// Per-thread registers of the dense factor (only meaningful for G == 32, DPL == 1): the lane's row of L^-1, or
+// (kLaneMma) its elements of the 20 A tiles on or below the diagonal: tile (b, s), s <= 2 b + 1, holds
+// Linv[8 b + lane / 4][4 s + lane % 4].
 template <int G, int DPL, bool RS = false>
 struct DenseRow {
-    static constexpr int N = (dense_in_regs(G, DPL) && !RS) ? 32 : 1;
+    static constexpr bool kRegs = dense_in_regs(G, DPL) && !RS;
+    static constexpr int N = kRegs ? (kLaneMma ? 20 : 32) : 1;
     double v[N];
     __device__ __forceinline__ void load(const ModelSmem &sm, int lane) {
-        if (dense_in_regs(G, DPL) && !RS) {
+        if (kRegs && kLaneMma) {
+            int ai = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+#pragma unroll
+                for (int s = 0; s < 2 * b + 2; ++s) {
+                    const int row = 8 * b + (lane >> 2), col = 4 * s + (lane & 3);
+                    v[ai++] = (sm.family == NSB200_FAM_GAUSS_DENSE && row < sm.D && col < sm.D && col <= row)
+                                  ? __ldg(sm.dense_global + (size_t) row * sm.D + col)
+                                  : 0.0;
+                }
+            }
+        } else if (kRegs) {
 #pragma unroll
             for (int j = 0; j < N; ++j)
                 v[j] = (sm.family == NSB200_FAM_GAUSS_DENSE && lane < sm.D && j <= lane)
@@ -239,6 +275,49 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
     switch (FAM) {  // compile-time: the kernels dispatch on the family once, outside the chain loop
         case NSB200_FAM_GAUSS_DENSE: {
             const double *mu = Pm + 1;
+            if (DenseRow<G, DPL, RS>::kRegs && kLaneMma && P <= 8) {
+                // residual of dimension `lane` for each proposal, then B tile s: lane (g, t) needs r[4 s + t] of
+                // proposal g (columns >= P are zero); the 8 tiles are shared by the 4 row blocks
+                const int lane = g.lane, gq = lane >> 2, tq = lane & 3;
+                double r[P];
+                const double m = mu[lane];
+#pragma unroll
+                for (int p = 0; p < P; ++p) r[p] = (lane < D) ? X[p][0] - m : 0.0;
+                double bt[8];
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    double bv = 0.0;
+#pragma unroll
+                    for (int p = 0; p < P; ++p) {
+                        const double y = __shfl_sync(0xFFFFFFFFu, r[p], 4 * s + tq);
+                        bv = (gq == p) ? y : bv;
+                    }
+                    bt[s] = bv;
+                }
+                double sq0 = 0.0, sq1 = 0.0;
+                int ai = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 2 * b + 2; ++s) dmma_m8n8k4(c0, c1, row.v[ai++], bt[s]);
+                    sq0 = fma(c0, c0, sq0);
+                    sq1 = fma(c1, c1, sq1);
+                }
+                // C fragment: rows g (+ 8 b), columns 2 t and 2 t + 1 -> sum over the rows = lanes with equal t
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {
+                    const double y0 = __shfl_xor_sync(0xFFFFFFFFu, sq0, o), y1 = __shfl_xor_sync(0xFFFFFFFFu, sq1, o);
+                    sq0 += y0;
+                    sq1 += y1;
+                }
+#pragma unroll
+                for (int p = 0; p < P; ++p) {
+                    const double qv = __shfl_sync(0xFFFFFFFFu, (p & 1) ? sq1 : sq0, p >> 1);  // column p: lanes with t = p / 2
+                    out[p] = Pm[0] - 0.5 * qv;
+                }
+                break;
+            }
             // residuals r_j^(p) -> scratch[j][p]
 #pragma unroll
             for (int s = 0; s < DPL; ++s) {

@@ -621,64 +621,41 @@ __global__ void __launch_bounds__(1024) k_chain_streams(StreamArgs a) {
         }
     }
     // phase 2: lanes = dimensions; direction of slice j+1 comes from after_key_j (:272), the first
-    // one from direction_key (:410-413).  Two directions per trip with the Threefry block inlined: this kernel is
-    // throughput code, and two independent Threefry / erf_inv / butterfly chains per warp keep the issue slots filled
-    // that a single dependent chain leaves empty.
+    // one from direction_key (:410-413).  (Two directions per trip with the Threefry block inlined was measured: no
+    // faster -- 32 warps per SM already fill the issue slots -- and the run 2 % slower.)
     const int jl0 = (base == 0) ? -1 : 0;
 #pragma unroll 1
-    for (int jl = jl0; jl < 32; jl += 2) {
-        Key k[2];
-        double *dst[2];
-        bool on[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int jj = jl + u;
-            const int jdst = base + jj + 1;  // slice that uses this direction
-            on[u] = jj < 32 && jdst < S;
-            if (jj < 0) {
-                k[u] = split_child(sample_key, 0);
-            } else {
-                k[u].a = __shfl_sync(0xFFFFFFFFu, after_key.a, jj & 31);
-                k[u].b = __shfl_sync(0xFFFFFFFFu, after_key.b, jj & 31);
-            }
-            dst[u] = a.dirs + (row * S + (on[u] ? jdst : 0)) * D;
+    for (int jl = jl0; jl < 32; ++jl) {
+        const int jdst = base + jl + 1;  // slice that uses this direction
+        if (jdst >= S) break;
+        Key k;
+        if (jl < 0) {
+            k = split_child(sample_key, 0);
+        } else {
+            k.a = __shfl_sync(0xFFFFFFFFu, after_key.a, jl);
+            k.b = __shfl_sync(0xFFFFFFFFu, after_key.b, jl);
         }
-        if (!on[0] && !on[1]) break;
+        double *dst = a.dirs + (row * S + jdst) * D;
         if (D == 1) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                if (on[u] && lane == 0) dst[u][0] = 1.0;
+            if (lane == 0) dst[0] = 1.0;
             continue;
         }
-        double v[2][QMAX];
-        double ss[2] = {0.0, 0.0};
+        double v[QMAX];
+        double ss = 0.0;
 #pragma unroll
         for (int q = 0; q < QMAX; ++q) {
             const int j = lane + 32 * q;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                uint32_t x0 = 0u, x1 = (uint32_t) j;  // bits64(k, j): threefry(key; hi(j), lo(j)), inlined
-                threefry2x32(k[u].a, k[u].b, x0, x1);
-                const uint64_t bits = ((uint64_t) x0 << 32) | (uint64_t) x1;
-                v[u][q] = (j < D) ? normal_from_bits(bits) : 0.0;
-                ss[u] = fma(v[u][q], v[u][q], ss[u]);
-            }
+            v[q] = (j < D) ? normal_from_bits(bits64(k, (uint64_t) j)) : 0.0;
+            ss = fma(v[q], v[q], ss);
             if (32 * (q + 1) >= D) break;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double y0 = __shfl_xor_sync(0xFFFFFFFFu, ss[0], o), y1 = __shfl_xor_sync(0xFFFFFFFFu, ss[1], o);
-            ss[0] += y0;
-            ss[1] += y1;
-        }
-        const double nrm0 = sqrt(ss[0]), nrm1 = sqrt(ss[1]);
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+        const double nrm = sqrt(ss);
 #pragma unroll
         for (int q = 0; q < QMAX; ++q) {
             const int j = lane + 32 * q;
-            if (j < D) {
-                if (on[0]) dst[0][j] = v[0][q] / nrm0;
-                if (on[1]) dst[1][j] = v[1][q] / nrm1;
-            }
+            if (j < D) dst[j] = v[q] / nrm;
             if (32 * (q + 1) >= D) break;
         }
     }
