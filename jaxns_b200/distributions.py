@@ -4,20 +4,61 @@ Minimal stand-in for the tensorflow_probability distributions the reference's Pr
 transform needs (event size + quantile parameters).  Real tfp objects are accepted too when they
 expose the same attributes (low/high, loc/scale, loc/scale_tril).
 """
+import math
+
 import numpy as np
 
 from jaxns_b200 import _consts
 
 
+def _is_tensor(x) -> bool:
+    return type(x).__module__.split(".")[0] == "torch"
+
+
+def _needs_general(*params) -> bool:
+    """A parameter that is a device tensor, or a placeholder of another prior's value (dependent priors), cannot be
+    packed into the static per-dimension quantile arrays: the model then evaluates its prior transform as batched
+    torch code (framework.Model general mode)."""
+    return any(_is_tensor(p) or getattr(p, "_nsb200_placeholder", False) for p in params)
+
+
+def _t(x, like=None):
+    import torch
+    dev = like.device if like is not None else ("cuda" if torch.cuda.is_available() else "cpu")
+    if _is_tensor(x):
+        return x.to(dtype=torch.float64, device=dev)
+    return torch.as_tensor(np.asarray(x, np.float64), dtype=torch.float64, device=dev)
+
+
+def _rows(x, like):
+    """parameter -> [1 or n, size] so that it broadcasts against a batch of draws [n, size]"""
+    x = _t(x, like)
+    if x.dim() == 0:
+        return x.reshape(1, 1)
+    if x.dim() == 1:
+        return x.reshape(1, -1)
+    return x
+
+
 class Distribution:
     prior_kind: int
+    dynamic = False  # parameters are tensors / other priors' values: only the torch path below can evaluate it
 
     def event_size(self) -> int:
-        return int(self._a.size)
+        return int(self._size)
 
     def quantile_params(self):
         """(prior_kind, a[D], b[D]) with X = a + b * U (uniform) or a + b * ndtri(U) (normal)."""
+        if self.dynamic or getattr(self, "_a", None) is None:
+            raise NotImplementedError("this prior has no static per-dimension quantile parameters")
         return self.prior_kind, self._a, self._b
+
+    # batched torch evaluation (general models, post-processing): U [n, size] -> X [n, size]; X -> log density [n]
+    def quantile_torch(self, U):
+        raise NotImplementedError
+
+    def log_prob_torch(self, X):
+        raise NotImplementedError
 
 
 class Uniform(Distribution):
@@ -25,11 +66,28 @@ class Uniform(Distribution):
     prior_kind = _consts.PRIOR_UNIFORM
 
     def __init__(self, low=0.0, high=1.0):
+        if _needs_general(low, high):
+            self.dynamic, self.low, self.high, self._a = True, low, high, None
+            self._size = max(1, *[int(p.shape[-1]) if _is_tensor(p) and p.dim() > 0 else int(np.size(p)) if not _is_tensor(p) else 1
+                                  for p in (low, high)])
+            return
         low, high = np.broadcast_arrays(np.asarray(low, np.float64), np.asarray(high, np.float64))
         self.low = np.atleast_1d(low).reshape(-1).copy()
         self.high = np.atleast_1d(high).reshape(-1).copy()
         self._a = self.low
         self._b = self.high - self.low
+        self._size = self._a.size
+
+    def quantile_torch(self, U):
+        low, high = _rows(self.low, U), _rows(self.high, U)
+        return low + (high - low) * U
+
+    def log_prob_torch(self, X):
+        import torch
+        low, high = _rows(self.low, X), _rows(self.high, X)
+        inside = (X >= low) & (X <= high)
+        lp = torch.where(inside, -torch.log(high - low).expand_as(X), torch.full_like(X, -math.inf))
+        return lp.sum(dim=-1)
 
     def log_prob(self, x):
         x = np.asarray(x, np.float64)
@@ -42,11 +100,27 @@ class Normal(Distribution):
     prior_kind = _consts.PRIOR_NORMAL
 
     def __init__(self, loc=0.0, scale=1.0):
+        if _needs_general(loc, scale):
+            self.dynamic, self.loc, self.scale, self._a = True, loc, scale, None
+            self._size = max(1, *[int(p.shape[-1]) if _is_tensor(p) and p.dim() > 0 else int(np.size(p)) if not _is_tensor(p) else 1
+                                  for p in (loc, scale)])
+            return
         loc, scale = np.broadcast_arrays(np.asarray(loc, np.float64), np.asarray(scale, np.float64))
         self.loc = np.atleast_1d(loc).reshape(-1).copy()
         self.scale = np.atleast_1d(scale).reshape(-1).copy()
         self._a = self.loc
         self._b = self.scale
+        self._size = self._a.size
+
+    def quantile_torch(self, U):
+        import torch
+        return _rows(self.loc, U) + _rows(self.scale, U) * torch.special.ndtri(U)
+
+    def log_prob_torch(self, X):
+        import torch
+        loc, scale = _rows(self.loc, X), _rows(self.scale, X)
+        z = (X - loc) / scale
+        return (-0.5 * z * z - torch.log(scale) - 0.5 * math.log(2.0 * math.pi)).expand_as(X).sum(dim=-1)
 
     def log_prob(self, x):
         z = (np.asarray(x, np.float64) - self.loc) / self.scale
@@ -66,9 +140,54 @@ class MultivariateNormalTriL(Normal):
     def __init__(self, loc, scale_tril):
         scale_tril = np.asarray(scale_tril, np.float64)
         if np.any(np.abs(scale_tril - np.diag(np.diag(scale_tril))) > 0):
-            raise NotImplementedError("MultivariateNormalTriL prior with a non-diagonal scale_tril is not "
-                                      "supported by the fused prior transform yet.")
+            # a dense factor is a matrix-vector product inside the prior transform: X = loc + L ndtri(U) (the reference's
+            # Sample(Normal) + TriL bijector, framework/tests/test_prior.py:93-103) -- evaluated by the torch path
+            self.dynamic, self._a = True, None
+            self.loc = np.atleast_1d(np.asarray(loc, np.float64)).reshape(-1)
+            self.scale_tril = np.tril(scale_tril)
+            self._size = self.scale_tril.shape[0]
+            return
         super().__init__(loc, np.diag(scale_tril))
+        self.scale_tril = scale_tril
+
+    def quantile_torch(self, U):
+        import torch
+        if not self.dynamic:
+            return super().quantile_torch(U)
+        return _rows(self.loc, U) + torch.special.ndtri(U) @ _t(self.scale_tril, U).T
+
+    def log_prob_torch(self, X):
+        import torch
+        if not self.dynamic:
+            return super().log_prob_torch(X)
+        L = _t(self.scale_tril, X)
+        z = torch.linalg.solve_triangular(L, (X - _rows(self.loc, X)).T, upper=False).T
+        return -0.5 * (z * z).sum(dim=-1) - torch.log(torch.diagonal(L)).sum() - 0.5 * L.shape[0] * math.log(2.0 * math.pi)
+
+
+class MultivariateNormalFullCovariance(MultivariateNormalTriL):
+    def __init__(self, loc, covariance_matrix):
+        super().__init__(loc, np.linalg.cholesky(np.asarray(covariance_matrix, np.float64)))
+
+
+class Constant(Distribution):
+    """Prior(value): a SingularPrior of the reference (framework/prior.py) -- no U dimensions, the value itself."""
+    dynamic = True
+    prior_kind = None
+
+    def __init__(self, value):
+        self.value = value
+        self._size = 0
+        self._a = None
+
+    def quantile_torch(self, U):
+        v = _t(self.value, U)
+        v = v.reshape(1, -1) if v.dim() < 2 else v
+        return v.expand(U.shape[0], v.shape[-1]) if v.shape[0] == 1 else v
+
+    def log_prob_torch(self, X):
+        import torch
+        return torch.zeros(X.shape[0], dtype=torch.float64, device=X.device)
 
 
 def from_any(dist) -> Distribution:
@@ -82,4 +201,6 @@ def from_any(dist) -> Distribution:
         return MultivariateNormalTriL(np.asarray(dist.loc), np.asarray(dist.scale_tril))
     if hasattr(dist, "loc") and hasattr(dist, "scale"):
         return Normal(np.asarray(dist.loc), np.asarray(dist.scale))
+    if _is_tensor(dist) or isinstance(dist, (int, float, np.ndarray, list, tuple)):
+        return Constant(dist)
     raise NotImplementedError(f"Unsupported prior distribution {name}")

@@ -19,11 +19,24 @@ from jaxns_b200.likelihoods import ExternalLikelihood, RegisteredLikelihood
 __all__ = ["Prior", "Model"]
 
 
+class _NeedsGeneral(Exception):
+    """The prior model does arithmetic on its variables or feeds them into other priors: it cannot be reduced to the
+    static per-dimension quantile arrays and is evaluated as batched torch code instead."""
+
+
 class _Var:
-    """Placeholder sent into the prior_model generator for a yielded Prior."""
+    """Placeholder sent into the prior_model generator for a yielded Prior (static analysis pass)."""
+    _nsb200_placeholder = True
 
     def __init__(self, index: int, size: int, name: Optional[str]):
         self.index, self.size, self.name = index, size, name
+
+    def _general(self, *args, **kwargs):
+        raise _NeedsGeneral()
+
+    __add__ = __radd__ = __sub__ = __rsub__ = __mul__ = __rmul__ = __truediv__ = __rtruediv__ = _general
+    __pow__ = __rpow__ = __neg__ = __abs__ = __getitem__ = __matmul__ = __rmatmul__ = __array__ = _general
+    __iter__ = __len__ = __float__ = _general
 
 
 class Prior:
@@ -47,21 +60,41 @@ class Model:
             log_likelihood = ExternalLikelihood(log_likelihood)
         self.prior_model = prior_model
         self.log_likelihood = log_likelihood
+        self.is_external = isinstance(log_likelihood, ExternalLikelihood)
+        self.is_general = False
         self._priors: List[Prior] = []
-        gen = prior_model()
+        try:
+            self._analyse_static()
+        except _NeedsGeneral:
+            if not self.is_external:
+                raise NotImplementedError(
+                    "Registered likelihood families are fused with per-dimension Uniform / Normal quantile transforms; "
+                    "dependent, mixed or dense-MVN priors need a callable likelihood (evaluated between the propose and "
+                    "accept kernels).")
+            self._analyse_general()
+        self._dev = None
+
+    def _analyse_static(self):
+        """Drive the generator once with placeholders: works when every prior has constant parameters and the model
+        returns its variables as they are -- then U -> X is the kernels' per-dimension quantile transform."""
+        self._priors = []
+        gen = self.prior_model()
         try:
             p = next(gen)
             while True:
                 if not isinstance(p, Prior):
                     raise TypeError(f"prior_model must yield Prior objects, got {type(p)}")
+                if p.dist.dynamic:
+                    raise _NeedsGeneral()
                 v = _Var(len(self._priors), p.dist.event_size(), p.name)
                 self._priors.append(p)
                 p = gen.send(v)
         except StopIteration as stop:
             ret = stop.value
         ret = ret if isinstance(ret, tuple) else (ret,)
-        self.is_external = isinstance(log_likelihood, ExternalLikelihood)
         if not all(isinstance(r, _Var) for r in ret):
+            if self.is_external:
+                raise _NeedsGeneral()
             raise NotImplementedError("prior_model must return (a tuple of) its yielded variables.")
         if not self.is_external and [r.index for r in ret] != list(range(len(self._priors))):
             raise NotImplementedError("prior_model must return its yielded variables in order: the registered "
@@ -70,13 +103,74 @@ class Model:
         self._ret_slices = [(int(offs[r.index]), int(offs[r.index + 1])) for r in ret]
         kinds = {p.dist.prior_kind for p in self._priors}
         if len(kinds) != 1:
-            raise NotImplementedError("Mixing Uniform and Normal priors in one model is not supported yet.")
+            if self.is_external:
+                raise _NeedsGeneral()
+            raise NotImplementedError("Mixing Uniform and Normal priors in one model needs a callable likelihood.")
         self._prior_kind = kinds.pop()
         self._a = np.concatenate([p.dist.quantile_params()[1] for p in self._priors])
         self._b = np.concatenate([p.dist.quantile_params()[2] for p in self._priors])
         self._D = int(self._a.size)
-        self._params_host = np.ascontiguousarray(log_likelihood.pack(self._D), np.float64)
-        self._dev = None
+        self._params_host = np.ascontiguousarray(self.log_likelihood.pack(self._D), np.float64)
+
+    def _analyse_general(self):
+        """General models (framework/ops.py:240-326 with arbitrary generators): the prior transform IS the generator,
+        run on batched device tensors -- every yielded Prior's quantile at its slice of U, its value sent back in, the
+        returned expressions handed to the likelihood.  The slice kernels only ever see U (propose / accept), so
+        dependent priors (tests/conftest.py:144-177 `basic3`), mixed families, dense MVN priors, constants and
+        re-ordered or derived return values all work; the kernels get a Uniform(0, 1) descriptor of the right width."""
+        self.is_general = True
+        _, named, _, sizes = self._run_generator(None)
+        self._D = int(sum(sizes))
+        self._names = list(named.keys())
+        self._prior_kind = distributions.Uniform.prior_kind
+        self._a = np.zeros(self._D)
+        self._b = np.ones(self._D)
+        self._params_host = np.zeros(0)
+        self._ret_slices = None
+
+    def _run_generator(self, U):
+        """One batched pass through the prior model.  U [n, D] on the device (None: a shape-discovery pass at U = 1/2).
+        Returns (likelihood inputs, {name: X}, log prior density [n], event sizes)."""
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        probe = U is None
+        n = 1 if probe else U.shape[0]
+        gen = self.prior_model()
+        named, sizes, o = {}, [], 0
+        log_prior = torch.zeros(n, dtype=torch.float64, device=dev if probe else U.device)
+        try:
+            p = next(gen)
+            while True:
+                if not isinstance(p, Prior):
+                    raise TypeError(f"prior_model must yield Prior objects, got {type(p)}")
+                size = p.dist.event_size()
+                u = torch.full((1, size), 0.5, dtype=torch.float64, device=dev) if probe else U[:, o:o + size]
+                x = p.dist.quantile_torch(u)
+                if x.shape[0] != n:
+                    x = x.expand(n, x.shape[-1])
+                log_prior = log_prior + p.dist.log_prob_torch(x)
+                if p.name is not None:
+                    named[p.name] = x
+                sizes.append(size)
+                o += size
+                p = gen.send(x)
+        except StopIteration as stop:
+            ret = stop.value
+        ret = ret if isinstance(ret, tuple) else (ret,)
+        return ret, named, log_prior, sizes
+
+    def _general_log_likelihood(self, U: torch.Tensor) -> torch.Tensor:
+        ret, _, _, _ = self._run_generator(U)
+        out = self.log_likelihood.fn(*ret)
+        out = torch.as_tensor(out, dtype=torch.float64, device=U.device)
+        out = out.expand(U.shape[0]) if out.dim() == 0 else out.reshape(-1)
+        if out.numel() != U.shape[0]:
+            raise ValueError(f"log_likelihood must return one value per row: got {out.numel()} for {U.shape[0]} rows")
+        return torch.nan_to_num(out, nan=-float("inf"), posinf=float("inf"), neginf=-float("inf")).contiguous()
+
+    def external_log_likelihood(self, U: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
+        """log L of a batch of proposals for the split slice step: U [n, D] in the unit cube, X = the kernels'
+        per-dimension transform of U (what static models consume; general models run their own transform on U)."""
+        return self._general_log_likelihood(U) if self.is_general else self.call_likelihood(X)
 
     # -- reference properties -----------------------------------------------------------------
     @property
@@ -131,6 +225,11 @@ class Model:
         batched = U.dim() == 2
         U2 = U.reshape(-1, self._D).contiguous()
         n = U2.shape[0]
+        if self.is_general:
+            logL = self._general_log_likelihood(U2) if want_L else None
+            if not batched:
+                return (logL[0] if want_L else None), None
+            return logL, None
         d = self.desc()
         if self.is_external:
             X = torch.empty_like(U2)
@@ -159,6 +258,10 @@ class Model:
 
     def transform(self, U):
         """U -> X dict keyed by prior names (framework/model.py:155-159)."""
+        if self.is_general:
+            U = torch.as_tensor(U, dtype=torch.float64, device="cuda")
+            _, named, _, _ = self._run_generator(U.reshape(-1, self._D))
+            return named if U.dim() == 2 else {k: v[0] for k, v in named.items()}
         X = self._forward_batch(U, True, False)[1]
         out, o = {}, 0
         for i, p in enumerate(self._priors):
@@ -172,6 +275,10 @@ class Model:
         return {}
 
     def prepare_input(self, U):
+        if self.is_general:
+            U = torch.as_tensor(U, dtype=torch.float64, device="cuda")
+            ret = self._run_generator(U.reshape(-1, self._D))[0]
+            return ret if U.dim() == 2 else tuple(r[0] for r in ret)
         return (self._forward_batch(U, True, False)[1],)
 
     def sample_U(self, key):
@@ -183,6 +290,10 @@ class Model:
         """Prior log density of the transformed point (framework/model.py:178-187), evaluated on the device
         (post-processing for NestedSamplerResults.log_posterior_density; small torch reductions)."""
         import math
+        if self.is_general:
+            U = torch.as_tensor(U, dtype=torch.float64, device="cuda")
+            lp = self._run_generator(U.reshape(-1, self._D))[2]
+            return lp if U.dim() == 2 else lp[0]
         X = self._forward_batch(U, True, False)[1]
         a = self._dev[0]
         b = self._dev[1]

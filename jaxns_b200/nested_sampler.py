@@ -339,7 +339,7 @@ class ShardedStaticNestedSampler:
         _lib.check(L.nsb200_init_propose(ctypes.byref(d), _lib.key_arg(sample_key), ctypes.c_int64(N), ctypes.c_int64(0),
                                          ctypes.c_int64(N), ctypes.c_int32(0), ctypes.c_void_p(0), _lib.ptr(U),
                                          _lib.ptr(X), st))
-        logL = self.model.call_likelihood(X)
+        logL = self.model.external_log_likelihood(U, X)
         rnd = 0
         while True:
             need = torch.isneginf(logL)  # `while log_L <= -inf` (uniform_sample.py:40-43)
@@ -352,7 +352,7 @@ class ShardedStaticNestedSampler:
             _lib.check(L.nsb200_init_propose(ctypes.byref(d), _lib.key_arg(sample_key), ctypes.c_int64(N),
                                              ctypes.c_int64(0), ctypes.c_int64(N), ctypes.c_int32(rnd), _lib.ptr(need8),
                                              _lib.ptr(U), _lib.ptr(X), st))
-            logL = torch.where(need, self.model.call_likelihood(X), logL)
+            logL = torch.where(need, self.model.external_log_likelihood(U, X), logL)
             nev += need.to(torch.int64)
         return U, logL.contiguous(), nev
 
@@ -382,7 +382,7 @@ class ShardedStaticNestedSampler:
             _lib.check(L.nsb200_engine_split_begin(eng.h, _lib.ptr(prop_U), _lib.ptr(prop_X), stream))
             while True:
                 for r in range(burst):
-                    logL = self.model.call_likelihood(prop_X)
+                    logL = self.model.external_log_likelihood(prop_U, prop_X)
                     last = r == burst - 1
                     if last:
                         active.zero_()

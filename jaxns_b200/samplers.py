@@ -153,7 +153,7 @@ class UniDimSliceSampler(AbstractSampler):
         burst = max(4, self.num_slices // 4)  # likelihood rounds between reads of the active-chain counter
         while True:
             for r in range(burst):
-                logL = self.model.call_likelihood(prop_X)
+                logL = self.model.external_log_likelihood(prop_U, prop_X)
                 last = r == burst - 1
                 if last:
                     active.zero_()
