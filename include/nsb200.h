@@ -64,7 +64,7 @@ typedef struct NsSliceParams {
     int32_t num_slices;      /* S */
     int32_t num_phantom;     /* k (num_phantom_save) */
     int32_t midpoint_shrink; /* bool */
-    int32_t reserved;
+    int32_t gradient_flags;  /* split path only: bit 0 = gradient_slice, bit 1 = gradient_guided (:202-214, :255-269) */
     int64_t num_live;    /* N: rows of live_U / live_logL (sorted ascending) */
     int64_t num_samples; /* m: keys = split(key, m) */
     int64_t chain_begin; /* this GPU evaluates chains [chain_begin, chain_end) -- the */
@@ -258,6 +258,21 @@ int nsb200_split_accept(const NsModelDesc *model, const NsSliceParams *p, const 
 int nsb200_split_finish(const NsModelDesc *model, const NsSliceParams *p, void *workspace,
                         int64_t workspace_bytes, double *out_U, double *out_logL, int64_t *out_nevals,
                         double *ph_U, double *ph_logL, nsb200_stream_t stream);
+/* Gradient variants of UniDimSliceSampler (samplers/uni_slice_sampler.py:202-214 gradient_slice: the slice direction is
+ * the normalised gradient of log L w.r.t. U at the chain's point and only the uphill half of the bracket is searched;
+ * :255-269 gradient_guided: the next direction is the Householder reflection of the last one about the gradient at the
+ * accepted point).  With NsSliceParams.gradient_flags != 0 a chain that is about to start a slice waits for the
+ * caller's gradient (jax.grad in the reference; any autodiff of the batched likelihood here):
+ *     nsb200_split_begin, then per round:
+ *         nsb200_split_grad_points -> U0 [n,D]; caller: grad [n,D] = d log L / dU at U0
+ *         nsb200_split_grad_begin  -> waiting chains start their slice (first proposals into prop_U / prop_X)
+ *         caller: prop_logL;  nsb200_split_accept  (accepting chains wait again)
+ * Every gradient counts as one likelihood evaluation, as in the reference. */
+int nsb200_split_grad_points(const NsModelDesc *model, const NsSliceParams *p, void *workspace, int64_t workspace_bytes,
+                             double *out_U, nsb200_stream_t stream);
+int nsb200_split_grad_begin(const NsModelDesc *model, const NsSliceParams *p, const double *contour, const double *grad,
+                            void *workspace, int64_t workspace_bytes, double *prop_U, double *prop_X, uint64_t *n_active,
+                            nsb200_stream_t stream);
 /* Redraw round `round` (0 = first draw) of _single_uniform_sample (common/uniform_sample.py:12-60) for
  * prior draws [begin, end) of split(sample_key, N); rows with need[i - begin] == 0 are left untouched
  * (need == NULL: all rows).  out_U / out_X [end - begin, D] (out_X optional). */
@@ -360,6 +375,11 @@ int nsb200_engine_split_begin(NsEngine *e, double *prop_U, double *prop_X, nsb20
 int nsb200_engine_split_accept(NsEngine *e, const double *prop_logL, double *prop_U, double *prop_X,
                                uint64_t *n_active, nsb200_stream_t stream);
 int nsb200_engine_split_finish(NsEngine *e, nsb200_stream_t stream);
+/* The same gradient protocol for an engine with model.family == NSB200_FAM_EXTERNAL (flags: bit 0 slice, bit 1 guided). */
+int nsb200_engine_set_gradient_flags(NsEngine *e, int32_t flags);
+int nsb200_engine_split_grad_points(NsEngine *e, double *out_U, nsb200_stream_t stream);
+int nsb200_engine_split_grad_begin(NsEngine *e, const double *grad, double *prop_U, double *prop_X, uint64_t *n_active,
+                                   nsb200_stream_t stream);
 /* Final live-set append (sharded_static.py:834-838). */
 int nsb200_engine_finalize(NsEngine *e, nsb200_stream_t stream);
 /* Non-blocking progress of the enqueued bodies: *completed = bodies whose register update has run on the

@@ -16,7 +16,8 @@
 
 namespace nsb {
 
-constexpr int kSplitWords = 12;  // u32 per chain: j, ne, done, pad, run_key[2], after_key[2], sample_key2[2], pad[2]
+// u32 per chain: j, ne, done, watchdog, run_key[2], after_key[2], sample_key2[2], need_grad, first_slice
+constexpr int kSplitWords = 12;
 
 // Struct-of-arrays view of the per-chain state inside the caller's workspace.
 struct SplitState {
@@ -78,10 +79,17 @@ struct SplitArgs {
     double *prop_U;                   // [n, D] proposals in U space (out)
     double *prop_X;                   // [n, D] proposals through the prior transform (out, optional)
     unsigned long long *active;       // optional device counter: += chains that still need evaluations
+    // gradient variants (uni_slice_sampler.py:202-214 gradient_slice = bit 0, :255-269 gradient_guided = bit 1): a chain
+    // that starts a slice waits (need_grad) until the caller has evaluated d log L / dU at its current point
+    // (k_split_export_U0 -> caller's autodiff -> mode 2)
+    int grad_flags;
+    const double *grad;               // mode 2: [n, D] gradient of log L w.r.t. U at the chains' current points
 };
 
 // mode 0: chain prelude (seed choice, first direction) + first proposal of slice 0
 // mode 1: accept or shrink on prop_logL, then the next proposal (of this or the next slice)
+// mode 2: (gradient variants) start the slice of every chain that waits for its gradient: Householder reflection of
+//         the last direction at the accepted point (gradient_guided), gradient direction with left = 0 (gradient_slice)
 template <int G, int DPL>
 __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, int mode) {
     extern __shared__ double smem[];
@@ -118,7 +126,65 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
     double left, right, t, logL0;
     long long nev;
     bool new_slice;
-    if (mode == 0) {
+    bool climb = false;  // gradient_slice with a usable gradient: only the uphill half of the bracket (left = 0)
+    if (mode == 2) {
+        if (st[2] || !st[10]) return;
+        const bool first = st[11] != 0;
+        j = (int) st[0];
+        ne = 0;
+        run_key = Key{st[4], st[5]};
+        after_key = Key{st[6], st[7]};
+        sk2 = Key{st[8], st[9]};
+        left = right = t = 0.0;
+        logL0 = sc[3];
+        nev = a.state.nev[row];
+        double gv[DPL];
+        double ss = 0.0;
+#pragma unroll
+        for (int s = 0; s < DPL; ++s) {
+            const int jj = s * G + g.lane;
+            U0[s] = (jj < D) ? a.state.U0[row * D + jj] : 0.5;
+            d[s] = (jj < D) ? a.state.d[row * D + jj] : 0.0;
+            gv[s] = (jj < D) ? a.grad[row * D + jj] : 0.0;
+            ss = fma(gv[s], gv[s], ss);
+        }
+        const double gn = sqrt(group_sum(g, ss));
+        const bool finite = (gn - gn == 0.0);
+        if (!first) {  // direction after the slice that just ended (:255-272)
+            if (a.grad_flags & 2) {
+                const Key after_key1 = split_child(after_key, 0);
+                double rnd[DPL];
+                sample_direction<G, DPL>(g, D, after_key1, rnd);
+                const bool mask = !(gn >= 1e-10) || !finite;
+                double dot = 0.0;
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) dot = fma(d[s], gv[s] / gn, dot);
+                dot = group_sum(g, dot);
+                double refl[DPL], rs = 0.0;
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    refl[s] = d[s] - 2.0 * dot * (gv[s] / gn);
+                    rs = fma(refl[s], refl[s], rs);
+                }
+                const double rn = sqrt(group_sum(g, rs));
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) d[s] = mask ? rnd[s] : refl[s] / rn;
+                nev += 1;
+            } else {
+                sample_direction<G, DPL>(g, D, after_key, d);
+            }
+        }
+        if (a.grad_flags & 1) {  // climb the gradient (:202-214)
+            nev += 1;
+            const bool mask = (gn == 0.0) || !finite;
+            if (!mask) {
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) d[s] = gv[s] / gn;
+                climb = true;
+            }
+        }
+        new_slice = true;
+    } else if (mode == 0) {
         // ---- chain prelude (bases.py:64; uni_slice_sampler.py:343-358, :410-413)
         const Key chain_key = split_child(base_key, (uint64_t) chain);
         const Key sample_key = split_child(chain_key, 0);
@@ -140,7 +206,35 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         run_key = after_key = Key{0, 0};
         left = right = t = 0.0;
         new_slice = true;
+        if (a.grad_flags) {  // the first slice starts in mode 2, once the gradient at the seed point is known
+#pragma unroll
+            for (int s = 0; s < DPL; ++s) {
+                const int jj = s * G + g.lane;
+                if (jj < D) {
+                    a.state.U0[row * D + jj] = U0[s];
+                    a.state.d[row * D + jj] = d[s];
+                    a.prop_U[row * D + jj] = U0[s];
+                }
+            }
+            if (g.lane == 0) {
+                st[0] = 0u;
+                st[1] = 0u;
+                st[2] = 0u;
+                st[3] = 0u;
+                st[4] = st[5] = st[6] = st[7] = 0u;
+                st[8] = sk2.a;
+                st[9] = sk2.b;
+                st[10] = 1u;
+                st[11] = 1u;
+                sc[0] = sc[1] = sc[2] = 0.0;
+                sc[3] = logL0;
+                a.state.nev[row] = 0;
+                if (a.active) atomicAdd(a.active, 1ull);
+            }
+            return;
+        }
     } else {
+        if (st[10]) return;  // waits for its gradient (mode 2)
         if (st[2]) {  // chain finished: prop_U keeps its final point
             // a chain stopped by the shrink-loop watchdog keeps reporting it through bit 62 of the active counter
             if (st[3] && a.active && g.lane == 0) atomicOr(a.active, 1ull << 62);
@@ -185,6 +279,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
             }
             j += 1;
             if (j == S) {
+                if (a.grad_flags & 2) nev += 1;  // the reflection at the last accepted point is still evaluated (:257-258)
 #pragma unroll
                 for (int s = 0; s < DPL; ++s) {
                     const int jj = s * G + g.lane;
@@ -195,6 +290,26 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
                     st[2] = 1u;
                     sc[3] = logL0;
                     a.state.nev[row] = nev;
+                }
+                return;
+            }
+            if (a.grad_flags) {  // the next slice starts in mode 2 with the gradient at the accepted point
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int jj = s * G + g.lane;
+                    if (jj < D) {
+                        a.state.U0[row * D + jj] = U0[s];
+                        a.prop_U[row * D + jj] = U0[s];
+                    }
+                }
+                if (g.lane == 0) {
+                    st[0] = (uint32_t) j;
+                    st[1] = 0u;
+                    st[10] = 1u;
+                    st[11] = 0u;
+                    sc[3] = logL0;
+                    a.state.nev[row] = nev;
+                    if (a.active) atomicAdd(a.active, 1ull);
                 }
                 return;
             }
@@ -236,6 +351,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         const Key t_key = split_child(slice_key, 2);
         after_key = split_child(slice_key, 3);
         slice_bounds<G, DPL>(g, D, U0, d, left, right);
+        if (climb) left = 0.0;  // :214
         const double uu = uniform01(t_key, 0);
         t = left + uu * (right - left);  // _pick_point_in_interval :83-85
         ne = 1;
@@ -267,6 +383,8 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         st[1] = (uint32_t) ne;
         st[2] = 0u;
         st[3] = 0u;
+        st[10] = 0u;
+        st[11] = 0u;
         st[4] = run_key.a;
         st[5] = run_key.b;
         st[6] = after_key.a;
@@ -280,6 +398,13 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         a.state.nev[row] = nev;
         if (a.active) atomicAdd(a.active, 1ull);
     }
+}
+
+// Current points of the chains (where the caller evaluates d log L / dU for the gradient variants).
+__global__ void k_split_export_U0(const DevCtl *ctl, SplitState s, long long n, int D, double *out_U) {
+    if (ctl && !ctl->active) return;
+    const long long stride = (long long) gridDim.x * blockDim.x;
+    for (long long e = (long long) blockIdx.x * blockDim.x + threadIdx.x; e < n * D; e += stride) out_U[e] = s.U0[e];
 }
 
 // Chain results out of the workspace: plain arrays (B1) and/or packed gather rows (engine).

@@ -735,6 +735,7 @@ static int split_args(const NsModelDesc *model, const NsSliceParams *p, void *wo
     a.S = p->num_slices;
     a.k = p->num_phantom;
     a.midpoint = p->midpoint_shrink;
+    a.grad_flags = p->gradient_flags & 3;
     a.state = split_state_view(workspace, model->D, n, p->num_phantom);
     return 0;
 }
@@ -771,6 +772,33 @@ extern "C" int nsb200_split_accept(const NsModelDesc *model, const NsSliceParams
     a.prop_X = prop_X;
     a.active = (unsigned long long *) n_active;
     return launch_split_step(a, 1, (cudaStream_t) stream);
+}
+
+extern "C" int nsb200_split_grad_points(const NsModelDesc *model, const NsSliceParams *p, void *workspace,
+                                        int64_t workspace_bytes, double *out_U, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
+    if (!out_U) return fail("out_U is NULL");
+    const long long n = p->chain_end - p->chain_begin;
+    if (n <= 0) return 0;
+    k_split_export_U0<<<296, 256, 0, (cudaStream_t) stream>>>(nullptr, a.state, n, model->D, out_U);
+    NSB_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int nsb200_split_grad_begin(const NsModelDesc *model, const NsSliceParams *p, const double *contour,
+                                       const double *grad, void *workspace, int64_t workspace_bytes, double *prop_U,
+                                       double *prop_X, uint64_t *n_active, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
+    if (!a.grad_flags) return fail("nsb200_split_grad_begin needs NsSliceParams.gradient_flags != 0");
+    if (!contour || !grad || !prop_U) return fail("NULL pointer");
+    a.contour = contour;
+    a.grad = grad;
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    a.active = (unsigned long long *) n_active;
+    return launch_split_step(a, 2, (cudaStream_t) stream);
 }
 
 extern "C" int nsb200_split_finish(const NsModelDesc *model, const NsSliceParams *p, void *workspace,
@@ -1100,6 +1128,7 @@ struct NsEngine {
     bool tables_ready = false;  // seed table / evidence-term tables / alpha table depend only on (N, S): built once
     // family EXTERNAL: chain state of the split slice step (ns_split.cuh) for this rank's chains
     bool external = false;
+    int grad_flags = 0;  // gradient_slice (1) / gradient_guided (2) chains: nsb200_engine_set_gradient_flags
     void *split_ws = nullptr;
     size_t split_ws_bytes = 0;
 };
@@ -1849,8 +1878,41 @@ static int engine_split_args(NsEngine *e, SplitArgs &a) {
     a.ctl = e->ctl;
     a.live0 = e->live[0];
     a.live1 = e->live[1];
+    a.grad_flags = e->grad_flags;
     a.state = split_state_view(e->split_ws, e->D, e->rows_per_rank, (int) e->k);
     return 0;
+}
+
+extern "C" int nsb200_engine_set_gradient_flags(NsEngine *e, int32_t flags) {
+    if (!e) return fail("NULL engine");
+    if (!e->external) return fail("gradient variants run on the split path: create the engine with family EXTERNAL");
+    if (flags < 0 || flags > 3) return fail("gradient flags: bit 0 = gradient_slice, bit 1 = gradient_guided");
+    e->grad_flags = flags;
+    return 0;
+}
+
+extern "C" int nsb200_engine_split_grad_points(NsEngine *e, double *out_U, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (engine_split_args(e, a)) return 1;
+    if (!out_U) return fail("out_U is NULL");
+    k_split_export_U0<<<296, 256, 0, (cudaStream_t) stream>>>(e->ctl, a.state, e->rows_per_rank, e->D, out_U);
+    NSB_LAUNCH_CHECK();
+    e->all_launches += 1;
+    return 0;
+}
+
+extern "C" int nsb200_engine_split_grad_begin(NsEngine *e, const double *grad, double *prop_U, double *prop_X,
+                                              uint64_t *n_active, nsb200_stream_t stream) {
+    SplitArgs a;
+    if (engine_split_args(e, a)) return 1;
+    if (!a.grad_flags) return fail("nsb200_engine_set_gradient_flags first");
+    if (!grad || !prop_U) return fail("NULL pointer");
+    a.grad = grad;
+    a.prop_U = prop_U;
+    a.prop_X = prop_X;
+    a.active = (unsigned long long *) n_active;
+    e->all_launches += 1;
+    return launch_split_step(a, 2, (cudaStream_t) stream);
 }
 
 extern "C" int nsb200_engine_split_begin(NsEngine *e, double *prop_U, double *prop_X, nsb200_stream_t stream) {

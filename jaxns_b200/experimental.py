@@ -7,10 +7,12 @@ store of only 10 x num_search_chains rows that wraps around (max_samples=None tu
 sharded_static.py:76-78, global_optimisation.py:163-172), termination on likelihood evaluations / contour / spread /
 efficiency, and "the result" = the best stored point instead of an evidence.
 
-Not built: the gradient-based fine-tune (global_optimisation.py:56-73: Newton-CG on jax.grad of the user likelihood)
-and gradient_slice / gradient_guided chains (uni_slice_sampler.py:202-214,255-269) -- they need gradients of the
-likelihood, which the fused families do not provide yet; asking for them raises NotImplementedError.  EvidenceMaximisation
-needs parametrised models (framework/context.py), out of the hot-path scope.
+gradient_slice chains (uni_slice_sampler.py:202-214, the reference's default for GlobalOptimisation) run through the
+split propose / accept kernels with Model.grad_U between them; the fine-tune (global_optimisation.py:56-73) is a
+Newton-CG descent of -log L over the quick_unit-unconstrained cube (internals/constraint_bijections.py:11-40), written
+here with torch autograd Hessian-vector products -- the reference's own newton_cg_solver is not restated step for step,
+so the fine-tuned point agrees with the reference's only to the optimiser's tolerance.  EvidenceMaximisation needs
+parametrised models (framework/context.py), out of the hot-path scope.
 """
 import dataclasses
 import io
@@ -24,7 +26,8 @@ from jaxns_b200.samplers import AbstractSampler, UniDimSliceSampler
 from jaxns_b200.types import SampleCollection, TerminationCondition
 
 __all__ = ["GlobalOptimisationResults", "GlobalOptimisationTerminationCondition", "GlobalOptimisationState",
-           "SimpleGlobalOptimisation", "GlobalOptimisation", "DefaultGlobalOptimisation", "go_summary"]
+           "SimpleGlobalOptimisation", "GlobalOptimisation", "DefaultGlobalOptimisation", "go_summary",
+           "gradient_based_optimisation", "quick_unit", "quick_unit_inverse"]
 
 
 class GlobalOptimisationState(NamedTuple):
@@ -57,6 +60,76 @@ class GlobalOptimisationTerminationCondition(NamedTuple):
     min_efficiency: Optional[float] = None
 
 
+def quick_unit(x):
+    """internals/constraint_bijections.py:11-21: a cheap sigmoid, R -> (0, 1)."""
+    return 0.5 * (x / (1 + torch.abs(x)) + 1)
+
+
+def quick_unit_inverse(y):
+    """internals/constraint_bijections.py:24-40."""
+    twoy = y + y
+    return torch.where(y >= 0.5, (1 - twoy) / (twoy - 2), 1 - 1 / twoy)
+
+
+def gradient_based_optimisation(model, init_U_point, max_iters: int = 100, cg_iters: int = 50, gtol: float = 1e-10):
+    """global_optimisation.py:56-73: minimise -log L(quick_unit(z)) from z0 = quick_unit_inverse(U) by Newton-CG.
+    Each outer step solves H p = -g by conjugate gradients on autograd Hessian-vector products (stopping at negative
+    curvature or the Eisenstat-Walker residual), then backtracks on the step length until the loss decreases.
+    Returns (U, log L, number of function evaluations counted as the reference does: 4 per CG iteration)."""
+    z = quick_unit_inverse(torch.as_tensor(init_U_point, dtype=torch.float64, device="cuda").reshape(1, -1)).clone()
+
+    def loss_of(zz):
+        return -model.log_likelihood_torch(quick_unit(zz))[0]
+
+    n_cg = 0
+    f = float(loss_of(z))
+    for _ in range(max_iters):
+        zz = z.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            fz = loss_of(zz)
+            (g,) = torch.autograd.grad(fz, zz, create_graph=True)
+        gn = float(g.detach().norm())
+        if not math.isfinite(gn) or gn < gtol:
+            break
+
+        def hvp(v):
+            (hv,) = torch.autograd.grad(g, zz, grad_outputs=v, retain_graph=True)
+            return hv
+
+        p = torch.zeros_like(z)
+        r = g.detach().clone()
+        d = -r
+        rr = float((r * r).sum())
+        tol = min(0.5, math.sqrt(gn)) * gn
+        for _ in range(cg_iters):
+            n_cg += 1
+            Hd = hvp(d)
+            curv = float((d * Hd).sum())
+            if curv <= 0:
+                if float(p.abs().sum()) == 0.0:
+                    p = -g.detach()  # steepest descent when the first direction already has negative curvature
+                break
+            alpha = rr / curv
+            p = p + alpha * d
+            r = r + alpha * Hd
+            rr_new = float((r * r).sum())
+            if math.sqrt(rr_new) < tol:
+                break
+            d = -r + (rr_new / rr) * d
+            rr = rr_new
+        step, improved = 1.0, False
+        for _ in range(30):
+            f_new = float(loss_of(z + step * p))
+            if math.isfinite(f_new) and f_new < f:
+                z, f, improved = z + step * p, f_new, True
+                break
+            step *= 0.5
+        if not improved:
+            break
+    U = quick_unit(z)[0].detach()
+    return U, -f, 4 * n_cg
+
+
 @dataclasses.dataclass(eq=False)
 class SimpleGlobalOptimisation:
     """global_optimisation.py:76-182."""
@@ -83,7 +156,12 @@ class SimpleGlobalOptimisation:
         )
 
     def _gradient_descent(self, results: GlobalOptimisationResults) -> GlobalOptimisationResults:
-        raise NotImplementedError("The Newton-CG fine-tune needs gradients of the likelihood (not built).")
+        """global_optimisation.py:103-115."""
+        U_solution, log_L_solution, n_evals = gradient_based_optimisation(self.model, results.U_solution)
+        return results._replace(
+            U_solution=U_solution, log_L_solution=log_L_solution, X_solution=self.model.transform(U_solution),
+            solution=self.model.prepare_input(U_solution),
+            num_likelihood_evaluations=results.num_likelihood_evaluations + n_evals)
 
     def _to_results(self, termination_reason, state: GlobalOptimisationState) -> GlobalOptimisationResults:
         """global_optimisation.py:118-147: best stored point; the store may have wrapped, so only the rows written
@@ -192,31 +270,28 @@ def go_summary(results: GlobalOptimisationResults, f_obj: Optional[Union[str, Te
 
 @dataclasses.dataclass(eq=False)
 class GlobalOptimisation:
-    """experimental/public.py:20-140.  `gradient_slice` defaults to False here (the reference's default True needs
-    gradients of the likelihood); the other defaults follow the reference's non-gradient branch."""
+    """experimental/public.py:20-140, defaults included (gradient_slice=True: 15 D chains, s = 2)."""
     model: Any
     num_search_chains: Optional[int] = None
     s: Optional[int] = None
     k: Optional[int] = None
-    gradient_slice: bool = False
+    gradient_slice: bool = True
     shell_frac: Optional[float] = None
     devices: Optional[Any] = None
     verbose: bool = False
 
     def __post_init__(self):
-        if self.gradient_slice:
-            raise NotImplementedError("gradient_slice=True needs gradients of the likelihood (SURVEY §8(f) row 2, not built).")
         if self.num_search_chains is None:
-            self.num_search_chains = self.model.U_ndims * 100
+            self.num_search_chains = self.model.U_ndims * (15 if self.gradient_slice else 100)
         if self.s is None:
-            self.s = 10
+            self.s = 2 if self.gradient_slice else 10
         if self.shell_frac is None:
             self.shell_frac = 0.5
         if self.k is None:
             self.k = self.model.U_ndims * self.s - 1
         sampler = UniDimSliceSampler(model=self.model, num_slices=self.model.U_ndims * int(self.s),
                                      num_phantom_save=int(self.k), midpoint_shrink=True, perfect=True,
-                                     gradient_slice=False)
+                                     gradient_slice=self.gradient_slice)
         self._global_optimiser = SimpleGlobalOptimisation(
             sampler=sampler, num_search_chains=int(self.num_search_chains), shell_frac=float(self.shell_frac),
             model=self.model, devices=self.devices, verbose=self.verbose)

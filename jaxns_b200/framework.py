@@ -170,7 +170,41 @@ class Model:
     def external_log_likelihood(self, U: torch.Tensor, X: torch.Tensor) -> torch.Tensor:
         """log L of a batch of proposals for the split slice step: U [n, D] in the unit cube, X = the kernels'
         per-dimension transform of U (what static models consume; general models run their own transform on U)."""
-        return self._general_log_likelihood(U) if self.is_general else self.call_likelihood(X)
+        if self.is_general:
+            return self._general_log_likelihood(U)
+        if not self.is_external:  # a registered family driven through the split step (gradient variants): k_forward
+            return self._forward_batch(U.contiguous(), False)[0]
+        return self.call_likelihood(X)
+
+    def grad_U(self, U: torch.Tensor) -> torch.Tensor:
+        """d log L / dU at a batch U [n, D]: jax.grad(model.forward) of the reference (uni_slice_sampler.py:135) as
+        one reverse pass over the whole batch (rows are independent, so the gradient of the summed log L is the
+        per-row gradient).  The prior transform and the likelihood are replayed as differentiable torch code; the
+        likelihood VALUES the chains are accepted on still come from the kernels / the caller's function."""
+        U = U.detach().clone().requires_grad_(True)
+        with torch.enable_grad():
+            (g,) = torch.autograd.grad(self.log_likelihood_torch(U).sum(), U)
+        return g.contiguous()
+
+    def log_likelihood_torch(self, U: torch.Tensor) -> torch.Tensor:
+        """log L [n] at U [n, D] as differentiable torch code (prior transform included)."""
+        if self.is_general:
+            ret, _, _, _ = self._run_generator(U)
+            out = self.log_likelihood.fn(*ret)
+        else:
+            a = torch.from_numpy(self._a).to(U.device)
+            b = torch.from_numpy(self._b).to(U.device)
+            q = U if self._prior_kind == distributions.Uniform.prior_kind else torch.special.ndtri(U)
+            X = a + b * q
+            if self.is_external:
+                out = self.log_likelihood.fn(*[X[:, lo:hi] for lo, hi in self._ret_slices])
+            else:
+                out = self.log_likelihood.log_prob_torch(X)
+        if not isinstance(out, torch.Tensor) or (U.requires_grad and not out.requires_grad):
+            raise TypeError("gradient_slice / gradient_guided / finetune need a log_likelihood made of differentiable "
+                            "torch operations (a jaxify_likelihood host function has no gradient)")
+        out = out.to(torch.float64)
+        return out.expand(U.shape[0]) if out.dim() == 0 else out.reshape(-1)
 
     # -- reference properties -----------------------------------------------------------------
     @property
@@ -198,7 +232,9 @@ class Model:
         return (self.log_likelihood.family, self._D, self._prior_kind, self.log_likelihood.K, self._a, self._b,
                 self._params_host)
 
-    def desc(self) -> _lib.NsModelDesc:
+    def desc(self, external: bool = False) -> _lib.NsModelDesc:
+        """`external`: describe the model as caller-evaluated (family EXTERNAL) whatever its likelihood is -- how a
+        registered family runs through the split slice step when the sampler needs gradients."""
         _lib.require_cuda()
         if self._dev is None:
             a = torch.from_numpy(self._a).cuda()
@@ -206,6 +242,10 @@ class Model:
             p = torch.from_numpy(self._params_host if self._params_host.size else np.zeros(1)).cuda()
             self._dev = (a, b, p)
         a, b, p = self._dev
+        if external and not self.is_external:
+            from jaxns_b200 import _consts
+            return _lib.NsModelDesc(_consts.FAM_EXTERNAL, self._D, self._prior_kind, 0, a.data_ptr(), b.data_ptr(),
+                                    p.data_ptr(), 0)
         return _lib.NsModelDesc(self.log_likelihood.family, self._D, self._prior_kind, self.log_likelihood.K,
                                 a.data_ptr(), b.data_ptr(), p.data_ptr(), int(self._params_host.size))
 

@@ -28,6 +28,12 @@ class RegisteredLikelihood:
     def __call__(self, *args):
         raise RuntimeError("Registered likelihoods are evaluated on the device; use Model.forward(U).")
 
+    def log_prob_torch(self, X):
+        """The family as differentiable torch code over X [n, D]: only the gradient variants of the slice sampler
+        use it (Model.grad_U, the analogue of jax.grad(model.forward), uni_slice_sampler.py:135); values always come
+        from the kernels."""
+        raise NotImplementedError
+
 
 class ExternalLikelihood(RegisteredLikelihood):
     """An arbitrary user likelihood: a BATCHED device callable `fn(*variables) -> log_L[n]` over torch CUDA
@@ -65,6 +71,14 @@ class DenseGaussianLikelihood(RegisteredLikelihood):
         c = -np.sum(np.log(np.diag(L))) - 0.5 * D * np.log(2.0 * np.pi)
         return np.concatenate([[c], self.loc, Linv.reshape(-1)])
 
+    def log_prob_torch(self, X):
+        import torch
+        D = self.loc.size
+        Linv = torch.from_numpy(np.tril(np.linalg.solve(self.scale_tril, np.eye(D)))).to(X.device)
+        z = (X - torch.from_numpy(self.loc).to(X.device)) @ Linv.T
+        c = -np.sum(np.log(np.diag(self.scale_tril))) - 0.5 * D * np.log(2.0 * np.pi)
+        return c - 0.5 * (z * z).sum(-1)
+
 
 class GaussianMixtureLikelihood(RegisteredLikelihood):
     """log sum_k w_k N(x | mean_k, diag(var_k)); weights default to 1 (the reference's spike-and-slab
@@ -89,13 +103,30 @@ class GaussianMixtureLikelihood(RegisteredLikelihood):
             rows.append(np.concatenate([[logc], self.means[k], 1.0 / np.sqrt(self.variances[k])]))
         return np.concatenate(rows)
 
+    def log_prob_torch(self, X):
+        import torch
+        mu = torch.from_numpy(self.means).to(X.device)
+        var = torch.from_numpy(self.variances).to(X.device)
+        logc = torch.from_numpy(self.log_weights - 0.5 * np.sum(np.log(2.0 * np.pi * self.variances), axis=1)).to(X.device)
+        q = ((X[:, None, :] - mu[None]) ** 2 / var[None]).sum(-1)
+        return torch.logsumexp(logc[None] - 0.5 * q, dim=1)
+
 
 class EggBoxLikelihood(RegisteredLikelihood):
     family = _consts.FAM_EGGBOX
 
+    def log_prob_torch(self, X):
+        import torch
+        return (2.0 + torch.cos(0.5 * X).prod(-1)) ** 5
+
 
 class RosenbrockLikelihood(RegisteredLikelihood):
     family = _consts.FAM_ROSENBROCK
+
+    def log_prob_torch(self, X):
+        a = X[:, 1:] - X[:, :-1] ** 2
+        b = 1.0 - X[:, :-1]
+        return -(100.0 * a * a + b * b).sum(-1)
 
 
 class GaussianShellsLikelihood(RegisteredLikelihood):
@@ -112,6 +143,15 @@ class GaussianShellsLikelihood(RegisteredLikelihood):
             raise ValueError(f"Shells are {self.centres.shape[1]}-D but the prior has {D} dims.")
         return np.concatenate([np.concatenate([[self.widths[k], self.radii[k]], self.centres[k]])
                                for k in range(self.K)])
+
+    def log_prob_torch(self, X):
+        import torch
+        c = torch.from_numpy(self.centres).to(X.device)
+        w = torch.from_numpy(self.widths).to(X.device)
+        r = torch.from_numpy(self.radii).to(X.device)
+        e = torch.sqrt(((X[:, None, :] - c[None]) ** 2).sum(-1)) - r[None]
+        g = -0.5 * e * e / (w * w)[None] - torch.log(torch.sqrt(2.0 * np.pi * w * w))[None]
+        return torch.logsumexp(g, dim=1)
 
 
 def jaxify_likelihood(log_likelihood, vectorised: bool = False):

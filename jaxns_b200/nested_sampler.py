@@ -163,13 +163,15 @@ class ShardedStaticNestedSampler:
     def _make_engine(self) -> _Engine:
         if self._engine is None:
             s = self.sampler
-            desc = self.model.desc()
+            desc = self.model.desc(external=bool(s.gradient_flags))
             eng_world = len(self.devices) if self._world > 1 else 1
             cfg = _lib.NsEngineConfig(desc, int(self.num_live_points), int(self.max_samples),
                                       int(self.num_live_points * self.shell_fraction), s.num_slices,
                                       s.num_phantom_save, int(s.midpoint_shrink), 0,
                                       self._rank if eng_world > 1 else 0, eng_world)
             self._engine = _Engine(cfg, keepalive=(self.model, desc))
+            if s.gradient_flags:
+                _lib.check(_lib.lib().nsb200_engine_set_gradient_flags(self._engine.h, ctypes.c_int32(s.gradient_flags)))
         return self._engine
 
     def _run(self, key, term_cond) -> Tuple[int, TerminationRegister, NestedSamplerState]:
@@ -190,7 +192,8 @@ class ShardedStaticNestedSampler:
             tc = _lib.NsTermCond()  # device stops only on plateau / no seed points; host decides the rest
         reg = _lib.NsRegister()
         world = len(self.devices) if self._world > 1 else 1
-        external = getattr(self.model, "is_external", False)
+        # gradient_slice / gradient_guided chains take the caller-evaluated path whatever the likelihood is
+        external = getattr(self.model, "is_external", False) or bool(self.sampler.gradient_flags)
         # fused NVLink all-gather: with connected peers a body needs no host-issued collective, so
         # the whole loop runs inside the library exactly as on one GPU
         p2p = world > 1 and not external and self._connect_peers(eng, world)
@@ -370,6 +373,7 @@ class ShardedStaticNestedSampler:
         prop_X = torch.empty((n, D), dtype=torch.float64, device="cuda")
         active = torch.zeros(1, dtype=torch.int64, device="cuda")
         burst = max(4, self.sampler.num_slices // 4)
+        grad_pts = torch.empty((n, D), dtype=torch.float64, device="cuda") if self.sampler.gradient_flags else None
         _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
         while True:
             if host_tc is None:
@@ -382,6 +386,11 @@ class ShardedStaticNestedSampler:
             _lib.check(L.nsb200_engine_split_begin(eng.h, _lib.ptr(prop_U), _lib.ptr(prop_X), stream))
             while True:
                 for r in range(burst):
+                    if grad_pts is not None:  # uni_slice_sampler.py:202-214, :255-269: gradients between the kernels
+                        _lib.check(L.nsb200_engine_split_grad_points(eng.h, _lib.ptr(grad_pts), stream))
+                        grad = self.model.grad_U(grad_pts)
+                        _lib.check(L.nsb200_engine_split_grad_begin(eng.h, _lib.ptr(grad), _lib.ptr(prop_U),
+                                                                    _lib.ptr(prop_X), ctypes.c_void_p(0), stream))
                     logL = self.model.external_log_likelihood(prop_U, prop_X)
                     last = r == burst - 1
                     if last:

@@ -87,12 +87,16 @@ class UniDimSliceSampler(AbstractSampler):
             raise ValueError("Only perfect slice sampler is implemented.")
         if self.gradient_guided:
             warnings.warn("Gradient guided slice sampler is experimental and will likely change.")
-        if self.gradient_guided or self.gradient_slice:
-            raise NotImplementedError("Gradient variants are SURVEY §8f row 2 (not built yet).")
         self._seed_tables = {}
 
     def num_phantom(self) -> int:
         return self.num_phantom_save
+
+    @property
+    def gradient_flags(self) -> int:
+        """NsSliceParams.gradient_flags: bit 0 gradient_slice, bit 1 gradient_guided.  Non-zero: the chains run through
+        the split propose / accept step with the model's gradient supplied between the kernels (Model.grad_U)."""
+        return int(self.gradient_slice) | (int(self.gradient_guided) << 1)
 
     def _seed_table(self, N: int) -> torch.Tensor:
         t = self._seed_tables.get(N)
@@ -120,10 +124,10 @@ class UniDimSliceSampler(AbstractSampler):
         out_nev = torch.empty(n, dtype=torch.int64, device="cuda")
         ph_U = torch.empty((n * k, D), dtype=torch.float64, device="cuda")
         ph_logL = torch.empty(n * k, dtype=torch.float64, device="cuda")
-        p = _lib.NsSliceParams(self.num_slices, k, int(self.midpoint_shrink), 0, N, int(num_samples),
+        p = _lib.NsSliceParams(self.num_slices, k, int(self.midpoint_shrink), self.gradient_flags, N, int(num_samples),
                                int(chain_begin), int(chain_end))
-        d = self.model.desc()
-        if getattr(self.model, "is_external", False):
+        d = self.model.desc(external=bool(self.gradient_flags))
+        if getattr(self.model, "is_external", False) or self.gradient_flags:
             self._split_batch(d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL)
         else:
             self._fused_batch(d, p, key, contour, live_U, live_logL, out_U, out_logL, out_nev, ph_U, ph_logL)
@@ -151,8 +155,17 @@ class UniDimSliceSampler(AbstractSampler):
                                         _lib.ptr(live_U), _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)),
                                         _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(prop_U), _lib.ptr(prop_X), st))
         burst = max(4, self.num_slices // 4)  # likelihood rounds between reads of the active-chain counter
+        grad_pts = torch.empty((n, D), dtype=torch.float64, device="cuda") if self.gradient_flags else None
         while True:
             for r in range(burst):
+                if grad_pts is not None:
+                    # chains between slices wait for d log L / dU at their point (include/nsb200.h, gradient protocol)
+                    _lib.check(L.nsb200_split_grad_points(ctypes.byref(d), ctypes.byref(p), _lib.ptr(ws),
+                                                          ctypes.c_int64(nbytes), _lib.ptr(grad_pts), st))
+                    grad = self.model.grad_U(grad_pts)
+                    _lib.check(L.nsb200_split_grad_begin(ctypes.byref(d), ctypes.byref(p), _lib.ptr(contour),
+                                                         _lib.ptr(grad), _lib.ptr(ws), ctypes.c_int64(nbytes),
+                                                         _lib.ptr(prop_U), _lib.ptr(prop_X), ctypes.c_void_p(0), st))
                 logL = self.model.external_log_likelihood(prop_U, prop_X)
                 last = r == burst - 1
                 if last:

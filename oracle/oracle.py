@@ -624,3 +624,20 @@ def set_num_threads(n: int):
 def set_fixed_alpha(a: float):
     """Test knob: constant midpoint-shrink factor instead of linspace(0.5, 1, S) (a < 0 restores the schedule)."""
     lib().o_set_fixed_alpha(ctypes.c_double(float(a)))
+
+
+def set_gradient_flags(flags: int):
+    """Test knob: bit 0 = gradient_slice, bit 1 = gradient_guided chains (uni_slice_sampler.py:202-214, :255-269)
+    in slice_batch / OracleNestedSampler; 0 restores the plain sampler."""
+    lib().o_set_gradient_flags(ctypes.c_int(int(flags)))
+
+
+def grad_U(model: "OModel", U) -> np.ndarray:
+    """Analytic d log L / dU of the registered families at U [n, D] (ns_oracle.c o_grad_U)."""
+    U = np.ascontiguousarray(np.atleast_2d(U), np.float64)
+    g = np.empty_like(U)
+    for i in range(U.shape[0]):
+        ui, gi = np.ascontiguousarray(U[i]), np.empty(U.shape[1])
+        lib().o_grad_U(model.c, _p(ui, _f64p), _p(gi, _f64p))
+        g[i] = gi
+    return g

@@ -1059,7 +1059,7 @@ def test_global_optimisation_wraparound_store_matches_oracle(torch_cuda, oracle)
     assert np.all(np.abs(x - 0.5) < 0.6)  # near the likelihood's peak at (0.5, 0.5)
     # the public facade with an explicit condition (its default min_efficiency=3e-2 stops before the first iteration,
     # like the reference's: SURVEY App. E #19)
-    opt = j.GlobalOptimisation(model=model, num_search_chains=200, s=4)
+    opt = j.GlobalOptimisation(model=model, num_search_chains=200, s=4, gradient_slice=False)
     out = opt(random.PRNGKey(0), GlobalOptimisationTerminationCondition(max_likelihood_evaluations=2e5, atol=1e-4))
     assert out.termination_reason & (16 | 512)
     assert out.log_L_solution > float(model.forward(torch.full((2,), 0.5, dtype=torch.float64, device="cuda")).item()) - 10.0
@@ -1198,3 +1198,183 @@ def test_general_prior_models(torch_cuda):
     from jaxns_b200 import likelihoods as lk
     with pytest.raises(NotImplementedError):
         j.Model(prior_model, lk.EggBoxLikelihood())
+
+
+# ---------------------------------------------------------------------------------------------------
+# gradient variants of the slice sampler (uni_slice_sampler.py:202-214 gradient_slice, :255-269 gradient_guided):
+# chains through the split kernels with torch-autograd gradients between them, against the oracle's restatement with
+# hand-written gradients.  The two gradients differ in the last bits, so positions are compared to a tolerance and a
+# handful of chains may take a different accept decision somewhere along their S slices.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flags", [1, 2, 3])
+@pytest.mark.parametrize("name,D,N,S,k", [("gauss", 4, 300, 6, 2), ("eggbox", 2, 300, 8, 0), ("rosenbrock", 5, 200, 6, 3),
+                                          ("shells", 3, 200, 6, 0), ("mixture", 6, 200, 5, 1)])
+def test_gradient_slice_batch_vs_oracle(torch_cuda, oracle, name, D, N, S, k, flags):
+    torch = torch_cuda
+    import warnings
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    from jaxns_b200.types import LivePointCollection
+    model = product_models()[name](D)
+    om = to_oracle(model, oracle)
+    key = random.PRNGKey(11 + flags)
+    live_U, live_logL, _ = oracle.init_batch(om, random.PRNGKey(5), N)
+    order = np.argsort(live_logL, kind="stable")
+    live_U, live_logL = live_U[order], live_logL[order]
+    contour = float(live_logL[N // 3])
+    n = N // 2
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=True, perfect=True,
+                                       gradient_slice=bool(flags & 1), gradient_guided=bool(flags & 2))
+    assert sampler.gradient_flags == flags
+    state = LivePointCollection(None, torch.from_numpy(live_U).cuda(), None, torch.from_numpy(live_logL).cuda(), None)
+    sample, phantom = sampler.get_samples_batch(key, contour, state, n)
+    oracle.set_gradient_flags(flags)
+    try:
+        exp = oracle.slice_batch(om, key, contour, live_U, live_logL, S, k=k, midpoint=True, num_samples=n)
+    finally:
+        oracle.set_gradient_flags(0)
+    got_U = sample.U_sample.cpu().numpy()
+    got_nev = sample.num_likelihood_evaluations.cpu().numpy()
+    assert np.all(sample.log_L.cpu().numpy() >= contour)
+    # every chain pays its gradients: S with gradient_slice, S with gradient_guided, on top of >= S proposals
+    assert got_nev.min() >= S * (1 + bin(flags).count("1"))
+    same = (np.abs(got_U - exp["U"]).max(axis=1) < 1e-7) & (got_nev == exp["n_evals"])
+    assert same.mean() >= 0.97, f"{same.sum()} of {n} chains agree with the oracle"
+    np.testing.assert_allclose(sample.log_L.cpu().numpy()[same], exp["log_L"][same], rtol=1e-6, atol=1e-6)
+    if k:
+        ph = phantom.U_sample.cpu().numpy().reshape(n, k, D)
+        np.testing.assert_allclose(ph[same], exp["ph_U"].reshape(n, k, D)[same], rtol=0, atol=1e-7)
+
+
+def test_model_grad_U_vs_oracle(torch_cuda, oracle):
+    torch = torch_cuda
+    for name, D in [("gauss", 8), ("eggbox", 3), ("rosenbrock", 6), ("shells", 4), ("mixture", 10)]:
+        model = product_models()[name](D)
+        om = to_oracle(model, oracle)
+        U = np.random.default_rng(D).uniform(0.05, 0.95, size=(64, D))
+        got = model.grad_U(torch.from_numpy(U).cuda()).cpu().numpy()
+        np.testing.assert_allclose(got, oracle.grad_U(om, U), rtol=1e-9, atol=1e-9)
+
+
+def test_gradient_slice_first_proposal_goes_uphill(torch_cuda):
+    """gradient_slice searches only t in [0, right] along +grad (:210-214): with a concave log L every first proposal of
+    a chain lies on the uphill side of its seed point, i.e. (x - U0) . grad(U0) >= 0."""
+    torch = torch_cuda
+    import ctypes
+    from jaxns_b200 import _lib, random
+    model = product_models()["gauss"](4)
+    L = _lib.lib()
+    N, n, D, S = 200, 100, 4, 3
+    U = random.uniform(random.PRNGKey(1), N * D).reshape(N, D).contiguous()
+    logL = model.forward(U)
+    order = torch.argsort(logL)
+    U, logL = U[order].contiguous(), logL[order].contiguous()
+    contour = logL[10:11].clone()
+    p = _lib.NsSliceParams(S, 0, 1, 1, N, n, 0, n)
+    d = model.desc(external=True)
+    nbytes = L.nsb200_split_workspace_bytes(D, n, 0)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    prop_U, prop_X, pts = (torch.empty((n, D), dtype=torch.float64, device="cuda") for _ in range(3))
+    table = torch.empty(N, dtype=torch.float64, device="cuda")
+    st = _lib.stream_arg()
+    _lib.check(L.nsb200_seed_table(ctypes.c_int64(N), _lib.ptr(table), st))
+    _lib.check(L.nsb200_split_begin(ctypes.byref(d), ctypes.byref(p), _lib.key_arg(random.PRNGKey(2)), _lib.ptr(contour),
+                                    _lib.ptr(U), _lib.ptr(logL), _lib.ptr(table), _lib.ptr(ws), ctypes.c_int64(nbytes),
+                                    _lib.ptr(prop_U), _lib.ptr(prop_X), st))
+    _lib.check(L.nsb200_split_grad_points(ctypes.byref(d), ctypes.byref(p), _lib.ptr(ws), ctypes.c_int64(nbytes),
+                                          _lib.ptr(pts), st))
+    np.testing.assert_array_equal(pts.cpu().numpy(), prop_U.cpu().numpy())  # waiting chains sit at their seed point
+    g = model.grad_U(pts)
+    _lib.check(L.nsb200_split_grad_begin(ctypes.byref(d), ctypes.byref(p), _lib.ptr(contour), _lib.ptr(g), _lib.ptr(ws),
+                                         ctypes.c_int64(nbytes), _lib.ptr(prop_U), _lib.ptr(prop_X), ctypes.c_void_p(0), st))
+    step = prop_U - pts
+    along = (step * g).sum(-1)
+    assert bool((along >= 0).all())
+    # and the step is parallel to the gradient
+    cos = along / (step.norm(dim=-1) * g.norm(dim=-1))
+    assert float(cos.min()) > 1 - 1e-9
+    assert bool(((prop_U >= 0) & (prop_U <= 1)).all())
+    # without gradient flags the same entry point refuses
+    p0 = _lib.NsSliceParams(S, 0, 1, 0, N, n, 0, n)
+    assert L.nsb200_split_grad_begin(ctypes.byref(d), ctypes.byref(p0), _lib.ptr(contour), _lib.ptr(g), _lib.ptr(ws),
+                                     ctypes.c_int64(nbytes), _lib.ptr(prop_U), _lib.ptr(prop_X), ctypes.c_void_p(0),
+                                     st) != 0
+
+
+def test_gradient_nested_sampling_run(torch_cuda, oracle):
+    """Whole runs with gradient chains: the engine's run against the oracle's run with the same flags over the first
+    shells (exact sample counts, likelihoods to a tolerance), and log Z of a full run against the analytic value."""
+    torch = torch_cuda
+    import warnings
+    import jaxns_b200 as j
+    from jaxns_b200 import random
+    D, N, S, k = 3, 120, 6, 2
+    model = product_models()["gauss"](D)
+    om = to_oracle(model, oracle)
+    true_logZ = oracle.gauss_analytic_logZ(D)
+    for flags in (1, 2):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            sampler = j.UniDimSliceSampler(model=model, num_slices=S, num_phantom_save=k, midpoint_shrink=True,
+                                           perfect=True, gradient_slice=bool(flags & 1), gradient_guided=bool(flags & 2))
+        ns = j.ShardedStaticNestedSampler(model=model, max_samples=60000, init_efficiency_threshold=0.1,
+                                          sampler=sampler, num_live_points=N, shell_fraction=0.5)
+        key = random.PRNGKey(4)
+        reason, reg, state = ns._run(key, j.TerminationCondition(dlogZ=1e-4))
+        res = ns._to_results(reason, state, trim=True)
+        # gradient_slice only searches the uphill half of every slice, so it is an optimiser's move, not a sampler of the
+        # constrained prior: its run races to the peak (and may end with every live point on the peak's plateau) and
+        # its evidence is biased -- the reference uses it in GlobalOptimisation only.  gradient_guided is a valid sampler.
+        assert reason != 0
+        if flags == 2:
+            assert reason & 4
+            assert abs(float(res.log_Z_mean) - true_logZ) < max(5 * float(res.log_Z_uncert), 0.5)
+        # the first two shells against the oracle's loop with the same flags
+        m2 = 2 * (N // 2) * (k + 1)
+        ns2 = j.ShardedStaticNestedSampler(model=model, max_samples=60000, init_efficiency_threshold=0.1,
+                                           sampler=sampler, num_live_points=N, shell_fraction=0.5)
+        reason2, reg2, state2 = ns2._run(key, j.TerminationCondition(max_samples=float(m2)))
+        oracle.set_gradient_flags(flags)
+        try:
+            ons = oracle.OracleNestedSampler(om, N, S, k, True, max_samples=60000)
+            oreason, ost = ons.run(key, oracle.TermCond(max_samples=float(m2)))
+        finally:
+            oracle.set_gradient_flags(0)
+        assert reason2 == oreason == 1 and ons.iterations == 2
+        assert state2.num_samples == ost["num_samples"]
+        mm = int(ost["num_samples"])
+        got = state2.sample_collection.log_L.cpu().numpy()[:mm]
+        agree = np.isclose(got, ost["log_L"][:mm], rtol=1e-6, atol=1e-6).mean()
+        assert agree >= 0.95, agree
+        # the evaluation count includes the gradients (one per slice per flag): chains that took the same decisions
+        # dominate, so the totals agree to a fraction of a percent
+        assert abs(reg2.num_likelihood_evaluations - ons.register["num_likelihood_evaluations"]) \
+            < 0.02 * ons.register["num_likelihood_evaluations"]
+
+
+def test_global_optimisation_gradient_default(torch_cuda):
+    """experimental/public.py:20-140 with its default gradient_slice=True, and the Newton-CG fine-tune."""
+    torch = torch_cuda
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd, random
+    from jaxns_b200.experimental import GlobalOptimisationTerminationCondition
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(low=-2.0 * np.ones(4), high=2.0 * np.ones(4)), name="x")
+        return x
+
+    def rosenbrock(x):
+        return -(100.0 * (x[:, 1:] - x[:, :-1] ** 2) ** 2 + (1.0 - x[:, :-1]) ** 2).sum(-1)
+
+    model = j.Model(prior_model=prior_model, log_likelihood=rosenbrock)
+    opt = j.GlobalOptimisation(model=model)
+    assert opt.gradient_slice and opt.num_search_chains == 60 and opt.s == 2
+    out = opt(random.PRNGKey(0), GlobalOptimisationTerminationCondition(max_likelihood_evaluations=3e5, atol=1e-6))
+    assert out.log_L_solution > -0.5, out.log_L_solution
+    tuned = opt(random.PRNGKey(0), GlobalOptimisationTerminationCondition(max_likelihood_evaluations=3e5, atol=1e-6),
+                finetune=True)
+    assert tuned.log_L_solution >= out.log_L_solution and tuned.log_L_solution > -1e-8
+    np.testing.assert_allclose(tuned.X_solution["x"].cpu().numpy(), np.ones(4), atol=1e-3)
+    assert tuned.num_likelihood_evaluations > out.num_likelihood_evaluations

@@ -439,3 +439,51 @@ def test_notebook_run_gaussian_shells_and_the_midpoint_rule(oracle):
     e_mid = np.array([r[2] for r in mid], float)
     assert (182018 - e_sched.mean()) < -4.0 * e_sched.std(ddof=1)  # far below the 2.6.9 schedule's cost
     assert e_mid.min() - 2 * e_mid.std(ddof=1) < 182018 < e_mid.max() + 2 * e_mid.std(ddof=1)  # inside the midpoint rule's
+
+
+# ---------------------------------------------------------------------------------------------------
+# gradient variants (uni_slice_sampler.py:202-214, :255-269): the oracle's hand-written gradients and chain logic
+# ---------------------------------------------------------------------------------------------------
+def test_oracle_gradients_match_finite_differences_and_autograd(oracle):
+    import torch
+    from tests.models import product_models, to_oracle
+    eps = 1e-6
+    for name, D in [("gauss", 4), ("eggbox", 3), ("rosenbrock", 5), ("shells", 3), ("mixture", 6)]:
+        model = product_models()[name](D)
+        om = to_oracle(model, oracle)
+        U = np.random.default_rng(D).uniform(0.2, 0.8, size=(5, D))
+        g = oracle.grad_U(om, U)
+        for i in range(U.shape[0]):
+            for jj in range(D):
+                up, um = U[i].copy(), U[i].copy()
+                up[jj] += eps
+                um[jj] -= eps
+                fd = (om.forward(up)[0] - om.forward(um)[0]) / (2 * eps)
+                assert abs(fd - g[i, jj]) < 1e-4 * max(1.0, abs(fd))
+        # the product's gradient (torch autograd over the replayed transform + family) is the same function
+        np.testing.assert_allclose(model.grad_U(torch.from_numpy(U)).numpy(), g, rtol=1e-9, atol=1e-9)
+
+
+def test_oracle_gradient_chains(oracle):
+    """gradient_slice and gradient_guided each cost one gradient per slice; chains still end above the contour and the
+    flags leave the plain sampler untouched once cleared."""
+    om = oracle.gauss_model(3)
+    N, S = 200, 5
+    live_U, live_logL, _ = oracle.init_batch(om, oracle.PRNGKey(5), N)
+    order = np.argsort(live_logL, kind="stable")
+    live_U, live_logL = live_U[order], live_logL[order]
+    contour = float(live_logL[N // 4])
+    key = oracle.PRNGKey(9)
+    base = oracle.slice_batch(om, key, contour, live_U, live_logL, S, k=2, num_samples=64)
+    try:
+        for flags in (1, 2, 3):
+            oracle.set_gradient_flags(flags)
+            out = oracle.slice_batch(om, key, contour, live_U, live_logL, S, k=2, num_samples=64)
+            assert np.all(out["log_L"] > contour)
+            assert np.all(out["n_evals"] >= S * (1 + bin(flags).count("1")))
+            np.testing.assert_array_equal(out["seed_idx"], base["seed_idx"])  # the seed draw does not depend on the flags
+            assert not np.array_equal(out["U"], base["U"])
+    finally:
+        oracle.set_gradient_flags(0)
+    again = oracle.slice_batch(om, key, contour, live_U, live_logL, S, k=2, num_samples=64)
+    np.testing.assert_array_equal(again["U"], base["U"])
