@@ -358,6 +358,10 @@ int nsb200_engine_step_end(NsEngine *e, nsb200_stream_t stream);
  * gather buffer = world_size blocks of [rows_per_rank, row_doubles] float64; this rank writes block
  * `rank`.  row = [U[D], log_L, n_evals (int64 bits), (U[D], log_L) x k phantom]. */
 int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *rows_per_rank, int64_t *row_doubles);
+/* Device address of the likelihood contour L_min of the body in flight (written by step_begin): with the host-issued
+ * collective the caller agrees it across ranks by ncclAllReduce(min) / (max) next to the all-gather
+ * (the fused path compares the contours inside its arrival barrier). */
+int nsb200_engine_contour(NsEngine *e, const double **contour);
 /* Whole run: loops step until determine_termination (common/termination.py:13-147) says done,
  * then appends the final live set (sharded_static.py:834-838).  Synchronises `stream`. */
 int nsb200_engine_run(NsEngine *e, const uint32_t key[2], const NsTermCond *term_cond,

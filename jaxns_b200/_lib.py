@@ -90,7 +90,7 @@ EXPORTS = (
     "nsb200_init_propose", "nsb200_transform_batch", "nsb200_engine_init_external", "nsb200_engine_split_begin",
     "nsb200_engine_split_accept", "nsb200_engine_split_finish", "nsb200_sample_evidence",
     "nsb200_slice_streams_bytes", "nsb200_slice_batch_ws", "nsb200_split_grad_points", "nsb200_split_grad_begin",
-    "nsb200_engine_set_gradient_flags", "nsb200_engine_split_grad_points", "nsb200_engine_split_grad_begin",
+    "nsb200_engine_set_gradient_flags", "nsb200_engine_contour", "nsb200_engine_split_grad_points", "nsb200_engine_split_grad_begin",
     "nsb200_engine_p2p_export", "nsb200_engine_p2p_connect", "nsb200_engine_p2p_enabled", "nsb200_engine_p2p_error",
 )
 

@@ -1949,6 +1949,12 @@ extern "C" int nsb200_engine_split_finish(NsEngine *e, nsb200_stream_t stream) {
     return 0;
 }
 
+extern "C" int nsb200_engine_contour(NsEngine *e, const double **contour) {
+    if (!e || !contour) return fail("NULL pointer");
+    *contour = &e->ctl->contour;
+    return 0;
+}
+
 extern "C" int nsb200_engine_gather_buffer(NsEngine *e, double **buf, int64_t *rows_per_rank, int64_t *row_doubles) {
     if (!e) return fail("NULL engine");
     if (buf) *buf = e->packed;

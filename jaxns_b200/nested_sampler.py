@@ -78,6 +78,27 @@ def get_samples(key, mesh, sampler: AbstractSampler, sampler_state: Any, log_L_c
     return Sample(*[gather(x) for x in sample]), Sample(*[gather(x) for x in phantom])
 
 
+class ContourAgreement:
+    """(min, max) all-reduce of a replicated scalar next to the per-body all-gather; `check` raises on the ranks that
+    differ from a peer.  `contour` is a 1-element float64 tensor that the engine rewrites in place every body."""
+
+    def __init__(self, contour: torch.Tensor, rank: int = 0):
+        self.contour = contour
+        self.rank = rank
+        self.bad = torch.zeros(1, dtype=torch.bool, device=contour.device)
+
+    def all_reduce(self):
+        import torch.distributed as dist
+        pair = torch.cat([self.contour, -self.contour])
+        dist.all_reduce(pair, op=dist.ReduceOp.MIN)
+        self.bad |= (pair[0] != self.contour[0]) | (pair[1] != -self.contour[0])
+
+    def check(self):
+        if bool(self.bad.item()):
+            raise RuntimeError(f"nsb200: rank {self.rank} disagrees with its peers on the likelihood contour L_min "
+                               "(the replicated live sets have diverged)")
+
+
 class _DevView:
     """Zero-copy torch view of engine-owned device memory via __cuda_array_interface__."""
 
@@ -217,6 +238,7 @@ class ShardedStaticNestedSampler:
         else:
             _lib.check(L.nsb200_engine_init(eng.h, _lib.key_arg(key), ctypes.byref(tc), stream))
             gather = self._gather_tensor(eng) if (world > 1 and not p2p) else None
+            lmin = self._contour_agreement(eng) if gather is not None else None
             host_tc = self._effective_host_cond(term_cond) if not plain else None
 
             def one_body():
@@ -226,6 +248,7 @@ class ShardedStaticNestedSampler:
                     import torch.distributed as dist
                     rows = gather.shape[0] // world
                     dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+                    lmin.all_reduce()
                 # p2p: the slice kernel already stored the rows into every rank's buffer; step_end starts with the
                 # device-side arrival barrier
                 _lib.check(L.nsb200_engine_step_end(eng.h, stream))
@@ -244,6 +267,8 @@ class ShardedStaticNestedSampler:
                         one_body()
                     t1 = time.perf_counter()
                     _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                    if lmin is not None:
+                        lmin.check()
                     if dbg and time.perf_counter() - t0 > 0.02:
                         print(f"[loop rank {self._rank}] slow burst at iteration {reg.iteration}: enqueue "
                               f"{1e3 * (t1 - t0):.1f} ms, wait {1e3 * (time.perf_counter() - t1):.1f} ms", file=sys.stderr)
@@ -255,6 +280,8 @@ class ShardedStaticNestedSampler:
                         break
                     one_body()
                     _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+                    if lmin is not None:
+                        lmin.check()
             _lib.check(L.nsb200_engine_finalize(eng.h, stream))
         if p2p:
             err = ctypes.c_int32()
@@ -327,6 +354,15 @@ class ShardedStaticNestedSampler:
         self._p2p_state = ok
         return ok
 
+    def _contour_agreement(self, eng):
+        """North star: "L_min is agreed each iteration by an NCCL all-reduce".  The sorted live log L is replicated, so
+        every rank derives the same contour on its own; with the host-issued collective the ranks still reduce
+        (min, max) of it by NCCL once per body and compare with their own value, so replicas that drifted apart stop
+        with an error instead of merging different shells.  (The fused path does the same inside k_peer_barrier.)"""
+        ptr = ctypes.c_void_p()
+        _lib.check(_lib.lib().nsb200_engine_contour(eng.h, ctypes.byref(ptr)))
+        return ContourAgreement(_view(ptr.value, (1,), "<f8", eng), self._rank)
+
     def _initial_points_external(self, key):
         """create_init_state's prior draws (common/initialisation.py:47-60, common/uniform_sample.py:12-60) with the
         caller's likelihood: round r redraws the rows whose log L is still -inf."""
@@ -367,6 +403,7 @@ class ShardedStaticNestedSampler:
         _lib.check(L.nsb200_engine_init_external(eng.h, _lib.key_arg(key), ctypes.byref(tc), _lib.ptr(U0), _lib.ptr(logL0),
                                                  _lib.ptr(nev0), stream))
         gather = self._gather_tensor(eng) if world > 1 else None
+        lmin = self._contour_agreement(eng) if world > 1 else None
         D = self.model.U_ndims
         n = int(self.num_live_points * self.shell_fraction) // world
         prop_U = torch.empty((n, D), dtype=torch.float64, device="cuda")
@@ -411,8 +448,11 @@ class ShardedStaticNestedSampler:
                 import torch.distributed as dist
                 rows = gather.shape[0] // world
                 dist.all_gather_into_tensor(gather, gather[self._rank * rows:(self._rank + 1) * rows])
+                lmin.all_reduce()
             _lib.check(L.nsb200_engine_step_end(eng.h, stream))
             _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+            if lmin is not None:
+                lmin.check()
         _lib.check(L.nsb200_engine_finalize(eng.h, stream))
 
     def _effective_host_cond(self, term_cond):

@@ -46,6 +46,37 @@ def _worker(rank, world, port, out_dir):
             assert a[0] == b[0] and a[1] == b[1] and a[1] > N * 8, (name, mode, a[:2], b[:2])
             for x, y in zip(a[2:], b[2:]):
                 assert torch.equal(x, y), (name, mode)
+    # caller-evaluated likelihood (split kernels, host-issued all-gather + NCCL L_min all-reduce every body), plain and
+    # with gradient_guided chains (torch-autograd gradients between the kernels): 2 ranks against one
+    import warnings
+    from jaxns_b200 import distributions as tfpd
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(low=-2.0 * np.ones(4), high=2.0 * np.ones(4)), name="x")
+        return x
+
+    def log_likelihood(x):
+        return -(100.0 * (x[:, 1:] - x[:, :-1] ** 2) ** 2 + (1.0 - x[:, :-1]) ** 2).sum(-1)
+
+    model = j.Model(prior_model=prior_model, log_likelihood=log_likelihood)
+    for guided in (False, True):
+        res = {}
+        for mode in ("nccl", "single"):
+            kw = dict(devices=[0]) if mode == "single" else {}
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                sampler = j.UniDimSliceSampler(model=model, num_slices=8, num_phantom_save=2, midpoint_shrink=True,
+                                               perfect=True, gradient_guided=guided)
+            ns = j.ShardedStaticNestedSampler(model=model, max_samples=20000, init_efficiency_threshold=0.1,
+                                              sampler=sampler, num_live_points=256, **kw)
+            reason, reg, state = ns._run(random.PRNGKey(9), j.TerminationCondition(max_samples=4000.0))
+            n = int(state.num_samples)
+            res[mode] = (int(reason), n, state.sample_collection.log_L[:n].clone(), int(reg.num_likelihood_evaluations))
+        a, b = res["nccl"], res["single"]
+        assert a[0] == b[0] and a[1] == b[1], (guided, a[:2], b[:2])
+        close = torch.isclose(a[2], b[2], rtol=1e-9, atol=1e-9).double().mean().item()
+        assert close >= 0.99, (guided, close)
+        assert abs(a[3] - b[3]) <= 0.01 * b[3]
     dist.barrier()
     open(os.path.join(out_dir, f"ok{rank}"), "w").write("ok")
     dist.destroy_process_group()

@@ -60,3 +60,35 @@ def test_two_rank_sharding_matches_single_rank(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert all(os.path.exists(os.path.join(tmp_path, f"ok{r}")) for r in range(world))
+
+
+def _agreement_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from jaxns_b200.nested_sampler import ContourAgreement
+    contour = torch.tensor([-3.25], dtype=torch.float64)
+    agree = ContourAgreement(contour, rank)
+    for value in (-float("inf"), -3.25, 0.0, 17.5):  # the engine rewrites the scalar in place every body
+        contour[0] = value
+        agree.all_reduce()
+    agree.check()  # identical replicas: silent
+    contour[0] = 1.0 + 1e-15 * rank  # one ulp-level drift on rank 1
+    agree.all_reduce()
+    try:
+        agree.check()
+        raised = False
+    except RuntimeError as e:
+        raised = "L_min" in str(e)
+    assert raised  # both ranks see that (min, max) differ from their own value or a peer's
+    open(os.path.join(out_dir, f"agree{rank}"), "w").write("ok")
+    dist.destroy_process_group()
+
+
+def test_contour_agreement_all_reduce(tmp_path):
+    """The NCCL L_min agreement of the host-collective path (nested_sampler.ContourAgreement), on gloo."""
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_agreement_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert all(os.path.exists(os.path.join(tmp_path, f"agree{r}")) for r in range(world))
