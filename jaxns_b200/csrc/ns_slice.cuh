@@ -529,8 +529,15 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
     }
 }
 
+// -DNSB_SLICE_MIN_BLOCKS=n (experiments): resident CTAs per SM the compiler must allow for, i.e. a register cap of
+// 65536 / (n * kThreadsPerBlock) per thread (kThreadsPerBlock = 128: n = 4 -> 128 registers).
+#ifdef NSB_SLICE_MIN_BLOCKS
+#define NSB_SLICE_BOUNDS __launch_bounds__(kThreadsPerBlock, NSB_SLICE_MIN_BLOCKS)
+#else
+#define NSB_SLICE_BOUNDS __launch_bounds__(kThreadsPerBlock)
+#endif
 template <int G, int DPL, int P>
-__global__ void __launch_bounds__(kThreadsPerBlock) k_slice_chains(SliceArgs a) {
+__global__ void NSB_SLICE_BOUNDS k_slice_chains(SliceArgs a) {
     extern __shared__ double smem[];
 #ifdef NSB_TIMELINE
     if (threadIdx.x == 0) atomicMin(&g_tl[2], gtime());
