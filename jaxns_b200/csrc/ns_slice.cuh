@@ -53,7 +53,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 
 // Uniforms per slice drawn ahead by the lane-parallel precompute (shrink steps beyond that fall
 // back to walking the run_key chain inline).
-constexpr int kPre = 8;
+#ifndef NSB_KPRE
+#define NSB_KPRE 8
+#endif
+constexpr int kPre = NSB_KPRE;
 
 // Watchdog of the shrink loop: a bracket that has collapsed onto the seed point re-evaluates the seed
 // itself, which satisfies the constraint, so a deterministic likelihood accepts within ~2200 halvings of a double.
