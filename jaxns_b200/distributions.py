@@ -40,6 +40,12 @@ def _rows(x, like):
     return x
 
 
+def _event_sum(lp, X):
+    """per-dimension log densities -> one value per row, whichever of the parameters / the points carries the batch"""
+    import torch
+    return torch.broadcast_tensors(lp, X)[0].sum(dim=-1)
+
+
 class Distribution:
     prior_kind: int
     dynamic = False  # parameters are tensors / other priors' values: only the torch path below can evaluate it
@@ -59,6 +65,12 @@ class Distribution:
 
     def log_prob_torch(self, X):
         raise NotImplementedError
+
+    def log_prob(self, x):
+        """tfpd's log_prob for use inside torch likelihoods (e.g. Normal(y, sigma).log_prob(0.) with batched y, sigma
+        [n, 1]): one value per row."""
+        x = _t(x)
+        return self.log_prob_torch(x.reshape(1, -1) if x.dim() < 2 else x)
 
 
 class Uniform(Distribution):
@@ -86,10 +98,12 @@ class Uniform(Distribution):
         import torch
         low, high = _rows(self.low, X), _rows(self.high, X)
         inside = (X >= low) & (X <= high)
-        lp = torch.where(inside, -torch.log(high - low).expand_as(X), torch.full_like(X, -math.inf))
-        return lp.sum(dim=-1)
+        lp = torch.where(inside, -torch.log(high - low), torch.full_like(X, -math.inf))
+        return _event_sum(lp, X)
 
     def log_prob(self, x):
+        if self.dynamic or _is_tensor(x):
+            return Distribution.log_prob(self, x)
         x = np.asarray(x, np.float64)
         inside = (x >= self.low) & (x <= self.high)
         return np.sum(np.where(inside, -np.log(self._b), -np.inf), axis=-1)
@@ -120,9 +134,11 @@ class Normal(Distribution):
         import torch
         loc, scale = _rows(self.loc, X), _rows(self.scale, X)
         z = (X - loc) / scale
-        return (-0.5 * z * z - torch.log(scale) - 0.5 * math.log(2.0 * math.pi)).expand_as(X).sum(dim=-1)
+        return _event_sum((-0.5 * z * z - torch.log(scale) - 0.5 * math.log(2.0 * math.pi)), X)
 
     def log_prob(self, x):
+        if self.dynamic or _is_tensor(x):
+            return Distribution.log_prob(self, x)
         z = (np.asarray(x, np.float64) - self.loc) / self.scale
         return np.sum(-0.5 * z * z - np.log(self.scale) - 0.5 * np.log(2 * np.pi), axis=-1)
 
@@ -188,6 +204,173 @@ class Constant(Distribution):
     def log_prob_torch(self, X):
         import torch
         return torch.zeros(X.shape[0], dtype=torch.float64, device=X.device)
+
+
+class _QuantileDistribution(Distribution):
+    """Scalar families with a closed-form quantile, evaluated by the batched torch prior transform only (models with a
+    callable likelihood).  Parameters broadcast over the event: numbers, arrays, tensors or other priors' values."""
+    dynamic = True
+    prior_kind = None
+    _a = None
+
+    def _set(self, **params):
+        self._p = params
+        self._size = max([1] + [int(p.shape[-1]) if _is_tensor(p) and p.dim() > 0 else (1 if _is_tensor(p) or getattr(p, "_nsb200_placeholder", False) else int(np.size(p)))
+                                for p in params.values()])
+
+    def _get(self, name, like):
+        return _rows(self._p[name], like)
+
+
+class Exponential(_QuantileDistribution):
+    """tfpd.Exponential(rate): quantile(u) = -log1p(-u) / rate."""
+
+    def __init__(self, rate=1.0):
+        self._set(rate=rate)
+
+    def quantile_torch(self, U):
+        import torch
+        return -torch.log1p(-U) / self._get("rate", U)
+
+    def log_prob_torch(self, X):
+        import torch
+        rate = self._get("rate", X)
+        lp = torch.where(X >= 0, torch.log(rate) - rate * X, torch.full_like(X, -math.inf))
+        return _event_sum(lp, X)
+
+
+class HalfNormal(_QuantileDistribution):
+    """tfpd.HalfNormal(scale): quantile(u) = scale * ndtri((1 + u) / 2)."""
+
+    def __init__(self, scale=1.0):
+        self._set(scale=scale)
+
+    def quantile_torch(self, U):
+        import torch
+        return self._get("scale", U) * torch.special.ndtri(0.5 * (1.0 + U))
+
+    def log_prob_torch(self, X):
+        import torch
+        scale = self._get("scale", X)
+        z = X / scale
+        lp = 0.5 * math.log(2.0 / math.pi) - torch.log(scale) - 0.5 * z * z
+        return _event_sum(torch.where(X >= 0, lp, torch.full_like(lp, -math.inf)), X)
+
+
+class Cauchy(_QuantileDistribution):
+    """tfpd.Cauchy(loc, scale): quantile(u) = loc + scale * tan(pi (u - 1/2))."""
+
+    def __init__(self, loc=0.0, scale=1.0):
+        self._set(loc=loc, scale=scale)
+
+    def quantile_torch(self, U):
+        import torch
+        return self._get("loc", U) + self._get("scale", U) * torch.tan(math.pi * (U - 0.5))
+
+    def log_prob_torch(self, X):
+        import torch
+        scale = self._get("scale", X)
+        z = (X - self._get("loc", X)) / scale
+        return _event_sum((-math.log(math.pi) - torch.log(scale) - torch.log1p(z * z)), X)
+
+
+class HalfCauchy(_QuantileDistribution):
+    """tfpd.HalfCauchy(loc, scale): quantile(u) = loc + scale * tan(pi u / 2)."""
+
+    def __init__(self, loc=0.0, scale=1.0):
+        self._set(loc=loc, scale=scale)
+
+    def quantile_torch(self, U):
+        import torch
+        return self._get("loc", U) + self._get("scale", U) * torch.tan(0.5 * math.pi * U)
+
+    def log_prob_torch(self, X):
+        import torch
+        scale, loc = self._get("scale", X), self._get("loc", X)
+        z = (X - loc) / scale
+        lp = math.log(2.0 / math.pi) - torch.log(scale) - torch.log1p(z * z)
+        return _event_sum(torch.where(X >= loc, lp, torch.full_like(lp, -math.inf)), X)
+
+
+class Laplace(_QuantileDistribution):
+    """tfpd.Laplace(loc, scale): quantile(u) = loc - scale sign(u - 1/2) log(1 - 2 |u - 1/2|)."""
+
+    def __init__(self, loc=0.0, scale=1.0):
+        self._set(loc=loc, scale=scale)
+
+    def quantile_torch(self, U):
+        import torch
+        q = U - 0.5
+        return self._get("loc", U) - self._get("scale", U) * torch.sign(q) * torch.log1p(-2.0 * torch.abs(q))
+
+    def log_prob_torch(self, X):
+        import torch
+        scale = self._get("scale", X)
+        return _event_sum((-math.log(2.0) - torch.log(scale) - torch.abs(X - self._get("loc", X)) / scale), X)
+
+
+class Gumbel(_QuantileDistribution):
+    """tfpd.Gumbel(loc, scale): quantile(u) = loc - scale log(-log u)."""
+
+    def __init__(self, loc=0.0, scale=1.0):
+        self._set(loc=loc, scale=scale)
+
+    def quantile_torch(self, U):
+        import torch
+        return self._get("loc", U) - self._get("scale", U) * torch.log(-torch.log(U))
+
+    def log_prob_torch(self, X):
+        import torch
+        scale = self._get("scale", X)
+        z = (X - self._get("loc", X)) / scale
+        return _event_sum((-(z + torch.exp(-z)) - torch.log(scale)), X)
+
+
+class Kumaraswamy(_QuantileDistribution):
+    """tfpd.Kumaraswamy(concentration1=a, concentration0=b): quantile(u) = (1 - (1 - u)^(1/b))^(1/a)."""
+
+    def __init__(self, concentration1=1.0, concentration0=1.0):
+        self._set(a=concentration1, b=concentration0)
+
+    def quantile_torch(self, U):
+        import torch
+        a, b = self._get("a", U), self._get("b", U)
+        return torch.exp(torch.log(-torch.expm1(torch.log1p(-U) / b)) / a)
+
+    def log_prob_torch(self, X):
+        import torch
+        a, b = self._get("a", X), self._get("b", X)
+        lp = torch.log(a) + torch.log(b) + (a - 1.0) * torch.log(X) + (b - 1.0) * torch.log1p(-X ** a)
+        inside = (X >= 0) & (X <= 1)
+        return _event_sum(torch.where(inside, lp, torch.full_like(lp, -math.inf)), X)
+
+
+class TruncatedNormal(_QuantileDistribution):
+    """tfpd.TruncatedNormal(loc, scale, low, high): quantile(u) = loc + scale ndtri(Phi(a) + u (Phi(b) - Phi(a)))."""
+
+    def __init__(self, loc=0.0, scale=1.0, low=-1.0, high=1.0):
+        self._set(loc=loc, scale=scale, low=low, high=high)
+
+    def _cdf_bounds(self, like):
+        import torch
+        loc, scale = self._get("loc", like), self._get("scale", like)
+        ca = torch.special.ndtr((self._get("low", like) - loc) / scale)
+        cb = torch.special.ndtr((self._get("high", like) - loc) / scale)
+        return loc, scale, ca, cb
+
+    def quantile_torch(self, U):
+        import torch
+        loc, scale, ca, cb = self._cdf_bounds(U)
+        x = loc + scale * torch.special.ndtri(ca + U * (cb - ca))
+        return torch.minimum(torch.maximum(x, self._get("low", U)), self._get("high", U))
+
+    def log_prob_torch(self, X):
+        import torch
+        loc, scale, ca, cb = self._cdf_bounds(X)
+        z = (X - loc) / scale
+        lp = -0.5 * z * z - 0.5 * math.log(2.0 * math.pi) - torch.log(scale) - torch.log(cb - ca)
+        inside = (X >= self._get("low", X)) & (X <= self._get("high", X))
+        return _event_sum(torch.where(inside, lp, torch.full_like(lp, -math.inf)), X)
 
 
 def from_any(dist) -> Distribution:

@@ -11,8 +11,11 @@ gradient_slice chains (uni_slice_sampler.py:202-214, the reference's default for
 split propose / accept kernels with Model.grad_U between them; the fine-tune (global_optimisation.py:56-73) is a
 Newton-CG descent of -log L over the quick_unit-unconstrained cube (internals/constraint_bijections.py:11-40), written
 here with torch autograd Hessian-vector products -- the reference's own newton_cg_solver is not restated step for step,
-so the fine-tuned point agrees with the reference's only to the optimiser's tolerance.  EvidenceMaximisation needs
-parametrised models (framework/context.py), out of the hot-path scope.
+so the fine-tuned point agrees with the reference's only to the optimiser's tolerance.
+
+EvidenceMaximisation (experimental/evidence_maximisation.py:40-300): the E-step IS a nested-sampling run of the model at
+the current parameters (`get_parameter`, `Prior(...).parametrised()`: jaxns_b200/context.py, framework.py); the M-step
+maximises log sum_i exp(log L(U_i; params) + log w_i) over the run's samples with the same Newton-CG.
 """
 import dataclasses
 import io
@@ -21,13 +24,14 @@ from typing import Any, NamedTuple, Optional, TextIO, Union
 
 import torch
 
+from jaxns_b200.constraint_bijections import quick_unit, quick_unit_inverse
 from jaxns_b200.nested_sampler import ShardedStaticNestedSampler
 from jaxns_b200.samplers import AbstractSampler, UniDimSliceSampler
 from jaxns_b200.types import SampleCollection, TerminationCondition
 
 __all__ = ["GlobalOptimisationResults", "GlobalOptimisationTerminationCondition", "GlobalOptimisationState",
            "SimpleGlobalOptimisation", "GlobalOptimisation", "DefaultGlobalOptimisation", "go_summary",
-           "gradient_based_optimisation", "quick_unit", "quick_unit_inverse"]
+           "gradient_based_optimisation", "quick_unit", "quick_unit_inverse", "newton_cg", "EvidenceMaximisation"]
 
 
 class GlobalOptimisationState(NamedTuple):
@@ -60,29 +64,15 @@ class GlobalOptimisationTerminationCondition(NamedTuple):
     min_efficiency: Optional[float] = None
 
 
-def quick_unit(x):
-    """internals/constraint_bijections.py:11-21: a cheap sigmoid, R -> (0, 1)."""
-    return 0.5 * (x / (1 + torch.abs(x)) + 1)
-
-
-def quick_unit_inverse(y):
-    """internals/constraint_bijections.py:24-40."""
-    twoy = y + y
-    return torch.where(y >= 0.5, (1 - twoy) / (twoy - 2), 1 - 1 / twoy)
-
-
-def gradient_based_optimisation(model, init_U_point, max_iters: int = 100, cg_iters: int = 50, gtol: float = 1e-10):
-    """global_optimisation.py:56-73: minimise -log L(quick_unit(z)) from z0 = quick_unit_inverse(U) by Newton-CG.
-    Each outer step solves H p = -g by conjugate gradients on autograd Hessian-vector products (stopping at negative
-    curvature or the Eisenstat-Walker residual), then backtracks on the step length until the loss decreases.
-    Returns (U, log L, number of function evaluations counted as the reference does: 4 per CG iteration)."""
-    z = quick_unit_inverse(torch.as_tensor(init_U_point, dtype=torch.float64, device="cuda").reshape(1, -1)).clone()
-
-    def loss_of(zz):
-        return -model.log_likelihood_torch(quick_unit(zz))[0]
-
+def newton_cg(loss_of, z0, max_iters: int = 100, cg_iters: int = 50, gtol: float = 1e-10):
+    """Minimise a scalar torch function of one tensor by Newton-CG (the role of the reference's newton_cg_solver in
+    global_optimisation.py:62 and evidence_maximisation.py:181).  Each outer step solves H p = -g by conjugate
+    gradients on autograd Hessian-vector products (stopping at negative curvature or the Eisenstat-Walker residual),
+    then backtracks on the step length until the loss decreases.  Returns (z, f(z), CG iterations)."""
+    z = z0.detach().clone()
     n_cg = 0
-    f = float(loss_of(z))
+    with torch.no_grad():
+        f = float(loss_of(z))
     for _ in range(max_iters):
         zz = z.detach().clone().requires_grad_(True)
         with torch.enable_grad():
@@ -119,15 +109,24 @@ def gradient_based_optimisation(model, init_U_point, max_iters: int = 100, cg_it
             rr = rr_new
         step, improved = 1.0, False
         for _ in range(30):
-            f_new = float(loss_of(z + step * p))
+            with torch.no_grad():
+                f_new = float(loss_of(z + step * p))
             if math.isfinite(f_new) and f_new < f:
-                z, f, improved = z + step * p, f_new, True
+                z, f, improved = (z + step * p).detach(), f_new, True
                 break
             step *= 0.5
         if not improved:
             break
-    U = quick_unit(z)[0].detach()
-    return U, -f, 4 * n_cg
+    return z, f, n_cg
+
+
+def gradient_based_optimisation(model, init_U_point):
+    """global_optimisation.py:56-73: minimise -log L(quick_unit(z)) from z0 = quick_unit_inverse(U).  Returns
+    (U, log L, number of function evaluations counted as the reference does: 4 per CG iteration)."""
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    z0 = quick_unit_inverse(torch.as_tensor(init_U_point, dtype=torch.float64, device=dev).reshape(1, -1))
+    z, f, n_cg = newton_cg(lambda zz: -model.log_likelihood_torch(quick_unit(zz))[0], z0)
+    return quick_unit(z)[0].detach(), -f, 4 * n_cg
 
 
 @dataclasses.dataclass(eq=False)
@@ -309,3 +308,114 @@ class GlobalOptimisation:
 
 
 DefaultGlobalOptimisation = GlobalOptimisation
+
+
+class MStepData(NamedTuple):
+    U_samples: Any
+    log_weights: Any
+
+
+@dataclasses.dataclass(eq=False)
+class EvidenceMaximisation:
+    """experimental/evidence_maximisation.py:40-300, same fields, defaults, convergence rules and printed lines.
+
+    E-step: NestedSampler(model(params), **ns_kwargs) run to `termination_cond`, trimmed results (:84-112) -- the hot
+    path.  M-step (:149-221): with the run's samples U_i and weights log w_i = log dp_i - log L_i + log Z, maximise
+    log Z(params) = logsumexp_i(log L(U_i; params) + log w_i) by Newton-CG, one solve per epoch, until no parameter
+    moved by more than `gtol` (or max_num_epochs).  The reference pads the samples to a power of two with zero-weight
+    rows so that XLA re-compiles less often; there is no compilation here, so nothing is padded."""
+    model: Any
+    ns_kwargs: Optional[dict] = None
+    max_num_epochs: int = 50
+    gtol: float = 1e-2
+    log_Z_ftol: float = 1.
+    log_Z_atol: float = 1e-4
+    batch_size: Optional[int] = 128
+    termination_cond: Optional[TerminationCondition] = None
+    verbose: bool = False
+
+    def __post_init__(self):
+        if self.ns_kwargs is None:
+            self.ns_kwargs = {}
+
+    def e_step(self, key, params, desc: str):
+        """The E-step is just nested sampling (:114-128)."""
+        from jaxns_b200.public import NestedSampler
+        print(f"Running E-step... {desc}")
+        ns = NestedSampler(model=self.model(params={k: v.detach() for k, v in params.items()}), **self.ns_kwargs)
+        termination_reason, state = ns(key, self.termination_cond)
+        return ns.to_results(termination_reason=termination_reason, state=state, trim=True)
+
+    def _log_evidence(self, params, data: MStepData):
+        log_dZ = self.model(params=params).log_likelihood_torch(data.U_samples) + data.log_weights
+        return torch.logsumexp(log_dZ, dim=0)
+
+    def _m_step(self, key, params, data: MStepData):
+        """One Newton-CG solve of -log Z over the flattened parameters (:174-188)."""
+        names = list(params.keys())
+        shapes = [params[k].shape for k in names]
+        sizes = [int(params[k].numel()) for k in names]
+        flat0 = torch.cat([params[k].detach().reshape(-1) for k in names]) if names else torch.zeros(0, dtype=torch.float64)
+
+        def unflatten(z):
+            out, o = {}, 0
+            for k, shp, sz in zip(names, shapes, sizes):
+                out[k] = z[o:o + sz].reshape(shp)
+                o += sz
+            return out
+
+        def loss(z):
+            log_Z = self._log_evidence(unflatten(z), data)
+            if self.verbose:
+                print(f"log_Z={float(log_Z)}")
+            return -log_Z
+
+        if flat0.numel() == 0:
+            return params, float(-loss(flat0))
+        z, f, _ = newton_cg(loss, flat0)
+        return {k: v.detach() for k, v in unflatten(z).items()}, -f
+
+    def m_step(self, key, params, ns_results, desc: str):
+        """:190-233."""
+        num_samples = int(ns_results.total_num_samples)
+        print(f"Running M-step ({num_samples} samples)... {desc}")
+        log_weights = ns_results.log_dp_mean - ns_results.log_L_samples + ns_results.log_Z_mean
+        data = MStepData(U_samples=ns_results.U_samples, log_weights=log_weights)
+        last_params = params
+        epoch = 0
+        log_Z = None
+        while epoch < self.max_num_epochs:
+            params, log_Z = self._m_step(key=key, params=params, data=data)
+            l_oo = {k: (float((params[k] - last_params[k]).abs().max()) if params[k].numel() > 0 else 0.) for k in params}
+            last_params = params
+            print(f"{desc}: Epoch {epoch}: log_Z={log_Z}, l_oo={l_oo}")
+            if all(v < self.gtol for v in l_oo.values()):
+                break
+            epoch += 1
+        return params, log_Z
+
+    def train(self, num_steps: int = 10, params=None):
+        """:235-300: alternate E and M steps until log Z stops changing (atol, or ftol x its uncertainty)."""
+        from jaxns_b200 import random
+        if params is None:
+            params = self.model.params
+        log_Z = -math.inf
+        ns_results = None
+        for step in range(num_steps):
+            key_e_step, key_m_step = random.split(random.PRNGKey(step), 2)
+            if ns_results is None:
+                desc = f"Step {step}: Initial run"
+            else:
+                desc = f"Step {step}: log Z = {float(ns_results.log_Z_mean):.4f} +- {float(ns_results.log_Z_uncert):.4f}"
+            ns_results = self.e_step(key=key_e_step, params=params, desc=desc)
+            log_Z_change = abs(float(ns_results.log_Z_mean) - log_Z)
+            if log_Z_change < self.log_Z_atol:
+                break
+            if log_Z_change < float(self.log_Z_ftol * float(ns_results.log_Z_uncert)):
+                break
+            log_Z = float(ns_results.log_Z_mean)
+            desc = f"Step {step}: log Z = {float(ns_results.log_Z_mean):.4f} +- {float(ns_results.log_Z_uncert):.4f}"
+            params, log_Z_opt = self.m_step(key=key_m_step, params=params, ns_results=ns_results, desc=desc)
+        if ns_results is None:
+            raise RuntimeError("No results were computed.")
+        return ns_results, params

@@ -13,10 +13,11 @@ from typing import Callable, List, Optional
 import numpy as np
 import torch
 
-from jaxns_b200 import _lib, distributions
+from jaxns_b200 import _lib, context, distributions
+from jaxns_b200.constraint_bijections import quick_unit
 from jaxns_b200.likelihoods import ExternalLikelihood, RegisteredLikelihood
 
-__all__ = ["Prior", "Model"]
+__all__ = ["Prior", "SingularPrior", "Model"]
 
 
 class _NeedsGeneral(Exception):
@@ -42,20 +43,52 @@ class _Var:
 class Prior:
     """Prior(dist_or_value, name=None) (framework/prior.py:65-161)."""
 
+    singular = False
+
     def __init__(self, dist_or_value, name: Optional[str] = None):
         self.name = name
         self.dist = distributions.from_any(dist_or_value)
 
-    def parametrised(self, random_init: bool = False):
-        raise NotImplementedError("Parametrised priors are out of the hot-path scope (SURVEY §2.1).")
+    def parametrised(self, random_init: bool = False) -> "SingularPrior":
+        """framework/prior.py:146-199: the prior becomes a point value driven by a free parameter `<name>_param` on
+        the real line (median of the prior at 0), mapped through quick_unit and the prior's quantile; it keeps the
+        prior's log density at that value.  Must be called inside prior_model (it asks the context for the parameter)."""
+        import warnings
+        if self.name is None:
+            raise ValueError("Prior must have a name to be parametrised.")
+        size = self.dist.event_size()
+        if size == 0:
+            warnings.warn(f"Creating a zero-sized parameter for {self.name}. Probably unintended.")
+
+        def init(shape, dtype):
+            if random_init:
+                from jaxns_b200 import random
+                return random.normal(context.next_rng_key(), int(np.prod(shape)))
+            return np.zeros(shape)
+
+        param = context.get_parameter(f"{self.name}_param", (size,), np.float64, init=init)
+        value = self.dist.quantile_torch(quick_unit(param).reshape(1, -1))
+        return SingularPrior(value=value, base_prior=self, name=self.name)
+
+
+class SingularPrior(Prior):
+    """framework/prior.py:32-62: no U dimensions, the value itself, the base prior's log density at it."""
+    singular = True
+
+    def __init__(self, value, base_prior: Prior, name: Optional[str] = None):
+        self.name = name
+        self.value = value
+        self.base_prior = base_prior
+        self.dist = distributions.Constant(value)
+
+    def __repr__(self):
+        return f"{self.value} -> {self.base_prior}"
 
 
 class Model:
     """Model(prior_model, log_likelihood, params=None) (framework/model.py:29-41)."""
 
     def __init__(self, prior_model: Callable, log_likelihood, params=None):
-        if params is not None:
-            raise NotImplementedError("Parametrised models are out of the hot-path scope (SURVEY §2.1).")
         if not isinstance(log_likelihood, RegisteredLikelihood):
             log_likelihood = ExternalLikelihood(log_likelihood)
         self.prior_model = prior_model
@@ -63,8 +96,22 @@ class Model:
         self.is_external = isinstance(log_likelihood, ExternalLikelihood)
         self.is_general = False
         self._priors: List[Prior] = []
+        self._params = {}
+        self._dev = None
+        if params is not None and not self.is_external:
+            raise NotImplementedError("Parametrised models need a callable likelihood.")
+        if self.is_external:
+            # framework/model.py:33-35: without params the model initialises them (one pass through the prior model
+            # and the likelihood in an initialising context, as parse_joint does)
+            dev = "cuda" if torch.cuda.is_available() else "cpu"
+            self._params = ({k: torch.as_tensor(v, dtype=torch.float64, device=dev) for k, v in params.items()}
+                            if params is not None else self.init_params())
+            if self._params:
+                self._analyse_general()
+                return
         try:
-            self._analyse_static()
+            with context.bind({}):
+                self._analyse_static()
         except _NeedsGeneral:
             if not self.is_external:
                 raise NotImplementedError(
@@ -72,7 +119,23 @@ class Model:
                     "dependent, mixed or dense-MVN priors need a callable likelihood (evaluated between the propose and "
                     "accept kernels).")
             self._analyse_general()
-        self._dev = None
+
+    def init_params(self, rng=None):
+        """framework/model.py:93-115: every get_parameter the prior model and the likelihood ask for, at its `init`."""
+        with context.bind(None, rng) as ctx:
+            ret, _, _, _ = self._run_generator(None, bound=False)
+            self.log_likelihood.fn(*ret)
+        return {k: v.detach() for k, v in ctx.params.items()}
+
+    def set_params(self, params) -> "Model":
+        """framework/model.py:62-73: a new model with these parameter values."""
+        return Model(prior_model=self.prior_model, log_likelihood=self.log_likelihood, params=params)
+
+    def __call__(self, params) -> "Model":
+        return self.set_params(params=params)
+
+    def __repr__(self):
+        return f"Model(U_ndims={self.U_ndims}, num_params={self.num_params})"
 
     def _analyse_static(self):
         """Drive the generator once with placeholders: works when every prior has constant parameters and the model
@@ -128,9 +191,13 @@ class Model:
         self._params_host = np.zeros(0)
         self._ret_slices = None
 
-    def _run_generator(self, U):
+    def _run_generator(self, U, bound: bool = True, parametrised: Optional[dict] = None):
         """One batched pass through the prior model.  U [n, D] on the device (None: a shape-discovery pass at U = 1/2).
-        Returns (likelihood inputs, {name: X}, log prior density [n], event sizes)."""
+        Returns (likelihood inputs, {name: X}, log prior density [n], event sizes).  `bound`: open a context with the
+        model's parameters (False: the caller already holds one); `parametrised` collects the singular priors' values."""
+        if bound:
+            with context.bind(self._params):
+                return self._run_generator(U, False, parametrised)
         dev = "cuda" if torch.cuda.is_available() else "cpu"
         probe = U is None
         n = 1 if probe else U.shape[0]
@@ -147,9 +214,14 @@ class Model:
                 x = p.dist.quantile_torch(u)
                 if x.shape[0] != n:
                     x = x.expand(n, x.shape[-1])
-                log_prior = log_prior + p.dist.log_prob_torch(x)
-                if p.name is not None:
-                    named[p.name] = x
+                if p.singular:
+                    log_prior = log_prior + p.base_prior.dist.log_prob_torch(x)
+                    if parametrised is not None and p.name is not None:
+                        parametrised[p.name] = x
+                else:
+                    log_prior = log_prior + p.dist.log_prob_torch(x)
+                    if p.name is not None:
+                        named[p.name] = x
                 sizes.append(size)
                 o += size
                 p = gen.send(x)
@@ -159,8 +231,9 @@ class Model:
         return ret, named, log_prior, sizes
 
     def _general_log_likelihood(self, U: torch.Tensor) -> torch.Tensor:
-        ret, _, _, _ = self._run_generator(U)
-        out = self.log_likelihood.fn(*ret)
+        with context.bind(self._params), torch.no_grad():
+            ret, _, _, _ = self._run_generator(U, bound=False)
+            out = self.log_likelihood.fn(*ret)
         out = torch.as_tensor(out, dtype=torch.float64, device=U.device)
         out = out.expand(U.shape[0]) if out.dim() == 0 else out.reshape(-1)
         if out.numel() != U.shape[0]:
@@ -189,8 +262,9 @@ class Model:
     def log_likelihood_torch(self, U: torch.Tensor) -> torch.Tensor:
         """log L [n] at U [n, D] as differentiable torch code (prior transform included)."""
         if self.is_general:
-            ret, _, _, _ = self._run_generator(U)
-            out = self.log_likelihood.fn(*ret)
+            with context.bind(self._params):
+                ret, _, _, _ = self._run_generator(U, bound=False)
+                out = self.log_likelihood.fn(*ret)
         else:
             a = torch.from_numpy(self._a).to(U.device)
             b = torch.from_numpy(self._b).to(U.device)
@@ -200,7 +274,8 @@ class Model:
                 out = self.log_likelihood.fn(*[X[:, lo:hi] for lo, hi in self._ret_slices])
             else:
                 out = self.log_likelihood.log_prob_torch(X)
-        if not isinstance(out, torch.Tensor) or (U.requires_grad and not out.requires_grad):
+        wants_grad = U.requires_grad or any(p.requires_grad for p in self._params.values())
+        if not isinstance(out, torch.Tensor) or (wants_grad and not out.requires_grad):
             raise TypeError("gradient_slice / gradient_guided / finetune need a log_likelihood made of differentiable "
                             "torch operations (a jaxify_likelihood host function has no gradient)")
         out = out.to(torch.float64)
@@ -217,11 +292,11 @@ class Model:
 
     @property
     def params(self):
-        return {}
+        return dict(self._params)
 
     @property
     def num_params(self) -> int:
-        return 0
+        return int(sum(v.numel() for v in self._params.values()))
 
     def __hash__(self):
         return id(self)
@@ -312,7 +387,14 @@ class Model:
         return out
 
     def transform_parametrised(self, U):
-        return {}
+        """framework/model.py:161-165: the values of the parametrised (singular) priors, keyed by prior name."""
+        if not self.is_general:
+            return {}
+        U = torch.as_tensor(U, dtype=torch.float64, device="cuda" if torch.cuda.is_available() else "cpu")
+        out = {}
+        with torch.no_grad():
+            self._run_generator(U.reshape(-1, self._D), parametrised=out)
+        return out if U.dim() == 2 else {k: v[0] for k, v in out.items()}
 
     def prepare_input(self, U):
         if self.is_general:

@@ -535,7 +535,7 @@ class ShardedStaticNestedSampler:
         log_post = log_L + self.model.log_prob_prior(U_samples)
         return NestedSamplerResults(
             log_Z_mean=log_Z_mean, log_Z_uncert=log_Z_uncert, ESS=ESS, H_mean=H_mean, samples=samples,
-            parametrised_samples={}, U_samples=U_samples, log_L_samples=log_L, log_dp_mean=log_dp,
+            parametrised_samples=self.model.transform_parametrised(U_samples), U_samples=U_samples, log_L_samples=log_L, log_dp_mean=log_dp,
             log_X_mean=per.log_X_mean, log_posterior_density=log_post, num_live_points_per_sample=num_live_points,
             num_likelihood_evaluations_per_sample=num_likelihood_evaluations, total_num_samples=num_samples,
             total_phantom_samples=total_phantom, total_num_likelihood_evaluations=total_evals,

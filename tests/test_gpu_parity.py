@@ -1378,3 +1378,61 @@ def test_global_optimisation_gradient_default(torch_cuda):
     assert tuned.log_L_solution >= out.log_L_solution and tuned.log_L_solution > -1e-8
     np.testing.assert_allclose(tuned.X_solution["x"].cpu().numpy(), np.ones(4), atol=1e-3)
     assert tuned.num_likelihood_evaluations > out.num_likelihood_evaluations
+
+
+# ---------------------------------------------------------------------------------------------------
+# EvidenceMaximisation (experimental/evidence_maximisation.py): E-step = the nested-sampling loop on a parametrised
+# model, M-step = Newton-CG on the run's samples
+# ---------------------------------------------------------------------------------------------------
+def test_evidence_maximisation_reference_tests(torch_cuda):
+    """The reference's own tests (src/jaxns/experimental/tests/test_evidence_maximisation.py:13-48), same models."""
+    import warnings
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(0., 1.))
+        y = yield j.Prior(tfpd.Normal(x, 1.), name='y').parametrised()
+        z = yield j.Prior(0., name='z').parametrised()  # This is a zero size parameter
+        sigma = yield j.Prior(tfpd.Exponential(1.))
+        return y, z, sigma
+
+    def log_likelihood(y, z, sigma):
+        return tfpd.Normal(y, sigma).log_prob(0.) + z[:, 0]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = j.Model(prior_model=prior_model, log_likelihood=log_likelihood)
+        em = j.EvidenceMaximisation(model=model, ns_kwargs=dict(num_live_points=100, max_samples=20000))
+        assert any(p.numel() == 0 for p in model.params.values())
+        ns_results, params = em.train(num_steps=2)
+    assert set(params) == {"y_param", "z_param"}
+    assert np.isfinite(float(ns_results.log_Z_mean)) and int(ns_results.total_num_samples) > 100
+    # the evidence is maximised by y -> 0 (the datum): the parameter moved from the prior median x towards it
+    assert float(params["y_param"].abs().max()) > 0
+
+
+def test_evidence_maximisation_finds_the_analytic_optimum(torch_cuda):
+    """Z(mu) = int_0^1 N(3 | x + mu, 0.5) dx = Phi((3 - mu) / 0.5) - Phi((2 - mu) / 0.5): maximal at mu = 2.5 where
+    log Z = log(Phi(1) - Phi(-1)) = -0.38172."""
+    import warnings
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+    torch = torch_cuda
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(0., 1.), name="x")
+        mu = yield j.Prior(tfpd.Normal(0., 5.), name="mu").parametrised()
+        return x, mu
+
+    def log_likelihood(x, mu):
+        return tfpd.Normal(x + mu, 0.5).log_prob(3.0)
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = j.Model(prior_model=prior_model, log_likelihood=log_likelihood)
+        em = j.EvidenceMaximisation(model=model, ns_kwargs=dict(num_live_points=200, max_samples=40000))
+        ns_results, params = em.train(num_steps=6)
+        mu = float(model(params=params).transform_parametrised(torch.full((1,), 0.5, dtype=torch.float64, device="cuda"))["mu"])
+    assert abs(mu - 2.5) < 0.1, mu
+    assert abs(float(ns_results.log_Z_mean) - (-0.38172)) < max(4 * float(ns_results.log_Z_uncert), 0.05)

@@ -274,3 +274,110 @@ def test_xla_ffi_shim_compiles(tmp_path):
                          "-I" + os.path.join(ROOT, "include"), bad, "-o", os.path.join(tmp_path, "bad.o")],
                         capture_output=True, text=True)
     assert rc.returncode != 0 and "does not match its FFI binding" in rc.stderr
+
+
+# ---------------------------------------------------------------------------------------------------
+# parametrised models (framework/context.py, framework/prior.py:146-199) and the pieces of EvidenceMaximisation that
+# need no GPU
+# ---------------------------------------------------------------------------------------------------
+def test_parametrised_model_cpu():
+    import warnings
+    import torch
+    from scipy import stats
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(0., 1.))
+        y = yield j.Prior(tfpd.Normal(x, 1.), name='y').parametrised()
+        z = yield j.Prior(0., name='z').parametrised()  # a zero-size parameter (the reference's test_basic_zero_size_param)
+        sigma = yield j.Prior(tfpd.Exponential(1.))
+        with j.scope("lik"):
+            shift = j.get_parameter("shift", (1,), init=lambda shape, dtype: np.full(shape, 0.25))
+        return y + shift, z, sigma
+
+    def log_likelihood(y, z, sigma):
+        return tfpd.Normal(y, sigma).log_prob(0.) + z[:, 0] + j.get_parameter("offset", init=lambda: np.zeros(()))
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = j.Model(prior_model=prior_model, log_likelihood=log_likelihood)
+    assert model.is_general and model.U_ndims == 2
+    assert set(model.params) == {"y_param", "z_param", "lik.shift", "offset"}
+    assert model.num_params == 3 and model.params["z_param"].numel() == 0
+    assert "num_params=3" in repr(model)
+    U = torch.rand(7, 2, dtype=torch.float64)
+    got = model.log_likelihood_torch(U).numpy()
+    x, sigma = U[:, 0].numpy(), -np.log1p(-U[:, 1].numpy())
+    np.testing.assert_allclose(got, stats.norm(x + 0.25, sigma).logpdf(0.0), rtol=1e-12)  # y = median of N(x, 1) = x
+    # new parameter values make a new model; gradients flow to them
+    p = {k: v.clone().requires_grad_(True) for k, v in model.params.items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m2 = model(params=p)
+    total = m2.log_likelihood_torch(U).sum()
+    g = torch.autograd.grad(total, [p["y_param"], p["offset"]])
+    assert float(g[1]) == 7.0 and torch.isfinite(g[0]).all() and float(g[0].abs().sum()) > 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m3 = model(params={**model.params, "offset": torch.tensor(2.0, dtype=torch.float64)})
+    np.testing.assert_allclose(m3.log_likelihood_torch(U).numpy(), got + 2.0, rtol=1e-12)
+    with pytest.raises(ValueError):
+        j.get_parameter("orphan", (1,), init=np.zeros)  # no context outside a model
+    with pytest.raises(ValueError):
+        list(iter(lambda: j.Prior(tfpd.Uniform(0., 1.)).parametrised(), None))  # unnamed priors cannot be parametrised
+
+
+def test_closed_form_quantile_distributions():
+    import torch
+    from scipy import stats
+    from jaxns_b200 import distributions as d
+    U = torch.linspace(0.01, 0.99, 9, dtype=torch.float64).reshape(-1, 1)
+    checks = [(d.Exponential(2.0), stats.expon(scale=0.5)), (d.HalfNormal(1.5), stats.halfnorm(scale=1.5)),
+              (d.Cauchy(1.0, 2.0), stats.cauchy(1.0, 2.0)), (d.HalfCauchy(0.5, 2.0), stats.halfcauchy(0.5, 2.0)),
+              (d.Laplace(1.0, 0.7), stats.laplace(1.0, 0.7)), (d.Gumbel(0.3, 1.2), stats.gumbel_r(0.3, 1.2)),
+              (d.TruncatedNormal(0.5, 2.0, -1.0, 3.0), stats.truncnorm(-0.75, 1.25, loc=0.5, scale=2.0))]
+    for mine, ref in checks:
+        x = mine.quantile_torch(U)
+        np.testing.assert_allclose(x.numpy()[:, 0], ref.ppf(U.numpy()[:, 0]), rtol=1e-10, atol=1e-12)
+        np.testing.assert_allclose(mine.log_prob_torch(x).numpy(), ref.logpdf(x.numpy()[:, 0]), rtol=1e-10, atol=1e-12)
+    k = d.Kumaraswamy(2.0, 3.0)
+    x = k.quantile_torch(U)
+    np.testing.assert_allclose((1 - (1 - x ** 2) ** 3).numpy(), U.numpy(), rtol=1e-12)
+
+
+def test_newton_cg_and_m_step_cpu():
+    """The optimiser behind GlobalOptimisation's fine-tune and the M-step: Rosenbrock to its minimum; one M-step solve on
+    synthetic samples recovers the evidence-maximising parameter exactly where the likelihood does not depend on U."""
+    import warnings
+    import torch
+    import jaxns_b200 as j
+    from jaxns_b200 import distributions as tfpd
+    from jaxns_b200.experimental import EvidenceMaximisation, MStepData, newton_cg
+
+    def rosen(z):
+        return (100.0 * (z[1:] - z[:-1] ** 2) ** 2 + (1.0 - z[:-1]) ** 2).sum()
+
+    z, f, n_cg = newton_cg(rosen, torch.tensor([-1.2, 1.0, -0.5, 0.8], dtype=torch.float64), max_iters=200)
+    assert f < 1e-16 and n_cg > 0
+    np.testing.assert_allclose(z.numpy(), np.ones(4), atol=1e-7)
+
+    def prior_model():
+        x = yield j.Prior(tfpd.Uniform(0., 1.), name="x")
+        mu = yield j.Prior(tfpd.Normal(0., 5.), name="mu").parametrised()
+        return x, mu
+
+    def log_likelihood(x, mu):
+        return tfpd.Normal(mu, 1.0).log_prob(2.0) + 0.0 * x[:, 0]
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = j.Model(prior_model=prior_model, log_likelihood=log_likelihood)
+        em = EvidenceMaximisation(model=model)
+        n = 64
+        data = MStepData(U_samples=torch.rand(n, 1, dtype=torch.float64),
+                         log_weights=torch.full((n,), -np.log(n), dtype=torch.float64))
+        params, log_Z = em._m_step(None, model.params, data)
+        mu = model(params=params).transform_parametrised(torch.full((1,), 0.5, dtype=torch.float64))["mu"]
+    assert abs(float(mu) - 2.0) < 1e-6
+    assert abs(log_Z + 0.5 * np.log(2 * np.pi)) < 1e-10
