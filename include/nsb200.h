@@ -64,7 +64,11 @@ typedef struct NsSliceParams {
     int32_t num_slices;      /* S */
     int32_t num_phantom;     /* k (num_phantom_save) */
     int32_t midpoint_shrink; /* bool */
-    int32_t gradient_flags;  /* split path only: bit 0 = gradient_slice, bit 1 = gradient_guided (:202-214, :255-269) */
+    int32_t split_flags;     /* split path only.  bit 0 = gradient_slice, bit 1 = gradient_guided (:202-214, :255-269);
+                              * bits 8-11 = P, proposals per chain and round (0 or 1: one; at most 8): the P proposals are
+                              * drawn as if the earlier ones of the round were rejected and evaluated in one batched
+                              * likelihood call -- results are identical for every P, the calls per slice drop ~P-fold
+                              * until ~1 */
     int64_t num_live;    /* N: rows of live_U / live_logL (sorted ascending) */
     int64_t num_samples; /* m: keys = split(key, m) */
     int64_t chain_begin; /* this GPU evaluates chains [chain_begin, chain_end) -- the */
@@ -236,8 +240,10 @@ int nsb200_slice_batch_ws(const NsModelDesc *model, const NsSliceParams *p, cons
  * batched likelihood (BASELINE north_star).  Same chains as nsb200_slice_batch
  * (samplers/bases.py:63-75, samplers/uni_slice_sampler.py:114-273,343-441) when the likelihood
  * values agree.  Protocol, all on one stream, n = chain_end - chain_begin:
- *     nsb200_split_begin(...)            -> prop_U / prop_X [n,D]: first proposal of every chain
- *     repeat:  prop_logL[n] = vmap(log_likelihood)(prop_X)        (caller; XLA / torch on the device)
+ *     nsb200_split_begin(...)            -> prop_U / prop_X [P,n,D]: first proposals of every chain (P = proposals per
+ *                                           round from NsSliceParams.split_flags, default 1; row p*n + i = proposal p
+ *                                           of chain i)
+ *     repeat:  prop_logL[P*n] = vmap(log_likelihood)(prop_X)      (caller; XLA / torch on the device)
  *              nsb200_split_accept(...)  -> accept or shrink (NaN -> -inf, framework/ops.py:323-325),
  *                                           next proposal, *n_active += chains still running
  *     until n_active == 0, then nsb200_split_finish(...) -> the Sample / phantom arrays.
@@ -261,7 +267,7 @@ int nsb200_split_finish(const NsModelDesc *model, const NsSliceParams *p, void *
 /* Gradient variants of UniDimSliceSampler (samplers/uni_slice_sampler.py:202-214 gradient_slice: the slice direction is
  * the normalised gradient of log L w.r.t. U at the chain's point and only the uphill half of the bracket is searched;
  * :255-269 gradient_guided: the next direction is the Householder reflection of the last one about the gradient at the
- * accepted point).  With NsSliceParams.gradient_flags != 0 a chain that is about to start a slice waits for the
+ * accepted point).  With gradient bits in NsSliceParams.split_flags a chain that is about to start a slice waits for the
  * caller's gradient (jax.grad in the reference; any autodiff of the batched likelihood here):
  *     nsb200_split_begin, then per round:
  *         nsb200_split_grad_points -> U0 [n,D]; caller: grad [n,D] = d log L / dU at U0
@@ -379,8 +385,8 @@ int nsb200_engine_split_begin(NsEngine *e, double *prop_U, double *prop_X, nsb20
 int nsb200_engine_split_accept(NsEngine *e, const double *prop_logL, double *prop_U, double *prop_X,
                                uint64_t *n_active, nsb200_stream_t stream);
 int nsb200_engine_split_finish(NsEngine *e, nsb200_stream_t stream);
-/* The same gradient protocol for an engine with model.family == NSB200_FAM_EXTERNAL (flags: bit 0 slice, bit 1 guided). */
-int nsb200_engine_set_gradient_flags(NsEngine *e, int32_t flags);
+/* The same gradient protocol for an engine with model.family == NSB200_FAM_EXTERNAL (flags as NsSliceParams.split_flags). */
+int nsb200_engine_set_split_flags(NsEngine *e, int32_t flags);
 int nsb200_engine_split_grad_points(NsEngine *e, double *out_U, nsb200_stream_t stream);
 int nsb200_engine_split_grad_begin(NsEngine *e, const double *grad, double *prop_U, double *prop_X, uint64_t *n_active,
                                    nsb200_stream_t stream);

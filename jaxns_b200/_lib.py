@@ -23,7 +23,7 @@ class NsModelDesc(ctypes.Structure):
 
 class NsSliceParams(ctypes.Structure):
     _fields_ = [("num_slices", ctypes.c_int32), ("num_phantom", ctypes.c_int32),
-                ("midpoint_shrink", ctypes.c_int32), ("gradient_flags", ctypes.c_int32),
+                ("midpoint_shrink", ctypes.c_int32), ("split_flags", ctypes.c_int32),
                 ("num_live", ctypes.c_int64), ("num_samples", ctypes.c_int64),
                 ("chain_begin", ctypes.c_int64), ("chain_end", ctypes.c_int64)]
 
@@ -90,7 +90,7 @@ EXPORTS = (
     "nsb200_init_propose", "nsb200_transform_batch", "nsb200_engine_init_external", "nsb200_engine_split_begin",
     "nsb200_engine_split_accept", "nsb200_engine_split_finish", "nsb200_sample_evidence",
     "nsb200_slice_streams_bytes", "nsb200_slice_batch_ws", "nsb200_split_grad_points", "nsb200_split_grad_begin",
-    "nsb200_engine_set_gradient_flags", "nsb200_engine_contour", "nsb200_engine_split_grad_points", "nsb200_engine_split_grad_begin",
+    "nsb200_engine_set_split_flags", "nsb200_engine_contour", "nsb200_engine_split_grad_points", "nsb200_engine_split_grad_begin",
     "nsb200_engine_p2p_export", "nsb200_engine_p2p_connect", "nsb200_engine_p2p_enabled", "nsb200_engine_p2p_error",
 )
 

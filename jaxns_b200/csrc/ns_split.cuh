@@ -19,11 +19,19 @@ namespace nsb {
 // u32 per chain: j, ne, done, watchdog, run_key[2], after_key[2], sample_key2[2], need_grad, first_slice
 constexpr int kSplitWords = 12;
 
+// Proposals per chain and round.  A rejected proposal shrinks the bracket to its own t, which is known before its
+// likelihood is, so the next proposals of a slice can be drawn assuming rejection and evaluated in the SAME batched
+// likelihood call (first accepted wins) -- the fused kernel's speculation (ns_slice.cuh), bit-identical to one
+// proposal per round.  The caller's likelihood is launch-bound at these batch sizes, so P x more rows per call cost
+// nothing and the number of calls per slice drops from ~3.8 to ~1.1 at P = 8.
+constexpr int kSplitMaxP = 8;
+
 // Struct-of-arrays view of the per-chain state inside the caller's workspace.
 struct SplitState {
     double *U0;       // [n, D] current point of the chain
     double *d;        // [n, D] direction of the current slice
-    double *sc;       // [n, 4] left, right, t, logL0
+    double *sc;       // [n, 4] left, right (bracket at the start of the round), unused, logL0
+    double *ts;       // [n, kSplitMaxP] step lengths t of the round's proposals
     uint32_t *st;     // [n, kSplitWords]
     long long *nev;   // [n] likelihood evaluations so far
     double *phU;      // [n * k, D] phantom points
@@ -36,6 +44,7 @@ __host__ inline size_t split_workspace_bytes(int D, long long n, int k) {
     size_t b = 0;
     b += 2 * split_align((size_t) n * D * 8);
     b += split_align((size_t) n * 4 * 8);
+    b += split_align((size_t) n * kSplitMaxP * 8);
     b += split_align((size_t) n * kSplitWords * 4);
     b += split_align((size_t) n * 8);
     b += split_align((size_t) n * k * D * 8);
@@ -52,6 +61,8 @@ __host__ inline SplitState split_state_view(void *ws, int D, long long n, int k)
     p += split_align((size_t) n * D * 8);
     s.sc = (double *) p;
     p += split_align((size_t) n * 4 * 8);
+    s.ts = (double *) p;
+    p += split_align((size_t) n * kSplitMaxP * 8);
     s.st = (uint32_t *) p;
     p += split_align((size_t) n * kSplitWords * 4);
     s.nev = (long long *) p;
@@ -75,9 +86,10 @@ struct SplitArgs {
     const DevCtl *ctl;  // engine mode: key / contour / live buffer from the device-resident control block
     LiveSet live0, live1;
     SplitState state;
-    const double *prop_logL;          // [n] likelihood of the proposals written by the previous call
-    double *prop_U;                   // [n, D] proposals in U space (out)
-    double *prop_X;                   // [n, D] proposals through the prior transform (out, optional)
+    int P;                            // proposals per chain and round (1..kSplitMaxP); row p * n + i = proposal p of chain i
+    const double *prop_logL;          // [P, n] likelihood of the proposals written by the previous call
+    double *prop_U;                   // [P, n, D] proposals in U space (out)
+    double *prop_X;                   // [P, n, D] proposals through the prior transform (out, optional)
     unsigned long long *active;       // optional device counter: += chains that still need evaluations
     // gradient variants (uni_slice_sampler.py:202-214 gradient_slice = bit 0, :255-269 gradient_guided = bit 1): a chain
     // that starts a slice waits (need_grad) until the caller has evaluated d log L / dU at its current point
@@ -117,13 +129,16 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
     const double contour = *contour_ptr;
     const int S = a.S, kph = a.k;
     const bool midpoint = a.midpoint != 0;
+    const int P = a.P;
+    const long long nrows = a.chain_end - a.chain_begin;  // rows of one proposal plane
     uint32_t *st = a.state.st + row * kSplitWords;
     double *sc = a.state.sc + row * 4;
+    double *tsv = a.state.ts + row * kSplitMaxP;
 
     double U0[DPL], d[DPL];
     int j, ne;
     Key run_key, after_key, sk2;
-    double left, right, t, logL0;
+    double left, right, logL0;
     long long nev;
     bool new_slice;
     bool climb = false;  // gradient_slice with a usable gradient: only the uphill half of the bracket (left = 0)
@@ -135,7 +150,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         run_key = Key{st[4], st[5]};
         after_key = Key{st[6], st[7]};
         sk2 = Key{st[8], st[9]};
-        left = right = t = 0.0;
+        left = right = 0.0;
         logL0 = sc[3];
         nev = a.state.nev[row];
         double gv[DPL];
@@ -204,7 +219,7 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         ne = 0;
         nev = 0;
         run_key = after_key = Key{0, 0};
-        left = right = t = 0.0;
+        left = right = 0.0;
         new_slice = true;
         if (a.grad_flags) {  // the first slice starts in mode 2, once the gradient at the seed point is known
 #pragma unroll
@@ -247,7 +262,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         sk2 = Key{st[8], st[9]};
         left = sc[0];
         right = sc[1];
-        t = sc[2];
         logL0 = sc[3];
         nev = a.state.nev[row];
 #pragma unroll
@@ -256,17 +270,26 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
             U0[s] = (jj < D) ? a.state.U0[row * D + jj] : 0.5;
             d[s] = (jj < D) ? a.state.d[row * D + jj] : 0.0;
         }
-        double logL = a.prop_logL[row];
-        if (logL != logL) logL = -__longlong_as_double(0x7FF0000000000000ll);  // ops.py:323-325
-        const bool ok = (logL > contour) || ((logL0 == contour) && (logL == contour));  // :160-166
+        // first accepted proposal of the round wins (:160-166)
+        int hit = -1;
+        double logL = 0.0;
+        for (int p = P - 1; p >= 0; --p) {
+            double v = a.prop_logL[(long long) p * nrows + row];
+            if (v != v) v = -__longlong_as_double(0x7FF0000000000000ll);  // ops.py:323-325
+            if ((v > contour) || ((logL0 == contour) && (v == contour))) {
+                hit = p;
+                logL = v;
+            }
+        }
+        const bool ok = hit >= 0;
         if (ok) {
 #pragma unroll
             for (int s = 0; s < DPL; ++s) {
                 const int jj = s * G + g.lane;
-                U0[s] = (jj < D) ? a.prop_U[row * D + jj] : 0.5;  // the point that was evaluated
+                U0[s] = (jj < D) ? a.prop_U[((long long) hit * nrows + row) * D + jj] : 0.5;  // the point that was evaluated
             }
             logL0 = logL;
-            nev += ne;
+            nev += ne + hit + 1;
             // phantom capture: cumulative_samples[-(k+1):-1] (:430-440)
             if (kph > 0 && j >= S - 1 - kph && j < S - 1) {
                 const long long slot = row * kph + (j - (S - 1 - kph));
@@ -316,15 +339,15 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
             sample_direction<G, DPL>(g, D, after_key, d);  // :272
             new_slice = true;
         } else {
-            // _shrink_interval (:92-111) then the next draw of the while loop (:169-186)
+            // every proposal of the round was rejected: _shrink_interval (:92-111) P times, then the next draws of
+            // the while loop (:169-186)
             const double alpha = alpha_schedule(j, S);
-            if (t < 0.0) left = midpoint ? alpha * t : t;
-            if (t > 0.0) right = midpoint ? alpha * t : t;
-            const Key t_key = split_child(run_key, 1);
-            run_key = split_child(run_key, 0);
-            const double uu = uniform01(t_key, 0);
-            t = left + uu * (right - left);
-            ne += 1;
+            for (int p = 0; p < P; ++p) {
+                const double t = tsv[p];
+                if (t < 0.0) left = midpoint ? alpha * t : t;
+                if (t > 0.0) right = midpoint ? alpha * t : t;
+            }
+            ne += P;
             new_slice = false;
             if (ne > kMaxShrinkProposals) {
                 // watchdog (ns_slice.cuh kMaxShrinkProposals): the caller's likelihood is non-deterministic or NaN at
@@ -345,37 +368,60 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
             }
         }
     }
+    Key first_t_key = Key{0, 0};
     if (new_slice) {
         const Key slice_key = split_child(sk2, (uint64_t) j);  // :420
         run_key = split_child(slice_key, 0);                   // :201
-        const Key t_key = split_child(slice_key, 2);
+        first_t_key = split_child(slice_key, 2);
         after_key = split_child(slice_key, 3);
         slice_bounds<G, DPL>(g, D, U0, d, left, right);
         if (climb) left = 0.0;  // :214
-        const double uu = uniform01(t_key, 0);
-        t = left + uu * (right - left);  // _pick_point_in_interval :83-85
-        ne = 1;
+        ne = 0;  // proposals of this slice evaluated before this round
     }
-    double x[1][DPL];
+    // the round's P proposals, each drawn as if the previous ones had been rejected (_pick_point_in_interval :83-85)
+    {
+        const double alpha = alpha_schedule(j, S);
+        double l = left, r = right;
+        for (int p = 0; p < P; ++p) {
+            Key t_key;
+            if (new_slice && p == 0) {
+                t_key = first_t_key;
+            } else {
+                t_key = split_child(run_key, 1);  // :169
+                run_key = split_child(run_key, 0);
+            }
+            const double uu = uniform01(t_key, 0);
+            const double t = l + uu * (r - l);
+            if (g.lane == 0) tsv[p] = t;
+            if (t < 0.0) l = midpoint ? alpha * t : t;
+            if (t > 0.0) r = midpoint ? alpha * t : t;
+            double x[1][DPL];
+            const long long prow = (long long) p * nrows + row;
 #pragma unroll
-    for (int s = 0; s < DPL; ++s) {
-        const int jj = s * G + g.lane;
-        x[0][s] = fma(t, d[s], U0[s]);
-        if (jj < D) {
-            a.prop_U[row * D + jj] = x[0][s];
-            if (new_slice) {
-                a.state.U0[row * D + jj] = U0[s];
-                a.state.d[row * D + jj] = d[s];
+            for (int s = 0; s < DPL; ++s) {
+                const int jj = s * G + g.lane;
+                x[0][s] = fma(t, d[s], U0[s]);
+                if (jj < D) a.prop_U[prow * D + jj] = x[0][s];
+            }
+            if (a.prop_X) {
+                double X[1][DPL];
+                transform_dims<G, DPL, 1>(sm, g, x, X);
+#pragma unroll
+                for (int s = 0; s < DPL; ++s) {
+                    const int jj = s * G + g.lane;
+                    if (jj < D) a.prop_X[prow * D + jj] = X[0][s];
+                }
             }
         }
     }
-    if (a.prop_X) {
-        double X[1][DPL];
-        transform_dims<G, DPL, 1>(sm, g, x, X);
+    if (new_slice) {
 #pragma unroll
         for (int s = 0; s < DPL; ++s) {
             const int jj = s * G + g.lane;
-            if (jj < D) a.prop_X[row * D + jj] = X[0][s];
+            if (jj < D) {
+                a.state.U0[row * D + jj] = U0[s];
+                a.state.d[row * D + jj] = d[s];
+            }
         }
     }
     if (g.lane == 0) {
@@ -393,7 +439,6 @@ __global__ void __launch_bounds__(kThreadsPerBlock) k_split_step(SplitArgs a, in
         st[9] = sk2.b;
         sc[0] = left;
         sc[1] = right;
-        sc[2] = t;
         sc[3] = logL0;
         a.state.nev[row] = nev;
         if (a.active) atomicAdd(a.active, 1ull);

@@ -735,7 +735,10 @@ static int split_args(const NsModelDesc *model, const NsSliceParams *p, void *wo
     a.S = p->num_slices;
     a.k = p->num_phantom;
     a.midpoint = p->midpoint_shrink;
-    a.grad_flags = p->gradient_flags & 3;
+    a.grad_flags = p->split_flags & 3;
+    a.P = (p->split_flags >> 8) & 0xF;
+    if (a.P < 1) a.P = 1;
+    if (a.P > kSplitMaxP) return fail("NsSliceParams.split_flags: at most %d proposals per round", kSplitMaxP);
     a.state = split_state_view(workspace, model->D, n, p->num_phantom);
     return 0;
 }
@@ -791,7 +794,7 @@ extern "C" int nsb200_split_grad_begin(const NsModelDesc *model, const NsSlicePa
                                        double *prop_X, uint64_t *n_active, nsb200_stream_t stream) {
     SplitArgs a;
     if (split_args(model, p, workspace, workspace_bytes, a)) return 1;
-    if (!a.grad_flags) return fail("nsb200_split_grad_begin needs NsSliceParams.gradient_flags != 0");
+    if (!a.grad_flags) return fail("nsb200_split_grad_begin needs gradient bits in NsSliceParams.split_flags");
     if (!contour || !grad || !prop_U) return fail("NULL pointer");
     a.contour = contour;
     a.grad = grad;
@@ -1128,7 +1131,8 @@ struct NsEngine {
     bool tables_ready = false;  // seed table / evidence-term tables / alpha table depend only on (N, S): built once
     // family EXTERNAL: chain state of the split slice step (ns_split.cuh) for this rank's chains
     bool external = false;
-    int grad_flags = 0;  // gradient_slice (1) / gradient_guided (2) chains: nsb200_engine_set_gradient_flags
+    int grad_flags = 0;  // gradient_slice (1) / gradient_guided (2) chains: nsb200_engine_set_split_flags
+    int split_P = 1;     // proposals per chain and round of the split step
     void *split_ws = nullptr;
     size_t split_ws_bytes = 0;
 };
@@ -1879,15 +1883,19 @@ static int engine_split_args(NsEngine *e, SplitArgs &a) {
     a.live0 = e->live[0];
     a.live1 = e->live[1];
     a.grad_flags = e->grad_flags;
+    a.P = e->split_P;
     a.state = split_state_view(e->split_ws, e->D, e->rows_per_rank, (int) e->k);
     return 0;
 }
 
-extern "C" int nsb200_engine_set_gradient_flags(NsEngine *e, int32_t flags) {
+extern "C" int nsb200_engine_set_split_flags(NsEngine *e, int32_t flags) {
     if (!e) return fail("NULL engine");
-    if (!e->external) return fail("gradient variants run on the split path: create the engine with family EXTERNAL");
-    if (flags < 0 || flags > 3) return fail("gradient flags: bit 0 = gradient_slice, bit 1 = gradient_guided");
-    e->grad_flags = flags;
+    if (!e->external) return fail("split flags belong to the split path: create the engine with family EXTERNAL");
+    const int P = (flags >> 8) & 0xF;
+    if (flags < 0 || (flags & ~0xF03) || P > kSplitMaxP)
+        return fail("split flags: bit 0 = gradient_slice, bit 1 = gradient_guided, bits 8-11 = proposals per round (<= %d)", kSplitMaxP);
+    e->grad_flags = flags & 3;
+    e->split_P = P < 1 ? 1 : P;
     return 0;
 }
 
@@ -1905,7 +1913,7 @@ extern "C" int nsb200_engine_split_grad_begin(NsEngine *e, const double *grad, d
                                               uint64_t *n_active, nsb200_stream_t stream) {
     SplitArgs a;
     if (engine_split_args(e, a)) return 1;
-    if (!a.grad_flags) return fail("nsb200_engine_set_gradient_flags first");
+    if (!a.grad_flags) return fail("nsb200_engine_set_split_flags with gradient bits first");
     if (!grad || !prop_U) return fail("NULL pointer");
     a.grad = grad;
     a.prop_U = prop_U;

@@ -72,7 +72,7 @@ static ffi::Error SliceBatchImpl(Stream stream, ffi::Buffer<ffi::U32> key, ffi::
     p.num_slices = num_slices;
     p.num_phantom = num_phantom;
     p.midpoint_shrink = midpoint_shrink;
-    p.gradient_flags = 0;
+    p.split_flags = 0;
     p.num_live = live_U.dimensions()[0];
     p.num_samples = num_samples;
     p.chain_begin = chain_begin;

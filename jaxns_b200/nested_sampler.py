@@ -191,8 +191,8 @@ class ShardedStaticNestedSampler:
                                       s.num_phantom_save, int(s.midpoint_shrink), 0,
                                       self._rank if eng_world > 1 else 0, eng_world)
             self._engine = _Engine(cfg, keepalive=(self.model, desc))
-            if s.gradient_flags:
-                _lib.check(_lib.lib().nsb200_engine_set_gradient_flags(self._engine.h, ctypes.c_int32(s.gradient_flags)))
+            if getattr(self.model, "is_external", False) or s.gradient_flags:
+                _lib.check(_lib.lib().nsb200_engine_set_split_flags(self._engine.h, ctypes.c_int32(s.split_flags)))
         return self._engine
 
     def _run(self, key, term_cond) -> Tuple[int, TerminationRegister, NestedSamplerState]:
@@ -406,10 +406,11 @@ class ShardedStaticNestedSampler:
         lmin = self._contour_agreement(eng) if world > 1 else None
         D = self.model.U_ndims
         n = int(self.num_live_points * self.shell_fraction) // world
-        prop_U = torch.empty((n, D), dtype=torch.float64, device="cuda")
-        prop_X = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        P = self.sampler.split_proposals
+        prop_U = torch.full((P * n, D), 0.5, dtype=torch.float64, device="cuda")  # [P, n, D]: P proposals per chain and round
+        prop_X = torch.zeros((P * n, D), dtype=torch.float64, device="cuda")
         active = torch.zeros(1, dtype=torch.int64, device="cuda")
-        burst = max(4, self.sampler.num_slices // 4)
+        burst = max(4, self.sampler.num_slices // (4 * min(P, 4)))
         grad_pts = torch.empty((n, D), dtype=torch.float64, device="cuda") if self.sampler.gradient_flags else None
         _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
         while True:

@@ -16,6 +16,11 @@ from jaxns_b200.types import LivePointCollection, Sample, TerminationRegister
 
 __all__ = ["UniDimSliceSampler", "UniformSampler", "AbstractSampler", "EphemeralState", "SeedPoint"]
 
+# Proposals per chain and round of the split (caller-evaluated likelihood) path: each batched likelihood call evaluates
+# this many speculative proposals per chain (include/nsb200.h NsSliceParams.split_flags).  Results do not depend on it;
+# the likelihood calls per slice drop from ~3.8 (1) to ~1.1 (8).  1..8.
+SPLIT_PROPOSALS = 8
+
 
 class EphemeralState(NamedTuple):
     key: Any
@@ -98,6 +103,20 @@ class UniDimSliceSampler(AbstractSampler):
         the split propose / accept step with the model's gradient supplied between the kernels (Model.grad_U)."""
         return int(self.gradient_slice) | (int(self.gradient_guided) << 1)
 
+    @property
+    def split_proposals(self) -> int:
+        return int(getattr(self, "_split_proposals", None) or SPLIT_PROPOSALS)
+
+    @split_proposals.setter
+    def split_proposals(self, P: int):
+        if not 1 <= int(P) <= 8:
+            raise ValueError("split_proposals must be in 1..8")
+        self._split_proposals = int(P)
+
+    @property
+    def split_flags(self) -> int:
+        return self.gradient_flags | (self.split_proposals << 8)
+
     def _seed_table(self, N: int) -> torch.Tensor:
         t = self._seed_tables.get(N)
         if t is None:
@@ -124,7 +143,7 @@ class UniDimSliceSampler(AbstractSampler):
         out_nev = torch.empty(n, dtype=torch.int64, device="cuda")
         ph_U = torch.empty((n * k, D), dtype=torch.float64, device="cuda")
         ph_logL = torch.empty(n * k, dtype=torch.float64, device="cuda")
-        p = _lib.NsSliceParams(self.num_slices, k, int(self.midpoint_shrink), self.gradient_flags, N, int(num_samples),
+        p = _lib.NsSliceParams(self.num_slices, k, int(self.midpoint_shrink), self.split_flags, N, int(num_samples),
                                int(chain_begin), int(chain_end))
         d = self.model.desc(external=bool(self.gradient_flags))
         if getattr(self.model, "is_external", False) or self.gradient_flags:
@@ -147,14 +166,15 @@ class UniDimSliceSampler(AbstractSampler):
             return
         nbytes = L.nsb200_split_workspace_bytes(D, n, k)
         ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        prop_U = torch.empty((n, D), dtype=torch.float64, device="cuda")
-        prop_X = torch.empty((n, D), dtype=torch.float64, device="cuda")
+        P = self.split_proposals
+        prop_U = torch.full((P * n, D), 0.5, dtype=torch.float64, device="cuda")  # [P, n, D]
+        prop_X = torch.zeros((P * n, D), dtype=torch.float64, device="cuda")
         active = torch.zeros(1, dtype=torch.int64, device="cuda")
         st = _lib.stream_arg()
         _lib.check(L.nsb200_split_begin(ctypes.byref(d), ctypes.byref(p), _lib.key_arg(key), _lib.ptr(contour),
                                         _lib.ptr(live_U), _lib.ptr(live_logL), _lib.ptr(self._seed_table(N)),
                                         _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(prop_U), _lib.ptr(prop_X), st))
-        burst = max(4, self.num_slices // 4)  # likelihood rounds between reads of the active-chain counter
+        burst = max(4, self.num_slices // (4 * min(P, 4)))  # likelihood rounds between reads of the active-chain counter
         grad_pts = torch.empty((n, D), dtype=torch.float64, device="cuda") if self.gradient_flags else None
         while True:
             for r in range(burst):

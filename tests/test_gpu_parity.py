@@ -558,6 +558,15 @@ def test_split_batch_equals_fused_batch(torch_cuda, name, D, N, S, k, midpoint):
     if k:
         assert torch.equal(fp.U_sample, ep.U_sample)
         assert torch.equal(fp.log_L, ep.log_L)
+    # the number of speculative proposals per round (default 8) does not change a single bit
+    for P in (1, 2, 5):
+        sampler = j.UniDimSliceSampler(model=external, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint, perfect=True)
+        sampler.split_proposals = P
+        ps, pp = sampler.get_samples_batch(random.PRNGKey(9), contour, state, m)
+        assert torch.equal(ps.num_likelihood_evaluations, es.num_likelihood_evaluations), P
+        assert torch.equal(ps.U_sample, es.U_sample) and torch.equal(ps.log_L, es.log_L), P
+        if k:
+            assert torch.equal(pp.U_sample, ep.U_sample), P
     # sharded ranges of the split path reproduce the full batch
     sampler = j.UniDimSliceSampler(model=external, num_slices=S, num_phantom_save=k, midpoint_shrink=midpoint, perfect=True)
     a, _ = sampler.get_samples_batch(random.PRNGKey(9), contour, state, m, 0, m // 2)
