@@ -22,12 +22,27 @@ def _needs_general(*params) -> bool:
     return any(_is_tensor(p) or getattr(p, "_nsb200_placeholder", False) for p in params)
 
 
+_const_cache = {}
+
+
 def _t(x, like=None):
+    """parameter -> float64 tensor on the device of `like`.  Host constants (numbers, numpy arrays) are uploaded once
+    and cached by content: a prior model rebuilds its distributions on every pass, and a fresh host-to-device copy per
+    pass would both cost a synchronisation and make the pass impossible to capture in a CUDA graph."""
     import torch
-    dev = like.device if like is not None else ("cuda" if torch.cuda.is_available() else "cpu")
+    dev = like.device if like is not None else torch.device("cuda" if torch.cuda.is_available() else "cpu")
     if _is_tensor(x):
         return x.to(dtype=torch.float64, device=dev)
-    return torch.as_tensor(np.asarray(x, np.float64), dtype=torch.float64, device=dev)
+    arr = np.asarray(x, np.float64)
+    if arr.size > 4096:
+        return torch.as_tensor(arr, dtype=torch.float64, device=dev)
+    key = (arr.tobytes(), arr.shape, str(dev))
+    t = _const_cache.get(key)
+    if t is None:
+        if len(_const_cache) >= 1024:
+            _const_cache.clear()
+        t = _const_cache[key] = torch.as_tensor(arr, dtype=torch.float64, device=dev)
+    return t
 
 
 def _rows(x, like):

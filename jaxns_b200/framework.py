@@ -266,8 +266,8 @@ class Model:
                 ret, _, _, _ = self._run_generator(U, bound=False)
                 out = self.log_likelihood.fn(*ret)
         else:
-            a = torch.from_numpy(self._a).to(U.device)
-            b = torch.from_numpy(self._b).to(U.device)
+            a = distributions._t(self._a, U)
+            b = distributions._t(self._b, U)
             q = U if self._prior_kind == distributions.Uniform.prior_kind else torch.special.ndtri(U)
             X = a + b * q
             if self.is_external:

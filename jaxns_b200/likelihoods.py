@@ -174,4 +174,5 @@ def jaxify_likelihood(log_likelihood, vectorised: bool = False):
             out = np.asarray([log_likelihood(*[h[i] for h in host]) for i in range(host[0].shape[0])], np.float64)
         return torch.from_numpy(out.reshape(-1)).to(args[0].device)
 
+    _log_likelihood._nsb200_host_callback = True  # leaves the device: the likelihood rounds are not graph-captured
     return _log_likelihood

@@ -407,12 +407,37 @@ class ShardedStaticNestedSampler:
         D = self.model.U_ndims
         n = int(self.num_live_points * self.shell_fraction) // world
         P = self.sampler.split_proposals
-        prop_U = torch.full((P * n, D), 0.5, dtype=torch.float64, device="cuda")  # [P, n, D]: P proposals per chain and round
-        prop_X = torch.zeros((P * n, D), dtype=torch.float64, device="cuda")
-        active = torch.zeros(1, dtype=torch.int64, device="cuda")
         burst = max(4, self.sampler.num_slices // (4 * min(P, 4)))
+        # buffers (and the captured graph of a burst, below) live as long as the engine: a second run replays at once
+        cache = getattr(self, "_ext_cache", None)
+        if cache is None or cache["key"] != (id(eng), P, n, D, burst):
+            cache = dict(key=(id(eng), P, n, D, burst), graph=None,
+                         prop_U=torch.full((P * n, D), 0.5, dtype=torch.float64, device="cuda"),  # [P, n, D]
+                         prop_X=torch.zeros((P * n, D), dtype=torch.float64, device="cuda"),
+                         active=torch.zeros(1, dtype=torch.int64, device="cuda"))
+            self._ext_cache = cache
+        prop_U, prop_X, active = cache["prop_U"], cache["prop_X"], cache["active"]
         grad_pts = torch.empty((n, D), dtype=torch.float64, device="cuda") if self.sampler.gradient_flags else None
         _lib.check(L.nsb200_engine_register(eng.h, ctypes.byref(reg), stream))
+
+        def one_burst(st):
+            for r in range(burst):
+                if grad_pts is not None:  # uni_slice_sampler.py:202-214, :255-269: gradients between the kernels
+                    _lib.check(L.nsb200_engine_split_grad_points(eng.h, _lib.ptr(grad_pts), st))
+                    grad = self.model.grad_U(grad_pts)
+                    _lib.check(L.nsb200_engine_split_grad_begin(eng.h, _lib.ptr(grad), _lib.ptr(prop_U),
+                                                                _lib.ptr(prop_X), ctypes.c_void_p(0), st))
+                logL = self.model.external_log_likelihood(prop_U, prop_X)
+                last = r == burst - 1
+                if last:
+                    active.zero_()
+                _lib.check(L.nsb200_engine_split_accept(eng.h, _lib.ptr(logL), _lib.ptr(prop_U), _lib.ptr(prop_X),
+                                                        _lib.ptr(active) if last else ctypes.c_void_p(0), st))
+
+        use_graph = (os.environ.get("NSB200_SPLIT_GRAPH", "1") != "0" and grad_pts is None
+                     and not getattr(getattr(self.model.log_likelihood, "fn", None), "_nsb200_host_callback", False))
+        graph = cache["graph"] if use_graph else None
+        try_graph = use_graph and graph is None
         while True:
             if host_tc is None:
                 done = bool(reg.done)
@@ -423,18 +448,25 @@ class ShardedStaticNestedSampler:
             _lib.check(L.nsb200_engine_step_begin(eng.h, stream))
             _lib.check(L.nsb200_engine_split_begin(eng.h, _lib.ptr(prop_U), _lib.ptr(prop_X), stream))
             while True:
-                for r in range(burst):
-                    if grad_pts is not None:  # uni_slice_sampler.py:202-214, :255-269: gradients between the kernels
-                        _lib.check(L.nsb200_engine_split_grad_points(eng.h, _lib.ptr(grad_pts), stream))
-                        grad = self.model.grad_U(grad_pts)
-                        _lib.check(L.nsb200_engine_split_grad_begin(eng.h, _lib.ptr(grad), _lib.ptr(prop_U),
-                                                                    _lib.ptr(prop_X), ctypes.c_void_p(0), stream))
-                    logL = self.model.external_log_likelihood(prop_U, prop_X)
-                    last = r == burst - 1
-                    if last:
-                        active.zero_()
-                    _lib.check(L.nsb200_engine_split_accept(eng.h, _lib.ptr(logL), _lib.ptr(prop_U), _lib.ptr(prop_X),
-                                                            _lib.ptr(active) if last else ctypes.c_void_p(0), stream))
+                if graph is not None:
+                    graph.replay()
+                else:
+                    one_burst(stream)
+                    if try_graph:
+                        # the burst is launch-bound (a dozen small kernels per round): capture it once, replay it for
+                        # the rest of the run.  Likelihoods that synchronise or call back to the host cannot be
+                        # captured; they keep the eager loop.
+                        try_graph = False
+                        try:
+                            graph = cache["graph"] = self._capture(one_burst)
+                        except Exception as exc:  # noqa: BLE001
+                            graph = None
+                            try:
+                                torch.cuda.synchronize()
+                            except Exception:  # noqa: BLE001
+                                pass
+                            warnings.warn(f"nsb200: the likelihood rounds could not be captured in a CUDA graph ({exc}); "
+                                          "continuing with eager launches (NSB200_SPLIT_GRAPH=0 silences this)")
                 if world > 1:  # every rank leaves the rounds together (the all-gather below must stay matched)
                     import torch.distributed as dist
                     dist.all_reduce(active, op=dist.ReduceOp.MAX)
@@ -455,6 +487,21 @@ class ShardedStaticNestedSampler:
             if lmin is not None:
                 lmin.check()
         _lib.check(L.nsb200_engine_finalize(eng.h, stream))
+
+    @staticmethod
+    def _capture(fn):
+        """Capture fn(stream) into a CUDA graph on a side stream (torch.cuda.graph() without its gc / cache flush)."""
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g.capture_begin()
+            try:
+                fn(_lib.stream_arg())
+            finally:
+                g.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
+        return g
 
     def _effective_host_cond(self, term_cond):
         """max_samples lowered by one iteration's space (sharded_static.py:464-470), applied to every leaf."""

@@ -18,8 +18,9 @@ __all__ = ["UniDimSliceSampler", "UniformSampler", "AbstractSampler", "Ephemeral
 
 # Proposals per chain and round of the split (caller-evaluated likelihood) path: each batched likelihood call evaluates
 # this many speculative proposals per chain (include/nsb200.h NsSliceParams.split_flags).  Results do not depend on it;
-# the likelihood calls per slice drop from ~3.8 (1) to ~1.1 (8).  1..8.
-SPLIT_PROPOSALS = 8
+# the likelihood calls per slice drop from ~3.8 (1) to ~1.3 (4) and ~1.1 (8).  1..8; 4 measured best on the config-2
+# problem with a torch likelihood (profiles/r2/external_path_r2.txt).
+SPLIT_PROPOSALS = 4
 
 
 class EphemeralState(NamedTuple):

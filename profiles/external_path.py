@@ -30,20 +30,28 @@ def log_likelihood(x):
     return c - 0.5 * (z * z).sum(-1)
 
 
-for name, model in (("callable", j.Model(prior_model, log_likelihood)),
-                    ("registered", j.Model(prior_model, lk.DenseGaussianLikelihood(np.full(D, 15.0), covariance_matrix=cov)))):
+from jaxns_b200 import samplers
+
+cases = [("callable", P, g) for P in (1, 2, 4, 8) for g in (0, 1)] + [("registered", 0, 0)]
+for name, P, g in cases:
+    if name == "callable":
+        samplers.SPLIT_PROPOSALS = P
+        os.environ["NSB200_SPLIT_GRAPH"] = str(g)
+        model = j.Model(prior_model, log_likelihood)
+    else:
+        model = j.Model(prior_model, lk.DenseGaussianLikelihood(np.full(D, 15.0), covariance_matrix=cov))
     ns = j.NestedSampler(model=model, num_live_points=N)
     tc = j.TerminationCondition(max_samples=float(SHELLS * N // 2))
-    for rep in range(2):
+    first = None
+    for rep in range(3):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
         e0.record()
         reason, state = ns(random.PRNGKey(rep), tc)
         e1.record()
         torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
+        first = first if first is not None else e0.elapsed_time(e1)
     evals = int(ns.nested_sampler.last_register.num_likelihood_evaluations)
     ms = e0.elapsed_time(e1)
-    print(f"{name:10s}: {SHELLS} shells, {evals} evals in {ms:.1f} ms (wall {1e3 * wall:.1f}) = {evals / ms / 1e3:.2f} M evals/s, "
-          f"{ms / SHELLS:.2f} ms per shell")
+    tag = f"{name} P={P} graph={g}" if name == "callable" else name
+    print(f"{tag:24s}: {SHELLS} shells, {evals} evals in {ms:8.1f} ms = {evals / ms / 1e3:7.2f} M evals/s, {ms / SHELLS:6.2f} ms per shell (first run {first:.0f} ms)")
