@@ -227,4 +227,161 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(nsb200_ffi_sample_evidence, SampleEvidenceImpl,
                                   .Arg<ffi::Buffer<ffi::F64>>()
                                   .Ret<ffi::Buffer<ffi::F64>>());
 
+// ---- arbitrary JAX likelihoods: the slice step split around vmap(log_likelihood) (include/nsb200.h nsb200_split_*) -----
+// XLA buffers are values, the chain state is not: `workspace`, `prop_U` (the accepted point of a round is read back from
+// it) and the `n_active` counter are operands AND results of the same call and must be bound with
+// jax.ffi.ffi_call(..., input_output_aliases={...}) so that both name one allocation (the handlers refuse otherwise;
+// `n_active` comes in as zeros).  One jitted round on the jaxns side is then
+//     logL = jax.vmap(model.log_prob_likelihood)(prop_U)                       # the user's JAX likelihood, on the device
+//     ws, prop_U, prop_X, n_active = ffi_call("nsb200_split_accept", ...)(contour, logL, a, b, ws, prop_U, zeros)
+// inside a lax.while_loop on n_active > 0 (uni_slice_sampler.py:114-273 is the loop this replaces).
+static NsModelDesc ExternalDesc(int32_t prior_kind, const ffi::Buffer<ffi::F64> &prior_a, const ffi::Buffer<ffi::F64> &prior_b) {
+    NsModelDesc m;
+    m.family = NSB200_FAM_EXTERNAL;
+    m.D = (int32_t) prior_a.element_count();
+    m.prior_kind = prior_kind;
+    m.K = 0;
+    m.prior_a = prior_a.typed_data();
+    m.prior_b = prior_b.typed_data();
+    m.params = nullptr;
+    m.n_params = 0;
+    return m;
+}
+
+static NsSliceParams SplitParams(int32_t num_slices, int32_t num_phantom, int32_t midpoint_shrink, int32_t split_flags,
+                                 int64_t num_live, int64_t num_samples, int64_t chain_begin, int64_t chain_end) {
+    NsSliceParams p;
+    p.num_slices = num_slices;
+    p.num_phantom = num_phantom;
+    p.midpoint_shrink = midpoint_shrink;
+    p.split_flags = split_flags;
+    p.num_live = num_live;
+    p.num_samples = num_samples;
+    p.chain_begin = chain_begin;
+    p.chain_end = chain_end;
+    return p;
+}
+
+static ffi::Error SplitBeginImpl(Stream stream, ffi::Buffer<ffi::U32> key, ffi::Buffer<ffi::F64> contour,
+                                 ffi::Buffer<ffi::F64> live_U, ffi::Buffer<ffi::F64> live_logL,
+                                 ffi::Buffer<ffi::F64> seed_table, ffi::Buffer<ffi::F64> prior_a,
+                                 ffi::Buffer<ffi::F64> prior_b, ffi::ResultBuffer<ffi::U8> workspace,
+                                 ffi::ResultBuffer<ffi::F64> prop_U, ffi::ResultBuffer<ffi::F64> prop_X,
+                                 int32_t prior_kind, int32_t num_slices, int32_t num_phantom, int32_t midpoint_shrink,
+                                 int32_t split_flags, int64_t num_samples, int64_t chain_begin, int64_t chain_end) {
+    if (live_U.dimensions().size() != 2) return ffi::Error::InvalidArgument("live_U must be [N, D]");
+    uint32_t k2[2];
+    if (ffi::Error err = ReadKey(key, k2, stream); !err.success()) return err;
+    const NsModelDesc m = ExternalDesc(prior_kind, prior_a, prior_b);
+    const NsSliceParams p = SplitParams(num_slices, num_phantom, midpoint_shrink, split_flags, live_U.dimensions()[0],
+                                        num_samples, chain_begin, chain_end);
+    return Status(nsb200_split_begin(&m, &p, k2, contour.typed_data(), live_U.typed_data(), live_logL.typed_data(),
+                                     seed_table.typed_data(), workspace->typed_data(),
+                                     (int64_t) workspace->element_count(), prop_U->typed_data(), prop_X->typed_data(),
+                                     stream));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(nsb200_ffi_split_begin, SplitBeginImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<Stream>>()
+                                  .Arg<ffi::Buffer<ffi::U32>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Attr<int32_t>("prior_kind")
+                                  .Attr<int32_t>("num_slices")
+                                  .Attr<int32_t>("num_phantom")
+                                  .Attr<int32_t>("midpoint_shrink")
+                                  .Attr<int32_t>("split_flags")
+                                  .Attr<int64_t>("num_samples")
+                                  .Attr<int64_t>("chain_begin")
+                                  .Attr<int64_t>("chain_end"));
+
+static ffi::Error SplitAcceptImpl(Stream stream, ffi::Buffer<ffi::F64> contour, ffi::Buffer<ffi::F64> prop_logL,
+                                  ffi::Buffer<ffi::F64> prior_a, ffi::Buffer<ffi::F64> prior_b,
+                                  ffi::Buffer<ffi::U8> workspace_in, ffi::Buffer<ffi::F64> prop_U_in,
+                                  ffi::Buffer<ffi::U64> n_active_in, ffi::ResultBuffer<ffi::U8> workspace,
+                                  ffi::ResultBuffer<ffi::F64> prop_U, ffi::ResultBuffer<ffi::F64> prop_X,
+                                  ffi::ResultBuffer<ffi::U64> n_active, int32_t prior_kind, int32_t num_slices,
+                                  int32_t num_phantom, int32_t midpoint_shrink, int32_t split_flags, int64_t num_live,
+                                  int64_t num_samples, int64_t chain_begin, int64_t chain_end) {
+    if (workspace_in.typed_data() != workspace->typed_data() || prop_U_in.typed_data() != prop_U->typed_data() ||
+        n_active_in.typed_data() != n_active->typed_data())
+        return ffi::Error::InvalidArgument("workspace, prop_U and n_active must be bound with input_output_aliases");
+    const NsModelDesc m = ExternalDesc(prior_kind, prior_a, prior_b);
+    const NsSliceParams p = SplitParams(num_slices, num_phantom, midpoint_shrink, split_flags, num_live, num_samples,
+                                        chain_begin, chain_end);
+    return Status(nsb200_split_accept(&m, &p, contour.typed_data(), prop_logL.typed_data(), workspace->typed_data(),
+                                      (int64_t) workspace->element_count(), prop_U->typed_data(), prop_X->typed_data(),
+                                      n_active->typed_data(), stream));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(nsb200_ffi_split_accept, SplitAcceptImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<Stream>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::U64>>()
+                                  .Ret<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::U64>>()
+                                  .Attr<int32_t>("prior_kind")
+                                  .Attr<int32_t>("num_slices")
+                                  .Attr<int32_t>("num_phantom")
+                                  .Attr<int32_t>("midpoint_shrink")
+                                  .Attr<int32_t>("split_flags")
+                                  .Attr<int64_t>("num_live")
+                                  .Attr<int64_t>("num_samples")
+                                  .Attr<int64_t>("chain_begin")
+                                  .Attr<int64_t>("chain_end"));
+
+static ffi::Error SplitFinishImpl(Stream stream, ffi::Buffer<ffi::F64> prior_a, ffi::Buffer<ffi::F64> prior_b,
+                                  ffi::Buffer<ffi::U8> workspace, ffi::ResultBuffer<ffi::F64> out_U,
+                                  ffi::ResultBuffer<ffi::F64> out_logL, ffi::ResultBuffer<ffi::S64> out_nevals,
+                                  ffi::ResultBuffer<ffi::F64> ph_U, ffi::ResultBuffer<ffi::F64> ph_logL,
+                                  int32_t prior_kind, int32_t num_slices, int32_t num_phantom, int32_t midpoint_shrink,
+                                  int32_t split_flags, int64_t num_live, int64_t num_samples, int64_t chain_begin,
+                                  int64_t chain_end) {
+    const NsModelDesc m = ExternalDesc(prior_kind, prior_a, prior_b);
+    const NsSliceParams p = SplitParams(num_slices, num_phantom, midpoint_shrink, split_flags, num_live, num_samples,
+                                        chain_begin, chain_end);
+    // the C entry point only reads the workspace; XLA hands operands over as const
+    return Status(nsb200_split_finish(&m, &p, const_cast<uint8_t *>(workspace.typed_data()),
+                                      (int64_t) workspace.element_count(), out_U->typed_data(), out_logL->typed_data(),
+                                      out_nevals->typed_data(), num_phantom ? ph_U->typed_data() : nullptr,
+                                      num_phantom ? ph_logL->typed_data() : nullptr, stream));
+}
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(nsb200_ffi_split_finish, SplitFinishImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<Stream>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::F64>>()
+                                  .Arg<ffi::Buffer<ffi::U8>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::S64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Ret<ffi::Buffer<ffi::F64>>()
+                                  .Attr<int32_t>("prior_kind")
+                                  .Attr<int32_t>("num_slices")
+                                  .Attr<int32_t>("num_phantom")
+                                  .Attr<int32_t>("midpoint_shrink")
+                                  .Attr<int32_t>("split_flags")
+                                  .Attr<int64_t>("num_live")
+                                  .Attr<int64_t>("num_samples")
+                                  .Attr<int64_t>("chain_begin")
+                                  .Attr<int64_t>("chain_end"));
+
 #endif  // __has_include("xla/ffi/api/ffi.h")

@@ -263,7 +263,8 @@ def test_xla_ffi_shim_compiles(tmp_path):
                            "-I" + os.path.join(ROOT, "jaxns_b200", "csrc", "ffi_stub"), "-I" + os.path.join(ROOT, "include"),
                            src, "-o", obj])
     syms = subprocess.run(["nm", "-g", "--defined-only", obj], capture_output=True, text=True, check=True).stdout
-    for name in ("slice_batch", "init_batch", "forward_batch", "count_crossed_edges", "evidence_stats", "sample_evidence"):
+    for name in ("slice_batch", "init_batch", "forward_batch", "count_crossed_edges", "evidence_stats", "sample_evidence",
+                 "split_begin", "split_accept", "split_finish"):
         assert f"nsb200_ffi_{name}" in syms
     # a handler whose signature drifts from its binding must not compile
     bad = os.path.join(tmp_path, "bad.cc")
