@@ -22,6 +22,18 @@ class RegisteredLikelihood:
     K: int = 0
     __nsb200_family__ = True
 
+    def _dev(self, name: str, array: np.ndarray, like):
+        """A host parameter as a device tensor, uploaded once per device (the gradient rounds are captured in a CUDA
+        graph, which rules out host-to-device copies inside them)."""
+        import torch
+        cache = self.__dict__.setdefault("_dev_cache", {})
+        key = (name, str(like.device))
+        if key not in cache:
+            if callable(array):
+                array = array()
+            cache[key] = torch.as_tensor(np.ascontiguousarray(array, np.float64), device=like.device)
+        return cache[key]
+
     def pack(self, D: int) -> np.ndarray:
         return np.zeros(0)
 
@@ -74,8 +86,8 @@ class DenseGaussianLikelihood(RegisteredLikelihood):
     def log_prob_torch(self, X):
         import torch
         D = self.loc.size
-        Linv = torch.from_numpy(np.tril(np.linalg.solve(self.scale_tril, np.eye(D)))).to(X.device)
-        z = (X - torch.from_numpy(self.loc).to(X.device)) @ Linv.T
+        Linv = self._dev("Linv", lambda: np.tril(np.linalg.solve(self.scale_tril, np.eye(D))), X)
+        z = (X - self._dev("loc", self.loc, X)) @ Linv.T
         c = -np.sum(np.log(np.diag(self.scale_tril))) - 0.5 * D * np.log(2.0 * np.pi)
         return c - 0.5 * (z * z).sum(-1)
 
@@ -105,9 +117,9 @@ class GaussianMixtureLikelihood(RegisteredLikelihood):
 
     def log_prob_torch(self, X):
         import torch
-        mu = torch.from_numpy(self.means).to(X.device)
-        var = torch.from_numpy(self.variances).to(X.device)
-        logc = torch.from_numpy(self.log_weights - 0.5 * np.sum(np.log(2.0 * np.pi * self.variances), axis=1)).to(X.device)
+        mu = self._dev("means", self.means, X)
+        var = self._dev("variances", self.variances, X)
+        logc = self._dev("logc", lambda: self.log_weights - 0.5 * np.sum(np.log(2.0 * np.pi * self.variances), axis=1), X)
         q = ((X[:, None, :] - mu[None]) ** 2 / var[None]).sum(-1)
         return torch.logsumexp(logc[None] - 0.5 * q, dim=1)
 
@@ -146,9 +158,9 @@ class GaussianShellsLikelihood(RegisteredLikelihood):
 
     def log_prob_torch(self, X):
         import torch
-        c = torch.from_numpy(self.centres).to(X.device)
-        w = torch.from_numpy(self.widths).to(X.device)
-        r = torch.from_numpy(self.radii).to(X.device)
+        c = self._dev("centres", self.centres, X)
+        w = self._dev("widths", self.widths, X)
+        r = self._dev("radii", self.radii, X)
         e = torch.sqrt(((X[:, None, :] - c[None]) ** 2).sum(-1)) - r[None]
         g = -0.5 * e * e / (w * w)[None] - torch.log(torch.sqrt(2.0 * np.pi * w * w))[None]
         return torch.logsumexp(g, dim=1)

@@ -434,7 +434,8 @@ class ShardedStaticNestedSampler:
                 _lib.check(L.nsb200_engine_split_accept(eng.h, _lib.ptr(logL), _lib.ptr(prop_U), _lib.ptr(prop_X),
                                                         _lib.ptr(active) if last else ctypes.c_void_p(0), st))
 
-        use_graph = (os.environ.get("NSB200_SPLIT_GRAPH", "1") != "0" and grad_pts is None
+        use_graph = (os.environ.get("NSB200_SPLIT_GRAPH", "1") != "0"
+                     and (grad_pts is None or os.environ.get("NSB200_SPLIT_GRAPH_GRAD", "1") != "0")
                      and not getattr(getattr(self.model.log_likelihood, "fn", None), "_nsb200_host_callback", False))
         graph = cache["graph"] if use_graph else None
         try_graph = use_graph and graph is None
