@@ -2,7 +2,7 @@
 """Tiny invocation of every kernel family for compute-sanitizer (racecheck / memcheck):
     compute-sanitizer --tool racecheck python profiles/sanitizer_run.py
 slice chains (lane kernel, DMMA kernel, warp team), stream generator, merge (brute + tiled), register update, radix sort,
-tree counts, evidence scan, sample_evidence, split propose / accept."""
+tree counts, evidence scan, sample_evidence, split propose / accept (plain, gradient_slice, gradient_guided)."""
 import os
 import sys
 
@@ -44,5 +44,15 @@ def prior_model():
 ns = j.NestedSampler(model=j.Model(prior_model, ext), num_live_points=48, max_samples=400)
 reason, state = ns(random.PRNGKey(0), j.TerminationCondition(max_samples=200.0))
 print("external", reason, flush=True)
+# gradient variants (k_split_step mode 2, k_split_export_U0) with the default 4 speculative proposals per round
+import warnings
+warnings.simplefilter("ignore")
+for kw in (dict(gradient_slice=True), dict(gradient_guided=True)):
+    sampler = j.UniDimSliceSampler(model=j.Model(prior_model, ext), num_slices=4, num_phantom_save=1, midpoint_shrink=True,
+                                   perfect=True, **kw)
+    sns = j.ShardedStaticNestedSampler(model=sampler.model, max_samples=400, init_efficiency_threshold=0.1, sampler=sampler,
+                                       num_live_points=48)
+    reason, reg, state = sns._run(random.PRNGKey(0), j.TerminationCondition(max_samples=200.0))
+    print("gradient", kw, reason, flush=True)
 torch.cuda.synchronize()
 print("sanitizer_run done")
