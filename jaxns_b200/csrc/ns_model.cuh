@@ -207,6 +207,38 @@ __device__ __forceinline__ void dmma_m8n8k4(double &c0, double &c1, double a, do
         : "d"(a), "d"(b));
 }
 
+// Sum over the 32 lanes of a warp through ONE FP64 tensor-core instruction per value instead of a 5-step butterfly:
+// with A = ones(8x4) and B[k][n] = the value of lane 4 n + k, C[m][n] = sum over the 4 lanes of group n for every row
+// m; lane (g, t) holds C[g][2 t] and C[g][2 t + 1], so c0 + c1 is the sum over 8 lanes and two shuffle steps over t
+// finish it (DMMA 26 cycles + add + 2 x (shuffle + add) against 5 x (shuffle + add)).  Measured on the same box
+// (profiles/r2/regcap_ab_r2.txt): one launch over 200 / 1600 / 25600 chains of config 2 0.510 -> 0.489 / 0.697 -> 0.691 /
+// 8.04 -> 7.92 ms, a whole run 95.2 -> 94.5 ms.  -DNSB_DMMA_REDUCE=0 restores the butterfly.
+#ifndef NSB_DMMA_REDUCE
+#define NSB_DMMA_REDUCE 1
+#endif
+constexpr bool kDmmaReduce = NSB_DMMA_REDUCE != 0;
+
+template <int P>
+__device__ __forceinline__ void warp_sum_dmma(double (&v)[P]) {
+    double s[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        double c0 = 0.0, c1 = 0.0;
+        dmma_m8n8k4(c0, c1, 1.0, v[p]);
+        s[p] = c0 + c1;
+    }
+#pragma unroll
+    for (int o = 1; o <= 2; o <<= 1) {
+        double y[P];
+#pragma unroll
+        for (int p = 0; p < P; ++p) y[p] = __shfl_xor_sync(0xFFFFFFFFu, s[p], o);
+#pragma unroll
+        for (int p = 0; p < P; ++p) s[p] += y[p];
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) v[p] = s[p];
+}
+
 // Per-thread registers of the dense factor (only meaningful for G == 32, DPL == 1): the lane's row of L^-1, or
 // (kLaneMma) its elements of the 20 A tiles on or below the diagonal: tile (b, s), s <= 2 b + 1, holds
 // Linv[8 b + lane / 4][4 s + lane % 4].
@@ -400,7 +432,11 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
                     }
                 }
             }
-            if (P > 1) {
+            if (kDmmaReduce && G == 32) {
+                warp_sum_dmma<P>(q);
+#pragma unroll
+                for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * q[p];
+            } else if (P > 1) {
                 group_sum_batch<G, P>(g, q);
 #pragma unroll
                 for (int p = 0; p < P; ++p) out[p] = Pm[0] - 0.5 * q[p];
