@@ -153,6 +153,14 @@ __device__ __forceinline__ double normal_from_bits(uint64_t bits) {
     return 1.4142135623730951 * erfinv_xla(u);
 }
 
+// Newton steps on the MUFU reciprocal seed before the quotient and its residual correction (experiments: 1 or 2).
+// One step suffices: the seed is good to ~2^-20, one step gives 2^-40, and the residual correction of the quotient
+// squares that again.  Measured (profiles/r2/regcap_ab_r2.txt): quantiles bit-identical to the two-step version over
+// 2.1e6 points from 1e-300 to 1 - 1e-16, a config-2 run 95.2 -> 94.1 ms.
+#ifndef NSB_DIV_NEWTON
+#define NSB_DIV_NEWTON 1
+#endif
+
 // The IEEE division of fast_div's fallback as a real call: inlined, the compiler evaluates the ~25-instruction
 // division sequence unconditionally and selects afterwards; out of line it costs one never-taken branch.
 __device__ __noinline__ double slow_div(double a, double b) { return a / b; }
@@ -168,7 +176,7 @@ __device__ __forceinline__ double fast_div(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);
-    r = fma(fma(-b, r, 1.0), r, r);
+    if (NSB_DIV_NEWTON >= 2) r = fma(fma(-b, r, 1.0), r, r);
     double q = a * r;
     q = fma(fma(-b, q, a), r, q);
     return (q - q == 0.0) ? q : slow_div(a, b);  // q - q != 0 for NaN / inf
@@ -183,7 +191,7 @@ __device__ __forceinline__ double fast_div_finite(double a, double b) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(b));
     r = fma(fma(-b, r, 1.0), r, r);
-    r = fma(fma(-b, r, 1.0), r, r);
+    if (NSB_DIV_NEWTON >= 2) r = fma(fma(-b, r, 1.0), r, r);
     const double q = a * r;
     return fma(fma(-b, q, a), r, q);
 }
@@ -216,11 +224,22 @@ __constant__ double kPpndF[8] = {1.0, 5.99832206555887937690E-1, 1.3692988092273
                                  7.86869131145613259100E-4, 1.84631831751005468180E-5, 1.42151175831644588870E-7,
                                  2.04426310338993978564E-15};
 
+// Degree-7 polynomial.  -DNSB_ESTRIN=1: Estrin's scheme (dependent depth 4 FMAs instead of 7, two extra multiplies).
+#ifndef NSB_ESTRIN
+#define NSB_ESTRIN 0
+#endif
 __device__ __forceinline__ double horner8(const double *c, double x) {
+#if NSB_ESTRIN
+    const double x2 = x * x, x4 = x2 * x2;
+    const double p01 = fma(c[1], x, c[0]), p23 = fma(c[3], x, c[2]), p45 = fma(c[5], x, c[4]), p67 = fma(c[7], x, c[6]);
+    const double q0 = fma(p23, x2, p01), q1 = fma(p67, x2, p45);
+    return fma(q1, x4, q0);
+#else
     double r = c[7];
 #pragma unroll
     for (int i = 6; i >= 0; --i) r = fma(r, x, c[i]);
     return r;
+#endif
 }
 
 #ifdef NSB_EXACT_MATH

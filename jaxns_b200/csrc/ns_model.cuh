@@ -366,7 +366,10 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
                 // z_lane = sum_j Linv[lane][j] r_j with the row in registers; two partial sums per
                 // proposal shorten the dependent FMA chain.
                 constexpr int NR = DenseRow<G, DPL, RS>::N;
-                constexpr int NA = NR >= 4 ? 4 : 1;  // partial sums: 8-deep FMA chains instead of 32
+#ifndef NSB_ACC
+#define NSB_ACC 4
+#endif
+                constexpr int NA = NR >= NSB_ACC ? NSB_ACC : 1;  // partial sums: 8-deep FMA chains instead of 32
                 double z[NA][P];
 #pragma unroll
                 for (int a = 0; a < NA; ++a)
@@ -381,6 +384,7 @@ __device__ __forceinline__ void loglik_group(const ModelSmem &sm, const Grp<G> &
                 for (int p = 0; p < P; ++p) {
                     double zz = z[0][p];
                     if (NA == 4) zz = (z[0][p] + z[1][p]) + (z[2][p] + z[3][p]);
+                    if (NA == 8) zz = ((z[0][p] + z[1][p]) + (z[2][p] + z[3][p])) + ((z[4][p] + z[5][p]) + (z[6][p] + z[7][p]));
                     q[p] = zz * zz;
                 }
             } else if (sm.dense_global) {
