@@ -132,10 +132,82 @@ __device__ __noinline__ double erfinv_tail(double x, double w) {
     return (fabs(x) == 1.0) ? x * __longlong_as_double(0x7FF0000000000000ll) : r;
 }
 
+// log(x) for the quantile's tail (0 < x <= 0.075; any normal positive double is handled, everything else goes to the
+// library log).  x = 2^e m, m in [1, 2); c_i = 1 + (2 i + 1) / 128 is the centre of m's 1/64-wide cell, so
+// u = m / c_i - 1 has |u| <= 2^-7 and log1p(u) needs a degree-9 Taylor polynomial: log x = e ln 2 + log c_i + log1p(u).
+// One table load + ~10 dependent FMAs (~115 cycles) where the library routine has ~290 cycles of dependent latency
+// (profiles/r1/microbench_lat.txt); relative error <= 3e-16 for |log x| >= 2.5.  -DNSB_FAST_LOG=0 keeps the library log.
+#ifndef NSB_FAST_LOG
+#define NSB_FAST_LOG 1
+#endif
+__device__ const double2 kLogTab[64] = {  // {1 / c_i, log c_i}
+    {0x1.fc07f01fc07f0p-1, 0x1.fe02a6b106789p-8}, {0x1.f44659e4a4271p-1, 0x1.7b91b07d5b11bp-6},
+    {0x1.ecc07b301ecc0p-1, 0x1.39e87b9febd60p-5}, {0x1.e573ac901e574p-1, 0x1.b42dd711971bfp-5},
+    {0x1.de5d6e3f8868ap-1, 0x1.16536eea37ae1p-4}, {0x1.d77b654b82c34p-1, 0x1.51b073f06183fp-4},
+    {0x1.d0cb58f6ec074p-1, 0x1.8c345d6319b21p-4}, {0x1.ca4b3055ee191p-1, 0x1.c5e548f5bc743p-4},
+    {0x1.c3f8f01c3f8f0p-1, 0x1.fec9131dbeabbp-4}, {0x1.bdd2b899406f7p-1, 0x1.1b72ad52f67a0p-3},
+    {0x1.b7d6c3dda338bp-1, 0x1.371fc201e8f74p-3}, {0x1.b2036406c80d9p-1, 0x1.526e5e3a1b438p-3},
+    {0x1.ac5701ac5701bp-1, 0x1.6d60fe719d21dp-3}, {0x1.a6d01a6d01a6dp-1, 0x1.87fa06520c911p-3},
+    {0x1.a16d3f97a4b02p-1, 0x1.a23bc1fe2b563p-3}, {0x1.9c2d14ee4a102p-1, 0x1.bc286742d8cd6p-3},
+    {0x1.970e4f80cb872p-1, 0x1.d5c216b4fbb91p-3}, {0x1.920fb49d0e229p-1, 0x1.ef0adcbdc5936p-3},
+    {0x1.8d3018d3018d3p-1, 0x1.0402594b4d041p-2}, {0x1.886e5f0abb04ap-1, 0x1.1058bf9ae4ad5p-2},
+    {0x1.83c977ab2beddp-1, 0x1.1c898c16999fbp-2}, {0x1.7f405fd017f40p-1, 0x1.2895a13de86a3p-2},
+    {0x1.7ad2208e0ecc3p-1, 0x1.347dd9a987d55p-2}, {0x1.767dce434a9b1p-1, 0x1.404308686a7e4p-2},
+    {0x1.724287f46debcp-1, 0x1.4be5f957778a1p-2}, {0x1.6e1f76b4337c7p-1, 0x1.5767717455a6cp-2},
+    {0x1.6a13cd1537290p-1, 0x1.62c82f2b9c795p-2}, {0x1.661ec6a5122f9p-1, 0x1.6e08eaa2ba1e4p-2},
+    {0x1.623fa77016240p-1, 0x1.792a55fdd47a2p-2}, {0x1.5e75bb8d015e7p-1, 0x1.842d1da1e8b17p-2},
+    {0x1.5ac056b015ac0p-1, 0x1.8f11e873662c7p-2}, {0x1.571ed3c506b3ap-1, 0x1.99d958117e08bp-2},
+    {0x1.5390948f40febp-1, 0x1.a484090e5bb0ap-2}, {0x1.5015015015015p-1, 0x1.af1293247786bp-2},
+    {0x1.4cab88725af6ep-1, 0x1.b9858969310fbp-2}, {0x1.49539e3b2d067p-1, 0x1.c3dd7a7cdad4dp-2},
+    {0x1.460cbc7f5cf9ap-1, 0x1.ce1af0b85f3ebp-2}, {0x1.42d6625d51f87p-1, 0x1.d83e7258a2f3ep-2},
+    {0x1.3fb013fb013fbp-1, 0x1.e24881a7c6c26p-2}, {0x1.3c995a47babe7p-1, 0x1.ec399d2468cc0p-2},
+    {0x1.3991c2c187f63p-1, 0x1.f6123fa7028acp-2}, {0x1.3698df3de0748p-1, 0x1.ffd2e0857f498p-2},
+    {0x1.33ae45b57bcb2p-1, 0x1.04bdf9da926d2p-1}, {0x1.30d190130d190p-1, 0x1.0986f4f573521p-1},
+    {0x1.2e025c04b8097p-1, 0x1.0e44985d1cc8cp-1}, {0x1.2b404ad012b40p-1, 0x1.12f719593efbcp-1},
+    {0x1.288b01288b013p-1, 0x1.179eabbd899a1p-1}, {0x1.25e22708092f1p-1, 0x1.1c3b81f713c25p-1},
+    {0x1.23456789abcdfp-1, 0x1.20cdcd192ab6ep-1}, {0x1.20b470c67c0d9p-1, 0x1.2555bce98f7cbp-1},
+    {0x1.1e2ef3b3fb874p-1, 0x1.29d37fec2b08bp-1}, {0x1.1bb4a4046ed29p-1, 0x1.2e47436e40268p-1},
+    {0x1.19453808ca29cp-1, 0x1.32b1339121d71p-1}, {0x1.16e0689427379p-1, 0x1.37117b54747b6p-1},
+    {0x1.1485f0e0acd3bp-1, 0x1.3b68449fffc23p-1}, {0x1.12358e75d3033p-1, 0x1.3fb5b84d16f42p-1},
+    {0x1.0fef010fef011p-1, 0x1.43f9fe2f9ce67p-1}, {0x1.0db20a88f4696p-1, 0x1.48353d1ea88dfp-1},
+    {0x1.0b7e6ec259dc8p-1, 0x1.4c679afccee3ap-1}, {0x1.0953f39010954p-1, 0x1.50913cc01686bp-1},
+    {0x1.073260a47f7c6p-1, 0x1.54b2467999498p-1}, {0x1.05197f7d73404p-1, 0x1.58cadb5cd7989p-1},
+    {0x1.03091b51f5e1ap-1, 0x1.5cdb1dc6c1765p-1}, {0x1.0101010101010p-1, 0x1.60e32f44788d9p-1},
+};
+
+__device__ __forceinline__ double tail_log(double x) {
+#if defined(NSB_EXACT_MATH) || !NSB_FAST_LOG
+    return log(x);
+#else
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    if ((unsigned) (hi - 0x00100000) >= 0x7fe00000u) return log(x);  // zero, denormal, negative, inf, NaN
+    const int e = (hi >> 20) - 1023;
+    const double2 tc = __ldg(&kLogTab[(hi >> 14) & 63]);
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
+    const double u = fma(m, tc.x, -1.0);
+    // log1p(u) = u + u^2 (-1/2 + u/3 - u^2/4 + u^3/5 - u^4/6 + u^5/7 - u^6/8 + u^7/9), Estrin
+    const double u2 = u * u, u4 = u2 * u2;
+    const double p01 = fma(u, 1.0 / 3.0, -0.5), p23 = fma(u, 0.2, -0.25), p45 = fma(u, 1.0 / 7.0, -1.0 / 6.0),
+                 p67 = fma(u, 1.0 / 9.0, -0.125);
+    const double q = fma(fma(p67, u2, p45), u4, fma(p23, u2, p01));
+    const double r = fma(u2, q, u);
+    return fma((double) e, 0.6931471805599453094, tc.y + r);
+#endif
+}
+
+// The same log inside erfinv (one per normal deviate of the chain-stream generator).  -DNSB_FAST_LOG_GEN=1.
+#ifndef NSB_FAST_LOG_GEN
+#define NSB_FAST_LOG_GEN 1
+#endif
+
 __device__ __forceinline__ double erfinv_xla(double x) {
     // w = -log1p(-x*x).  Evaluated as -log(1 - x*x): w only enters additively (w - 3.125, sqrt(w) - c), so the
     // absolute error of the plain log (~1e-16) is what matters and libdevice's log is ~4x cheaper than log1p.
+#if NSB_FAST_LOG_GEN
+    const double w0 = -tail_log(fma(x, -x, 1.0));
+#else
     const double w0 = -log(fma(x, -x, 1.0));
+#endif
     if (w0 < 6.25) {
         const double w = w0 - 3.125;
         double p = kErfInvA[0];
@@ -310,7 +382,7 @@ __device__ __forceinline__ double ndtri(double p, unsigned mask) {
         const double kInf = __longlong_as_double(0x7FF0000000000000ll);
         double pp = (q < 0.0) ? p : 1.0 - p;
         pp = tail ? pp : 0.05;  // keep the non-tail lanes on the fast paths of log / sqrt
-        const double rr = sqrt(-log(pp));
+        const double rr = sqrt(-tail_log(pp));
         const double a = rr - 1.6, b = rr - 5.0;
         double v = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
         if (__any_sync(mask, rr > 5.0)) {  // far tail (p < 1.4e-11): rare, warp-uniform
@@ -359,7 +431,7 @@ __device__ __forceinline__ void ndtri_batch(const double (&p)[P], unsigned mask,
         for (int i = 0; i < P; ++i) {
             double pp = (q[i] < 0.0) ? p[i] : 1.0 - p[i];
             pp = tail[i] ? pp : 0.05;  // keep the non-tail lanes on the fast paths of log / sqrt
-            rr[i] = sqrt(-log(pp));
+            rr[i] = sqrt(-tail_log(pp));
         }
 #pragma unroll
         for (int i = 0; i < P; ++i) {
@@ -452,7 +524,7 @@ __device__ __forceinline__ void ndtri_multi(const double (&p)[K], double (&x)[K]
         const double q = pv - 0.5;
         double pp = (q < 0.0) ? pv : 1.0 - pv;
         pp = tail ? pp : 0.05;  // idle lanes stay on the fast paths of log / sqrt
-        const double rr = sqrt(-log(pp));
+        const double rr = sqrt(-tail_log(pp));
         const double a = rr - 1.6, b = rr - 5.0;
         double v = fast_div_finite(horner8(kPpndC, a), horner8(kPpndD, a));
         if (__any_sync(0xFFFFFFFFu, rr > 5.0)) {  // far tail (p < 1.4e-11): rare, warp-uniform
