@@ -360,6 +360,15 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
             int ne = 0;  // proposals generated so far in this slice
             double logL_acc = 0.0;
             double u_ahead = uq[0];
+#ifndef NSB_U_AHEAD
+#define NSB_U_AHEAD 0
+#endif
+            // P > 1 (-DNSB_U_AHEAD=1): the round's P uniforms are loaded one round ahead, like u_ahead for P = 1
+            double u_pre[P];
+            if (NSB_U_AHEAD && P > 1) {
+#pragma unroll
+                for (int p = 0; p < P; ++p) u_pre[p] = uq[p < kPre ? p : kPre - 1];
+            }
             if (TEAM) {
                 for (;;) {
                     double ts[W];
@@ -429,7 +438,7 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     if (P == 1 && n < kPre) {
                         uu = u_ahead;  // loaded while the previous proposal was being evaluated
                     } else if (n < kPre) {
-                        uu = uq[n];
+                        uu = (NSB_U_AHEAD && P > 1) ? u_pre[p] : uq[n];
                     } else {
                         const Key t_key = split_child(run_key, 1);
                         run_key = split_child(run_key, 0);
@@ -443,6 +452,10 @@ __device__ __forceinline__ void slice_chains_body(const SliceArgs &a, double *sm
                     for (int s = 0; s < DPL; ++s) x[p][s] = fma(t, d[s], U0[s]);
                 }
                 if (P == 1) u_ahead = uq[min(ne + 1, kPre - 1)];  // next proposal's uniform: hide the smem latency
+                if (NSB_U_AHEAD && P > 1) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) u_pre[p] = uq[min(ne + P + p, kPre - 1)];
+                }
                 NSB_TICK(3)  // proposal generation
 #ifdef NSB_PROFILE
                 {
