@@ -391,9 +391,10 @@ def run_native(args, emit=print):
             pass
         roofline = {"bound": "fp64", "achieved": achieved, "peak": tf.value, "unit": "TFLOP/s",
                     "frac": achieved / tf.value if tf.value else None,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r2/): the
-                    # pre-generated chain streams (directions, uniforms, keys), read once; algorithmic bytes ~0.4 MB
-                    "traffic": 86.8e6,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full,
+                    # profiles/r2/slice_r2_final.txt: 84.35 MB + 3.16 MB): the pre-generated chain streams (directions,
+                    # uniforms, keys), read once; algorithmic bytes ~0.4 MB
+                    "traffic": 87.5e6,
                     "kernel": "k_slice_chains<32,1,P> (fused slice chains)",
                     "kernel_share_of_step": slice_ms / tot_ms,
                     "peak_source": "FP64 FMA microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 "
