@@ -382,3 +382,30 @@ def test_newton_cg_and_m_step_cpu():
         mu = model(params=params).transform_parametrised(torch.full((1,), 0.5, dtype=torch.float64))["mu"]
     assert abs(float(mu) - 2.0) < 1e-6
     assert abs(log_Z + 0.5 * np.log(2 * np.pi)) < 1e-10
+
+
+def test_bench_clock_sampler_reports_only_the_timed_region():
+    """bench.py starts nvidia-smi before the warm-up runs and reports the samples taken after mark()."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cs = bench.ClockSampler(0)
+
+    class _Proc:
+        def terminate(self):
+            pass
+
+        def wait(self, timeout=None):
+            return 0
+
+    cs.proc = _Proc()
+    row = lambda mhz, cap: ["0", str(mhz), "1965", "700", "x", "Not Active", "Not Active", "Not Active", cap]  # noqa: E731
+    cs.rows = [row(300, "Not Active"), row(1200, "Not Active")]  # idle / warm-up samples
+    cs.mark()
+    cs.rows += [row(1965, "Not Active"), row(1950, "Active"), row(1965, "Not Active")]
+    out = cs.stop()
+    assert out["samples"] == 3 and out["sm_mhz"] == 1965.0 and out["sm_max_mhz"] == 1965.0
+    assert out["reasons"] == ["sw_power_cap"]
+    empty = bench.ClockSampler(0)
+    assert empty.stop()["reasons"] == ["nvidia-smi unavailable"]
